@@ -1,0 +1,427 @@
+"""Closed-form CPU restatements of every cv2/numpy call on the hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Each function cites the
+reference call site it restates (paths are into /root/reference) and is
+checked against the real ``cv2`` call in tests/test_oracle_vs_cv2.py.
+Integer ops are written with numpy integer arithmetic only, so they are an
+independent statement of what OpenCV computes, not a wrapper around it.  The
+one exception is the float32 DCT (``cv2.dct``/``cv2.idct``, Intel IPP inside
+opencv-python): that algorithm is closed source, so ``block_dct_quantise``
+calls cv2 itself -- batched through ``cv2.DCT_ROWS``, which
+tests/test_oracle_vs_cv2.py shows is bit-identical to the per-block 2-D call
+the reference makes.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ----------------------------------------------------------------------------
+# colour conversions
+# ----------------------------------------------------------------------------
+
+def bgr2gray(bgr: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(frame, COLOR_BGR2GRAY) on uint8 (frame_differencing.py:75,92;
+    motion_compression_opt.py:60,71,149,181).  15-bit fixed point, round half up."""
+    b = bgr[..., 0].astype(np.int32)
+    g = bgr[..., 1].astype(np.int32)
+    r = bgr[..., 2].astype(np.int32)
+    return ((3735 * b + 19235 * g + 9798 * r + 16384) >> 15).astype(np.uint8)
+
+
+def _sat_u8(x: np.ndarray) -> np.ndarray:
+    return np.clip(x, 0, 255).astype(np.uint8)
+
+
+def bgr2ycrcb(bgr: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(frame, COLOR_BGR2YCrCb) on uint8 (frame_differencing.py:115;
+    motion_compression_opt.py:152).  14-bit fixed point."""
+    b = bgr[..., 0].astype(np.int32)
+    g = bgr[..., 1].astype(np.int32)
+    r = bgr[..., 2].astype(np.int32)
+    y = (1868 * b + 9617 * g + 4899 * r + 8192) >> 14
+    half = 128 << 14
+    cr = ((r - y) * 11682 + half + 8192) >> 14
+    cb = ((b - y) * 9241 + half + 8192) >> 14
+    return np.stack([_sat_u8(y), _sat_u8(cr), _sat_u8(cb)], axis=-1)
+
+
+def ycrcb2bgr(ycrcb: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(frame, COLOR_YCrCb2BGR) on uint8 (frame_differencing.py:130;
+    motion_compression_opt.py:171)."""
+    y = ycrcb[..., 0].astype(np.int32)
+    cr = ycrcb[..., 1].astype(np.int32) - 128
+    cb = ycrcb[..., 2].astype(np.int32) - 128
+    b = y + ((29049 * cb + 8192) >> 14)
+    g = y + ((-5636 * cb - 11698 * cr + 8192) >> 14)
+    r = y + ((22987 * cr + 8192) >> 14)
+    return np.stack([_sat_u8(b), _sat_u8(g), _sat_u8(r)], axis=-1)
+
+
+# ----------------------------------------------------------------------------
+# mask front end
+# ----------------------------------------------------------------------------
+
+def _reflect101_pad(img: np.ndarray, p: int) -> np.ndarray:
+    return np.pad(img, p, mode="reflect")       # numpy 'reflect' == BORDER_REFLECT_101
+
+
+def gaussian_blur5(gray: np.ndarray) -> np.ndarray:
+    """cv2.GaussianBlur(gray, (5, 5), 0) on uint8 (frame_differencing.py:93).
+    sigma=0, ksize 5 selects the fixed binomial kernel [1,4,6,4,1]/16; OpenCV
+    evaluates it in 8.8 fixed point, which reduces to (sum + 128) >> 8 over the
+    separable 5x5 integer kernel with BORDER_REFLECT_101."""
+    h, w = gray.shape
+    if h < 3 or w < 3:
+        # reflect-101 needs at least 3 samples for a 2-pixel border; cv2 handles
+        # tiny images by repeated reflection -- do the same by index arithmetic.
+        return _gaussian_blur5_small(gray)
+    k = np.array([1, 4, 6, 4, 1], np.int32)
+    p = _reflect101_pad(gray.astype(np.int32), 2)
+    hor = sum(k[i] * p[:, i:i + w] for i in range(5))
+    ver = sum(k[i] * hor[i:i + h, :] for i in range(5))
+    return ((ver + 128) >> 8).astype(np.uint8)
+
+
+def _reflect101_index(i: int, n: int) -> int:
+    if n == 1:
+        return 0
+    period = 2 * (n - 1)
+    i %= period
+    return i if i < n else period - i
+
+
+def _gaussian_blur5_small(gray: np.ndarray) -> np.ndarray:
+    h, w = gray.shape
+    k = (1, 4, 6, 4, 1)
+    g = gray.astype(np.int64)
+    out = np.zeros((h, w), np.int64)
+    for y in range(h):
+        for x in range(w):
+            s = 0
+            for j in range(5):
+                yy = _reflect101_index(y + j - 2, h)
+                for i in range(5):
+                    xx = _reflect101_index(x + i - 2, w)
+                    s += k[j] * k[i] * g[yy, xx]
+            out[y, x] = (s + 128) >> 8
+    return out.astype(np.uint8)
+
+
+def absdiff(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """cv2.absdiff on uint8 (frame_differencing.py:96)."""
+    return np.abs(a.astype(np.int16) - b.astype(np.int16)).astype(np.uint8)
+
+
+def threshold_floor(thresh: float) -> int:
+    """cv2.threshold on uint8 floors the float threshold: 0.5 -> 0, 25 -> 25."""
+    return int(np.floor(thresh))
+
+
+def threshold_binary(diff: np.ndarray, thresh: float, maxval: int = 255) -> np.ndarray:
+    """cv2.threshold(diff, thresh, 255, THRESH_BINARY) on uint8 (frame_differencing.py:97)."""
+    return np.where(diff.astype(np.int32) > threshold_floor(thresh), maxval, 0).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------
+# morphology
+# ----------------------------------------------------------------------------
+
+def structuring_rect(k: int) -> np.ndarray:
+    """np.ones((k, k), np.uint8) (frame_differencing.py:80)."""
+    return np.ones((k, k), np.uint8)
+
+
+def structuring_ellipse(k: int) -> np.ndarray:
+    """cv2.getStructuringElement(MORPH_ELLIPSE, (k, k)) (motion_compression_opt.py:62),
+    restating OpenCV >= 4.x morph.dispatch.cpp: row i spans |dx| <= rint(c*sqrt(r^2-dy^2)/r)
+    (here r = c since the element is square)."""
+    r = k // 2
+    c = k // 2
+    inv_r2 = 1.0 / (r * r) if r else 0.0
+    out = np.zeros((k, k), np.uint8)
+    for i in range(k):
+        dy = i - r
+        if abs(dy) <= r:
+            dx = int(np.rint(c * np.sqrt((r * r - dy * dy) * inv_r2)))
+            j1, j2 = max(c - dx, 0), min(c + dx + 1, k)
+            out[i, j1:j2] = 1
+    return out
+
+
+def _morph(img: np.ndarray, kernel: np.ndarray, is_dilate: bool) -> np.ndarray:
+    kh, kw = kernel.shape
+    ay, ax = kh // 2, kw // 2                      # default anchor (-1,-1) -> centre = k//2
+    h, w = img.shape
+    pad_val = 0 if is_dilate else 255               # morphologyDefaultBorderValue: ignored pixels
+    top, left = ay, ax
+    bottom, right = kh - 1 - ay, kw - 1 - ax
+    p = np.pad(img, ((top, bottom), (left, right)), mode="constant", constant_values=pad_val)
+    out = np.full((h, w), 0 if is_dilate else 255, np.uint8)
+    for j in range(kh):
+        for i in range(kw):
+            if kernel[j, i]:
+                win = p[j:j + h, i:i + w]
+                out = np.maximum(out, win) if is_dilate else np.minimum(out, win)
+    return out
+
+
+def dilate(img: np.ndarray, kernel: np.ndarray) -> np.ndarray:
+    """cv2.dilate(mask, kernel, iterations=1) (frame_differencing.py:106)."""
+    return _morph(img, kernel, True)
+
+
+def erode(img: np.ndarray, kernel: np.ndarray) -> np.ndarray:
+    return _morph(img, kernel, False)
+
+
+def morph_close(img: np.ndarray, kernel: np.ndarray) -> np.ndarray:
+    """cv2.morphologyEx(mask, MORPH_CLOSE, kernel) = erode(dilate(.)) (motion_compression_opt.py:89)."""
+    return erode(dilate(img, kernel), kernel)
+
+
+def morph_open(img: np.ndarray, kernel: np.ndarray) -> np.ndarray:
+    """cv2.morphologyEx(mask, MORPH_OPEN, kernel) = dilate(erode(.)) (motion_compression_opt.py:90)."""
+    return dilate(erode(img, kernel), kernel)
+
+
+# ----------------------------------------------------------------------------
+# temporal smoothing
+# ----------------------------------------------------------------------------
+
+def _fma32(a: np.ndarray, b: np.float32, c: np.ndarray) -> np.ndarray:
+    # a*b is exact in float64 for a <= 255 and b float32; one rounding to float32.
+    return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)
+
+
+def add_weighted(a: np.ndarray, alpha: float, b: np.ndarray, beta: float) -> np.ndarray:
+    """cv2.addWeighted(a, alpha, b, beta, 0) on uint8 (frame_differencing.py:107):
+    float32 arithmetic, t = b*beta rounded, then fma(a, alpha, t), round half to even, saturate."""
+    al, be = np.float32(alpha), np.float32(beta)
+    t = (b.astype(np.float32) * be).astype(np.float32)
+    s = _fma32(a.astype(np.float32), al, t)
+    return _sat_u8(np.rint(s).astype(np.int64))
+
+
+def window_min_counts(alpha_fraction: float, window_size: int) -> list[int]:
+    """For L = 1..K, the smallest count c of 255-valued masks with
+    ``c*255 >= alpha_fraction * L * 255`` evaluated exactly as the reference
+    writes it in Python floats (motion_compression_opt.py:85-86)."""
+    out = []
+    for L in range(1, window_size + 1):
+        rhs = alpha_fraction * L * 255
+        c = 0
+        while not (c * 255 >= rhs):
+            c += 1
+            if c > L:                       # vote can never pass
+                break
+        out.append(c)
+    return out
+
+
+def window_vote(masks: list[np.ndarray], alpha_fraction: float) -> np.ndarray:
+    """np.sum over the deque + compare (motion_compression_opt.py:85-86); ``masks`` is the
+    current deque content (at most window_size entries of 0/255 uint8)."""
+    cumulative = np.sum(np.array(masks), axis=0)
+    return (cumulative >= (alpha_fraction * len(masks) * 255)).astype(np.uint8) * 255
+
+
+# ----------------------------------------------------------------------------
+# contour filter (frame_differencing.py:100-104)
+# ----------------------------------------------------------------------------
+
+def contour_filter(mask: np.ndarray, min_area: float) -> np.ndarray:
+    """findContours(RETR_EXTERNAL) -> keep contourArea > min_area -> drawContours(FILLED),
+    restated without contour tracing:
+
+    O = background pixels 4-connected to the outside of the image;  F = not O
+    (foreground plus enclosed holes);  label F with 8-connectivity;  for each
+    label, twice the polygon area through pixel centres is 2*Q4 + Q3, where
+    Q4/Q3 count the 2x2 windows with 4/3 pixels of that label;  keep labels
+    with area > min_area.
+    """
+    from scipy import ndimage
+    fg = mask != 0
+    h, w = fg.shape
+    bg = np.pad(~fg, 1, mode="constant", constant_values=True)
+    lab4, _ = ndimage.label(bg, structure=[[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+    outside = lab4 == lab4[0, 0]
+    filled = ~outside[1:-1, 1:-1]
+    lab8, n = ndimage.label(filled, structure=np.ones((3, 3), int))
+    if n == 0:
+        return np.zeros((h, w), np.uint8)
+    f = filled.astype(np.int32)
+    cnt = f[:-1, :-1] + f[:-1, 1:] + f[1:, :-1] + f[1:, 1:]
+    # a 2x2 window with >=3 pixels of F lies in exactly one 8-component; take its label as the max.
+    lab_win = np.maximum(np.maximum(lab8[:-1, :-1], lab8[:-1, 1:]), np.maximum(lab8[1:, :-1], lab8[1:, 1:]))
+    twice_area = (np.bincount(lab_win[cnt == 4], minlength=n + 1) * 2
+                  + np.bincount(lab_win[cnt == 3], minlength=n + 1))
+    keep = twice_area > 2 * min_area
+    keep[0] = False
+    return np.where(keep[lab8], 255, 0).astype(np.uint8)
+
+
+def contour_filter_cv2(mask: np.ndarray, min_area: float) -> np.ndarray:
+    """The literal reference lines (frame_differencing.py:100-104)."""
+    import cv2
+    contours, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    out = np.zeros_like(mask)
+    for c in contours:
+        if cv2.contourArea(c) > min_area:
+            cv2.drawContours(out, [c], -1, 255, thickness=cv2.FILLED)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# block DCT degrade (frame_differencing.py:117-127; motion_compression_opt.py:156-183)
+# ----------------------------------------------------------------------------
+
+def block_all_zero(mask: np.ndarray, bs: int, full_blocks_only: bool = False) -> np.ndarray:
+    """``mask[y:y+bs, x:x+bs].mean() == 0`` per block (frame_differencing.py:120).  Returns a bool
+    array [ceil(H/bs), ceil(W/bs)]; with ``full_blocks_only`` clipped edge blocks are False
+    (motion_compression_opt.py:159 skips them)."""
+    h, w = mask.shape
+    nby, nbx = -(-h // bs), -(-w // bs)
+    p = np.zeros((nby * bs, nbx * bs), bool)
+    p[:h, :w] = mask != 0
+    static = ~p.reshape(nby, bs, nbx, bs).any(axis=(1, 3))
+    if full_blocks_only:
+        if h % bs:
+            static[-1, :] = False
+        if w % bs:
+            static[:, -1] = False
+    return static
+
+
+def _dct_rows(x: np.ndarray, inverse: bool) -> np.ndarray:
+    import cv2
+    flags = cv2.DCT_ROWS | (cv2.DCT_INVERSE if inverse else 0)
+    return cv2.dct(np.ascontiguousarray(x, np.float32), flags=flags)
+
+
+_BATCH_OK: dict = {}
+
+
+def _batched_rows_is_exact(bs: int, inverse: bool) -> bool:
+    """Does rows-pass + columns-pass through cv2.DCT_ROWS reproduce the per-block 2-D call bit for
+    bit on THIS host?  (True for 4x4 here; False for 8x8, where IPP has a dedicated 2-D routine.)
+    Decided by a one-off self-check so the oracle never silently drifts from the literal call."""
+    import cv2
+    key = (bs, inverse)
+    if key not in _BATCH_OK:
+        rng = np.random.default_rng(12345)
+        blocks = rng.integers(-128, 128, (256, bs, bs)).astype(np.float32)
+        if inverse:
+            blocks = (np.round(blocks / 3) * 100).astype(np.float32)
+        lit = np.stack([(cv2.idct if inverse else cv2.dct)(b) for b in blocks])
+        _BATCH_OK[key] = bool(np.array_equal(lit, _dct2_blocks_batched(blocks, inverse)))
+    return _BATCH_OK[key]
+
+
+def _dct2_blocks_batched(blocks: np.ndarray, inverse: bool) -> np.ndarray:
+    n, bh, bw = blocks.shape
+    r = _dct_rows(blocks.reshape(n * bh, bw), inverse).reshape(n, bh, bw)
+    rt = np.ascontiguousarray(r.transpose(0, 2, 1)).reshape(n * bw, bh)
+    c = _dct_rows(rt, inverse).reshape(n, bw, bh).transpose(0, 2, 1)
+    return np.ascontiguousarray(c)
+
+
+def dct2_blocks(blocks: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """2-D DCT of a stack [N, bs, bs] float32, bit-identical to calling cv2.dct / cv2.idct on each
+    block as the reference does (frame_differencing.py:122,124).  Uses one batched DCT_ROWS call per
+    pass where that is verified to be bit-identical on this host, else the literal per-block calls."""
+    import cv2
+    blocks = np.ascontiguousarray(blocks, np.float32)
+    n, bh, bw = blocks.shape
+    if n == 0:
+        return blocks.copy()
+    if bh == bw and _batched_rows_is_exact(bh, inverse):
+        return _dct2_blocks_batched(blocks, inverse)
+    f = cv2.idct if inverse else cv2.dct
+    return np.stack([f(b) for b in blocks])
+
+
+def quantise_plane_blocks(plane: np.ndarray, static: np.ndarray, bs: int, q: float) -> np.ndarray:
+    """For every full bs x bs block flagged static:
+    ``clip(idct(round(dct(block - 128) / q) * q) + 128, 0, 255)`` stored to uint8 (truncation),
+    frame_differencing.py:121-125.  Clipped edge blocks are handled by the callers."""
+    h, w = plane.shape
+    nby, nbx = h // bs, w // bs
+    out = plane.copy()
+    st = static[:nby, :nbx]
+    if not st.any():
+        return out
+    view = plane[:nby * bs, :nbx * bs].reshape(nby, bs, nbx, bs).transpose(0, 2, 1, 3)
+    blocks = view[st].astype(np.float32) - np.float32(128)
+    d = dct2_blocks(blocks)
+    qd = np.round(d / q) * q                      # numpy: float32 / python scalar stays float32
+    r = dct2_blocks(qd.astype(np.float32), inverse=True) + np.float32(128)
+    res = np.clip(r, 0, 255).astype(np.uint8)       # assignment into a uint8 array truncates
+    oview = out[:nby * bs, :nbx * bs].reshape(nby, bs, nbx, bs).transpose(0, 2, 1, 3)
+    oview[st] = res                                  # writes through: oview is a view of ``out``
+    return out
+
+
+def tie_blocks(plane: np.ndarray, static: np.ndarray, bs: int, q: float, eps: float = 2e-3) -> np.ndarray:
+    """Blocks (bool [H//bs, W//bs]) having a DCT coefficient within ``eps`` of an exact quantiser tie
+    (d/q = n + 1/2).  IPP's float32 rounding decides such ties, so no other float32 implementation
+    can be expected to agree on them."""
+    h, w = plane.shape
+    nby, nbx = h // bs, w // bs
+    view = plane[:nby * bs, :nbx * bs].reshape(nby, bs, nbx, bs).transpose(0, 2, 1, 3)
+    blocks = view.reshape(-1, bs, bs).astype(np.float64) - 128.0
+    from scipy.fft import dctn
+    d = dctn(blocks, axes=(1, 2), norm="ortho")
+    frac = np.abs(d / q - np.floor(d / q) - 0.5)
+    tie = (frac < eps / q).any(axis=(1, 2)).reshape(nby, nbx)
+    return tie & static[:nby, :nbx]
+
+
+def degrade_fd(bgr: np.ndarray, acc_mask: np.ndarray, bs: int, q: float) -> np.ndarray:
+    """frame_differencing.py:115-130 on one frame: BGR->YCrCb, static blocks (mask block all zero)
+    get DCT-quantised luma and neutral chroma, YCrCb->BGR.  Requires H, W multiples of ``bs`` or
+    even-sized clipped edge blocks (cv2.dct rejects odd sizes, as it does in the reference)."""
+    import cv2
+    ycc = bgr2ycrcb(bgr)
+    h, w = acc_mask.shape
+    static = block_all_zero(acc_mask, bs)
+    y = quantise_plane_blocks(ycc[..., 0], static, bs, q)
+    cr, cb = ycc[..., 1].copy(), ycc[..., 2].copy()
+    nby, nbx = static.shape
+    st_px = np.repeat(np.repeat(static, bs, axis=0), bs, axis=1)[:h, :w]
+    cr[st_px] = 128
+    cb[st_px] = 128
+    # clipped edge blocks: literal per-block path, exactly as the reference slices them
+    for by in range(nby):
+        for bx in range(nbx):
+            y0, x0 = by * bs, bx * bs
+            full = (y0 + bs <= h) and (x0 + bs <= w)
+            if full or not static[by, bx]:
+                continue
+            blk = ycc[y0:y0 + bs, x0:x0 + bs, 0]
+            d = cv2.dct(blk.astype(np.float32) - 128)
+            qd = np.round(d / q) * q
+            r = cv2.idct(qd) + 128
+            y[y0:y0 + bs, x0:x0 + bs] = np.clip(r, 0, 255)
+    return ycrcb2bgr(np.stack([y, cr, cb], axis=-1))
+
+
+def degrade_mco(bgr: np.ndarray, mask: np.ndarray, q: float = 100.0) -> np.ndarray:
+    """motion_compression_opt.py:152-183 on one frame: 8x8 full blocks whose mask block is all zero get
+    Y, Cr and Cb DCT-quantised, then after YCrCb->BGR the same blocks are re-grayed."""
+    bs = 8
+    ycc = bgr2ycrcb(bgr)
+    static = block_all_zero(mask, bs, full_blocks_only=True)
+    planes = [quantise_plane_blocks(ycc[..., c], static, bs, q) for c in range(3)]
+    out = ycrcb2bgr(np.stack(planes, axis=-1))
+    h, w = mask.shape
+    st_px = np.repeat(np.repeat(static, bs, axis=0), bs, axis=1)[:h, :w]
+    g = bgr2gray(out)
+    out[st_px] = g[st_px][:, None]
+    return out
+
+
+def overlay_paint(bgr: np.ndarray, acc_mask: np.ndarray) -> np.ndarray:
+    """``ov = frame.copy(); ov[acc > 127] = [0, 0, 255]`` (frame_differencing.py:110-111)."""
+    ov = bgr.copy()
+    ov[acc_mask > 127] = (0, 0, 255)
+    return ov

@@ -1,0 +1,27 @@
+"""Helpers shared by the golden-fixture tests (CPU oracle tests and GPU parity tests)."""
+import ast
+import hashlib
+import os
+
+import numpy as np
+
+from dynamic_video_compression_surveillance_b200.synth import make_clip
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FD_FIXTURES = ["fd_default_96x128", "fd_main_cfg_64x96", "fd_minarea50_noise_72x112"]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def unpack(bits, w):
+    return (np.unpackbits(bits, axis=-1)[..., :w] * 255).astype(np.uint8)
+
+
+def load_fd(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    h, w, n, seed, noise = (int(v) for v in z["recipe"])
+    kw = ast.literal_eval(str(z["kwargs"]))
+    frames = make_clip((h, w), n, seed=seed, temporal_noise=bool(noise)).frames()
+    return z, frames, kw, (h, w, n)

@@ -1,0 +1,188 @@
+"""Pins oracle/stage_ops.py (numpy restatements) to the real cv2 calls the reference makes."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import stage_ops as so
+
+SHAPES = [(1, 1), (1, 7), (5, 1), (2, 2), (3, 5), (17, 33), (48, 64), (101, 67)]
+
+
+def _rng(seed=0):
+    return np.random.default_rng(seed)
+
+
+def _cv2_blur5(img):
+    """cv2 4.13.0's multi-threaded fixed-point GaussianBlur races on tiny images (height ~ number of
+    threads): row 1 comes back with garbage in some calls.  Single-threaded it is deterministic."""
+    n = cv2.getNumThreads()
+    cv2.setNumThreads(1)
+    try:
+        return cv2.GaussianBlur(img, (5, 5), 0)
+    finally:
+        cv2.setNumThreads(n)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_bgr2gray(shape):
+    img = _rng(1).integers(0, 256, shape + (3,), dtype=np.uint8)
+    assert np.array_equal(so.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+
+
+def test_bgr2gray_exhaustive_slices():
+    # all 2^24 colours is 16.7 M pixels: cheap enough
+    v = np.arange(256, dtype=np.uint8)
+    b, g, r = np.meshgrid(v, v, v, indexing="ij")
+    img = np.stack([b, g, r], -1).reshape(4096, 4096, 3)
+    assert np.array_equal(so.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    assert np.array_equal(so.bgr2ycrcb(img), cv2.cvtColor(img, cv2.COLOR_BGR2YCrCb))
+    assert np.array_equal(so.ycrcb2bgr(img), cv2.cvtColor(img, cv2.COLOR_YCrCb2BGR))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_blur5(shape):
+    img = _rng(2).integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(so.gaussian_blur5(img), _cv2_blur5(img))
+
+
+def test_blur5_extremes():
+    for val in (0, 255):
+        img = np.full((9, 11), val, np.uint8)
+        assert np.array_equal(so.gaussian_blur5(img), _cv2_blur5(img))
+
+
+def test_absdiff_threshold():
+    a = _rng(3).integers(0, 256, (64, 80), dtype=np.uint8)
+    b = _rng(4).integers(0, 256, (64, 80), dtype=np.uint8)
+    d = so.absdiff(a, b)
+    assert np.array_equal(d, cv2.absdiff(a, b))
+    for t in (0.5, 0.0, 1.0, 1.5, 25, 254.9, 255):
+        _, m = cv2.threshold(d, t, 255, cv2.THRESH_BINARY)
+        assert np.array_equal(so.threshold_binary(d, t), m), t
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 9, 10, 15])
+def test_structuring_ellipse(k):
+    assert np.array_equal(so.structuring_ellipse(k), cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (k, k)))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (17, 33), (48, 70)])
+@pytest.mark.parametrize("kind,k", [("rect", 1), ("rect", 2), ("rect", 3), ("rect", 7), ("rect", 10), ("rect", 15),
+                                    ("ell", 2), ("ell", 3), ("ell", 5), ("ell", 9)])
+def test_morphology(shape, kind, k):
+    rng = _rng(5)
+    kernel = so.structuring_rect(k) if kind == "rect" else so.structuring_ellipse(k)
+    for density in (0.02, 0.5, 0.97):
+        m = (rng.random(shape) < density).astype(np.uint8) * 255
+        assert np.array_equal(so.dilate(m, kernel), cv2.dilate(m, kernel, iterations=1))
+        assert np.array_equal(so.erode(m, kernel), cv2.erode(m, kernel, iterations=1))
+        assert np.array_equal(so.morph_close(m, kernel), cv2.morphologyEx(m, cv2.MORPH_CLOSE, kernel))
+        assert np.array_equal(so.morph_open(m, kernel), cv2.morphologyEx(m, cv2.MORPH_OPEN, kernel))
+    g = rng.integers(0, 256, shape, dtype=np.uint8)        # grey-level input too
+    assert np.array_equal(so.dilate(g, kernel), cv2.dilate(g, kernel))
+    assert np.array_equal(so.erode(g, kernel), cv2.erode(g, kernel))
+
+
+@pytest.mark.parametrize("rf", [0.5, 0.3, 0.1, 0.25, 0.7, 0.9, 0.05, 0.95, 1 / 3])
+def test_add_weighted_exhaustive(rf):
+    a, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    ref = cv2.addWeighted(a, rf, b, 1 - rf, 0)
+    assert np.array_equal(so.add_weighted(a, rf, b, 1 - rf), ref)
+
+
+def test_window_vote_and_min_counts():
+    rng = _rng(6)
+    for alpha, K in ((0.2, 30), (0.2, 5), (0.5, 4), (0.34, 7), (1.0, 3), (0.0, 3)):
+        mc = so.window_min_counts(alpha, K)
+        masks = []
+        for t in range(2 * K):
+            masks.append((rng.random((12, 16)) < 0.3).astype(np.uint8) * 255)
+            win = masks[-K:]
+            ref = so.window_vote(win, alpha)
+            cnt = np.sum(np.array(win) != 0, axis=0)
+            got = np.where(cnt >= mc[len(win) - 1], 255, 0).astype(np.uint8)
+            assert np.array_equal(got, ref), (alpha, K, t)
+
+
+def _random_blob_mask(rng, shape, n):
+    m = np.zeros(shape, np.uint8)
+    h, w = shape
+    for _ in range(n):
+        kind = rng.integers(0, 3)
+        cx, cy = int(rng.integers(0, w)), int(rng.integers(0, h))
+        if kind == 0:
+            cv2.circle(m, (cx, cy), int(rng.integers(1, 25)), 255, int(rng.choice([-1, 1, 2, 3])))
+        elif kind == 1:
+            cv2.rectangle(m, (cx, cy), (cx + int(rng.integers(1, 40)), cy + int(rng.integers(1, 40))), 255,
+                          int(rng.choice([-1, 1, 2])))
+        else:
+            cv2.line(m, (cx, cy), (int(rng.integers(0, w)), int(rng.integers(0, h))), 255, int(rng.integers(1, 4)))
+    noise = rng.random(shape) < 0.02
+    m[noise] = 255 - m[noise]
+    return m
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_contour_filter(seed):
+    rng = _rng(100 + seed)
+    shape = [(96, 128), (61, 83), (120, 160), (32, 200)][seed % 4]
+    m = _random_blob_mask(rng, shape, int(rng.integers(1, 12)))
+    for min_area in (0, 20, 100, 500):
+        assert np.array_equal(so.contour_filter(m, min_area), so.contour_filter_cv2(m, min_area)), (seed, min_area)
+
+
+def test_contour_filter_dense_random():
+    rng = _rng(7)
+    for density in (0.3, 0.5, 0.6, 0.8):
+        m = (rng.random((80, 100)) < density).astype(np.uint8) * 255
+        for min_area in (0, 5, 50):
+            assert np.array_equal(so.contour_filter(m, min_area), so.contour_filter_cv2(m, min_area))
+
+
+@pytest.mark.parametrize("bs", [4, 8])
+def test_dct_rows_equals_block_dct(bs):
+    rng = _rng(8)
+    blocks = rng.integers(0, 256, (3000, bs, bs)).astype(np.float32) - 128
+    ref = np.stack([cv2.dct(b) for b in blocks])
+    got = so.dct2_blocks(blocks)
+    assert np.array_equal(ref, got)
+    q = np.round(ref / 100) * 100
+    refi = np.stack([cv2.idct(b) for b in q])
+    assert np.array_equal(refi, so.dct2_blocks(q, inverse=True))
+
+
+def _literal_fd_degrade(frame, acc, bs, q):
+    """frame_differencing.py:115-130 written out literally."""
+    h, w = acc.shape
+    ycc = cv2.cvtColor(frame, cv2.COLOR_BGR2YCrCb)
+    ch = list(cv2.split(ycc))
+    for y in range(0, h, bs):
+        for x in range(0, w, bs):
+            if acc[y:y + bs, x:x + bs].mean() == 0:
+                block = ch[0][y:y + bs, x:x + bs]
+                d = cv2.dct(block.astype(np.float32) - 128)
+                qd = np.round(d / q) * q
+                r = cv2.idct(qd) + 128
+                ch[0][y:y + bs, x:x + bs] = np.clip(r, 0, 255)
+                ch[1][y:y + bs, x:x + bs] = 128
+                ch[2][y:y + bs, x:x + bs] = 128
+    return cv2.cvtColor(cv2.merge(ch), cv2.COLOR_YCrCb2BGR)
+
+
+@pytest.mark.parametrize("shape,bs", [((48, 64), 4), ((48, 64), 8), ((50, 66), 4), ((44, 60), 8)])
+def test_degrade_fd_vs_literal(shape, bs):
+    rng = _rng(9)
+    frame = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+    acc = np.zeros(shape, np.uint8)
+    acc[10:30, 20:40] = rng.integers(0, 256, (20, 20), dtype=np.uint8)
+    assert np.array_equal(so.degrade_fd(frame, acc, bs, 100), _literal_fd_degrade(frame, acc, bs, 100))
+
+
+def test_overlay():
+    rng = _rng(10)
+    frame = rng.integers(0, 256, (20, 30, 3), dtype=np.uint8)
+    acc = rng.integers(0, 256, (20, 30), dtype=np.uint8)
+    ov = so.overlay_paint(frame, acc)
+    assert np.array_equal(ov[acc > 127], np.tile(np.array([0, 0, 255], np.uint8), ((acc > 127).sum(), 1)))
+    assert np.array_equal(ov[acc <= 127], frame[acc <= 127])
