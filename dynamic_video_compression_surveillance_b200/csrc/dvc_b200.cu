@@ -1,0 +1,901 @@
+// dvc_b200.cu -- host side of the C ABI declared in include/dvc_b200.h: per-stream state, the batch
+// loop (kernel sequencing for both loop flavours), the double-buffered host pipeline, and the
+// stage-level entry points.  Kernels live in the k_*.cuh headers next to this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/dvc_b200.h"
+#include "k_ccl.cuh"
+#include "k_degrade.cuh"
+#include "k_front.cuh"
+#include "k_mask.cuh"
+
+using namespace dvc;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int set_err(char* dst, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (dst) { strncpy(dst, g_err, 511); dst[511] = 0; }
+    return code;
+}
+
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return set_err(ERRBUF, e_ == cudaErrorMemoryAllocation ? DVC_ERR_NOMEM : DVC_ERR_CUDA,       \
+                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);  \
+    } while (0)
+#define CHECK_LAUNCH() CU(cudaGetLastError())
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// structuring elements -> MorphChain
+// ------------------------------------------------------------------------------------------------
+// Row runs of np.ones((k,k)) or cv2.getStructuringElement(MORPH_ELLIPSE,(k,k)) relative to the default
+// anchor (k/2, k/2).  The ellipse restates OpenCV's morph code: row i spans |dx| <= rint(c*sqrt(r^2-dy^2)/r).
+static bool make_prim(int shape, int k, bool erode, MorphPrim& p) {
+    if (k < 1 || k > MORPH_MAX_K) return false;
+    memset(&p, 0, sizeof(p));
+    p.erode = erode;
+    const int a = k / 2;
+    int n = 0;
+    for (int i = 0; i < k; ++i) {
+        int j1 = 0, j2 = k;
+        if (shape == DVC_SHAPE_ELLIPSE) {
+            const int r = k / 2, c = k / 2;
+            const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+            const int dy = i - r;
+            j1 = j2 = 0;
+            if (std::abs(dy) <= r) {
+                const int dx = (int)std::nearbyint(c * std::sqrt((r * r - dy * dy) * inv_r2));
+                j1 = std::max(c - dx, 0);
+                j2 = std::min(c + dx + 1, k);
+            }
+        }
+        if (j2 <= j1) continue;
+        p.dy[n] = (int8_t)(i - a);
+        p.lo[n] = (int8_t)(j1 - a);
+        p.hi[n] = (int8_t)(j2 - 1 - a);
+        ++n;
+    }
+    p.nrows = (int8_t)n;
+    if (n == 0) return false;
+    bool sep = true;
+    for (int i = 1; i < n; ++i)
+        if (p.lo[i] != p.lo[0] || p.hi[i] != p.hi[0] || p.dy[i] != p.dy[i - 1] + 1) sep = false;
+    p.separable = sep;
+    return true;
+}
+
+static bool chain_push(MorphChain& ch, int op, int shape, int k) {
+    auto push = [&](bool erode) {
+        if (ch.n >= MORPH_MAX_PRIMS) return false;
+        MorphPrim& p = ch.p[ch.n];
+        if (!make_prim(shape, k, erode, p)) return false;
+        ch.halo_top += -std::min<int>(p.dy[0], 0);
+        ch.halo_bot += std::max<int>(p.dy[p.nrows - 1], 0);
+        ++ch.n;
+        return true;
+    };
+    switch (op) {
+        case DVC_MORPH_ERODE: return push(true);
+        case DVC_MORPH_DILATE: return push(false);
+        case DVC_MORPH_OPEN: return push(true) && push(false);
+        case DVC_MORPH_CLOSE: return push(false) && push(true);
+    }
+    return false;
+}
+
+// python: smallest c with c*255 >= alpha*L*255, evaluated in doubles exactly as motion_compression_opt.py:86
+static void window_min_counts(double alpha, int K, MinCounts& mc) {
+    memset(&mc, 0, sizeof(mc));
+    for (int L = 1; L <= K; ++L) {
+        const double rhs = alpha * L * 255;
+        int c = 0;
+        while (!((double)(c * 255) >= rhs) && c <= L) ++c;
+        mc.v[L - 1] = (uint8_t)std::min(c, 63);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers (all asynchronous on `st`)
+// ------------------------------------------------------------------------------------------------
+static int g_morph_smem_limit = 0;
+
+static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, int n, int H, int W,
+                              const MorphChain& ch, cudaStream_t st) {
+    const int wpr = words_per_row(W);
+    if (ch.n == 0) {
+        if (src != dst) CU(cudaMemcpyAsync(dst, src, (size_t)n * H * wpr * 4, cudaMemcpyDeviceToDevice, st));
+        return DVC_OK;
+    }
+    if (!g_morph_smem_limit) {
+        int dev = 0, lim = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        CU(cudaFuncSetAttribute(k_morph_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        g_morph_smem_limit = lim;
+    }
+    const int halo = ch.halo_top + ch.halo_bot;
+    // band height: as tall as fits in ~96 KB (two planes), at least 8 rows beyond the halo
+    const size_t budget = std::min<size_t>((size_t)g_morph_smem_limit - 64, 96 * 1024);
+    int band = (int)(budget / (2 * (size_t)wpr * 4)) - halo;
+    if (band < 8) band = (int)(((size_t)g_morph_smem_limit - 64) / (2 * (size_t)wpr * 4)) - halo;
+    if (band < 1) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "morphology chain halo %d rows x %d words does not fit in shared memory", halo, wpr);
+    band = std::min(band, H);
+    const int nbands = (H + band - 1) / band;
+    band = (H + nbands - 1) / nbands;
+    const size_t smem = 2 * (size_t)(band + halo) * wpr * 4 + 16;
+    dim3 grid(nbands, n);
+    k_morph_chain<<<grid, 256, smem, st>>>(src, dst, H, W, wpr, band, ch);
+    CHECK_LAUNCH();
+    return DVC_OK;
+}
+
+struct CclScratch {
+    int* parents_a = nullptr;   // [frames][plane_words*32+1]
+    int* parents_b = nullptr;
+    int* areas = nullptr;
+    uint32_t* filled = nullptr;  // [frames] planes
+    int frames = 0;
+};
+
+static int launch_contour_filter(char* ERRBUF, const uint32_t* raw, uint32_t* out, int n, int H, int W,
+                                 double min_area, const CclScratch& sc, cudaStream_t st) {
+    const int wpr = words_per_row(W);
+    const size_t pw = (size_t)H * wpr;
+    const double t2 = std::floor(2.0 * min_area);
+    const int thr = t2 >= 2147483647.0 ? 2147483647 : (t2 < -1.0 ? -1 : (int)t2);
+    for (int i0 = 0; i0 < n; i0 += sc.frames) {
+        const int m = std::min(sc.frames, n - i0);
+        dim3 grid(cdiv(pw, 256), m);
+        const uint32_t* r = raw + (size_t)i0 * pw;
+        k_ccl_init<true><<<grid, 256, 0, st>>>(r, sc.parents_a, nullptr, H, W, wpr);
+        k_ccl_union<true, 4, true><<<grid, 256, 0, st>>>(r, sc.parents_a, H, W, wpr);
+        k_ccl_fill<<<grid, 256, 0, st>>>(r, sc.parents_a, sc.filled, H, W, wpr);
+        k_ccl_init<false><<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, H, W, wpr);
+        k_ccl_union<false, 8, false><<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, H, W, wpr);
+        k_ccl_area<<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, H, W, wpr);
+        k_ccl_select<<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, out + (size_t)i0 * pw, H, W, wpr, thr);
+        CHECK_LAUNCH();
+    }
+    return DVC_OK;
+}
+
+static int ccl_scratch_alloc(char* ERRBUF, CclScratch& sc, int frames, int H, int W) {
+    const size_t pw = (size_t)H * words_per_row(W);
+    const size_t nodes = pw * 32 + 1;
+    sc.frames = frames;
+    CU(cudaMalloc(&sc.parents_a, nodes * sizeof(int) * frames));
+    CU(cudaMalloc(&sc.parents_b, nodes * sizeof(int) * frames));
+    CU(cudaMalloc(&sc.areas, nodes * sizeof(int) * frames));
+    CU(cudaMalloc(&sc.filled, pw * 4 * frames));
+    return DVC_OK;
+}
+static void ccl_scratch_free(CclScratch& sc) {
+    cudaFree(sc.parents_a); cudaFree(sc.parents_b); cudaFree(sc.areas); cudaFree(sc.filled);
+    sc = CclScratch();
+}
+
+static bool g_dct8_ready = false;
+static int ensure_dct8(char* ERRBUF) {
+    if (g_dct8_ready) return DVC_OK;
+    float t[8][4];
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < 8; ++k)
+        for (int n = 0; n < 4; ++n)
+            t[k][n] = (float)((k == 0 ? std::sqrt(1.0 / 8.0) : 0.5) * std::cos(pi * (2 * n + 1) * k / 16.0));
+    CU(cudaMemcpyToSymbol(c_dct8, t, sizeof(t)));
+    g_dct8_ready = true;
+    return DVC_OK;
+}
+
+static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* over127, const uint32_t* nonzero,
+                          uint8_t* compressed, uint8_t* overlay, int n, int H, int W, int bs, float q, int flavour,
+                          Counters* counters, cudaStream_t st) {
+    const int wpr = words_per_row(W);
+    if (bs != 4 && bs != 8) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "block_size %d: the GPU path implements 4 and 8", bs);
+    if (flavour == DVC_DEGRADE_MCO && bs != 8) return set_err(ERRBUF, DVC_ERR_INVALID, "MCO flavour uses 8x8 blocks");
+    if (!(q > 0.0f)) return set_err(ERRBUF, DVC_ERR_INVALID, "quantization_level must be > 0");
+    if (flavour == DVC_DEGRADE_FD && (H % bs || W % bs))
+        return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "frame %dx%d is not a multiple of block_size %d (clipped edge blocks are not implemented)", W, H, bs);
+    if (n <= 0) return DVC_OK;
+    if (flavour == DVC_DEGRADE_FD && bs == 4 && W % 16 == 0) {
+        dim3 grid(cdiv((size_t)(W / 16) * (H / 4), 128), n);
+        k_degrade4<<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, q, counters);
+    } else {
+        int rc = ensure_dct8(ERRBUF);
+        if (rc) return rc;
+        if (flavour == DVC_DEGRADE_MCO && (H % 8 || W % 8)) {
+            // clipped edge blocks are skipped by the reference (motion_compression_opt.py:159): they only
+            // see the colour round trip.  The kernel covers full blocks; edges handled by a second launch
+            // would go here.
+            return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "MCO flavour needs W, H multiples of 8");
+        }
+        dim3 grid(cdiv((size_t)(W / bs) * (H / bs), 128), n);
+        if (flavour == DVC_DEGRADE_FD && bs == 4)
+            k_degrade_generic<4, 0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, q, counters);
+        else if (flavour == DVC_DEGRADE_FD)
+            k_degrade_generic<8, 0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, q, counters);
+        else
+            k_degrade_generic<8, 1><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, q, counters);
+    }
+    CHECK_LAUNCH();
+    return DVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct ProfRec { int kid; int launches; cudaEvent_t a, b; };
+
+struct dvc_handle {
+    dvc_config cfg;
+    int H, W, wpr;
+    size_t plane_words, plane_bytes, frame_bytes;
+    bool aligned;                 // W % 16 == 0: vector paths
+    long long n_masks;            // masks produced so far in this stream
+    int seg_len;
+    // state
+    uint8_t* prev_gray[2];
+    int cur;
+    uint8_t* acc;                 // FD: accumulated_mask
+    uint32_t* ring;               // WINDOW: raw-mask ring, ring_cap planes
+    int ring_cap;
+    MinCounts min_counts;
+    // scratch (max_batch planes each)
+    uint32_t *bits_a, *bits_b, *bits_c;
+    uint8_t* blurred;             // FD: [max_batch] gray planes
+    CclScratch ccl;
+    MorphChain chain;
+    Counters* counters_dev;
+    dvc_counters counters_host;   // frames / pixels / blocks are counted on the host
+    // host pipeline
+    cudaStream_t s_h2d, s_comp, s_d2h;
+    cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
+    uint8_t *st_in[2], *st_ov[2], *st_cp[2], *st_mask[2];
+    bool staging;
+    // profiling: CUDA events around each kernel group, on the launching stream
+    bool prof;
+    std::vector<ProfRec>* prof_recs;
+    long long launches;           // kernels launched by the loop so far
+    char err[512];
+};
+
+static int alloc_staging(dvc_handle* h) {
+    char* ERRBUF = h->err;
+    if (h->staging) return DVC_OK;
+    const size_t fb = h->frame_bytes * h->cfg.max_batch;
+    for (int b = 0; b < 2; ++b) {
+        CU(cudaMalloc(&h->st_in[b], fb));
+        CU(cudaMalloc(&h->st_ov[b], fb));
+        CU(cudaMalloc(&h->st_cp[b], fb));
+        CU(cudaMalloc(&h->st_mask[b], h->plane_bytes * h->cfg.max_batch));
+        CU(cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
+    }
+    CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    h->staging = true;
+    return DVC_OK;
+}
+
+extern "C" int dvc_abi_version(void) { return DVC_ABI_VERSION; }
+
+extern "C" const char* dvc_last_error(const dvc_handle* h) { return h ? h->err : g_err; }
+
+extern "C" void dvc_default_config(dvc_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->mode = DVC_MODE_FD;
+    c->block_size = 4;
+    c->motion_threshold = 0.5f;
+    c->min_area = 500.0;
+    c->kernel_size = 7;
+    c->release_factor = 0.5;
+    c->quantization_level = 100.0f;
+    c->window_size = 30;
+    c->alpha_fraction = 0.2;
+    c->morph_kernel = 2;
+    c->morph_shape = DVC_SHAPE_ELLIPSE;
+    c->max_batch = 16;
+    c->device = 0;
+}
+
+static int create_impl(const dvc_config* cfg, dvc_handle* h) {
+    char* ERRBUF = h->err;
+    h->cfg = *cfg;
+    h->W = cfg->width; h->H = cfg->height;
+    h->wpr = words_per_row(h->W);
+    h->plane_words = (size_t)h->H * h->wpr;
+    h->plane_bytes = (size_t)h->H * h->W;
+    h->frame_bytes = h->plane_bytes * 3;
+    h->aligned = (h->W % 16) == 0;
+    const int T = cfg->max_batch;
+    const char* sl = getenv("DVC_SEG_LEN");
+    h->seg_len = sl ? std::max(1, atoi(sl)) : 8;
+    CU(cudaSetDevice(cfg->device));
+    for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&h->prev_gray[i], h->plane_bytes)); CU(cudaMemset(h->prev_gray[i], 0, h->plane_bytes)); }
+    CU(cudaMalloc(&h->bits_a, h->plane_words * 4 * T));
+    CU(cudaMalloc(&h->bits_b, h->plane_words * 4 * T));
+    CU(cudaMalloc(&h->bits_c, h->plane_words * 4 * T));
+    CU(cudaMemset(h->bits_a, 0, h->plane_words * 4 * T));
+    CU(cudaMemset(h->bits_b, 0, h->plane_words * 4 * T));
+    CU(cudaMemset(h->bits_c, 0, h->plane_words * 4 * T));
+    CU(cudaMalloc(&h->counters_dev, sizeof(Counters)));
+    CU(cudaMemset(h->counters_dev, 0, sizeof(Counters)));
+    h->chain.n = 0; h->chain.halo_top = h->chain.halo_bot = 0;
+    if (cfg->mode == DVC_MODE_FD) {
+        CU(cudaMalloc(&h->acc, h->plane_bytes));
+        CU(cudaMemset(h->acc, 0, h->plane_bytes));
+        CU(cudaMalloc(&h->blurred, h->plane_bytes * T));
+        int rc = ccl_scratch_alloc(h->err, h->ccl, std::min(T, 16), h->H, h->W);
+        if (rc) return rc;
+        if (cfg->kernel_size > 0 && !chain_push(h->chain, DVC_MORPH_DILATE, DVC_SHAPE_RECT, cfg->kernel_size))
+            return set_err(h->err, DVC_ERR_UNSUPPORTED, "kernel_size %d: supported range is 1..%d", cfg->kernel_size, MORPH_MAX_K);
+    } else {
+        if (cfg->window_size < 1 || cfg->window_size > 31)
+            return set_err(h->err, DVC_ERR_UNSUPPORTED, "window_size %d: supported range is 1..31", cfg->window_size);
+        h->ring_cap = T + cfg->window_size + 1;
+        CU(cudaMalloc(&h->ring, h->plane_words * 4 * h->ring_cap));
+        CU(cudaMemset(h->ring, 0, h->plane_words * 4 * h->ring_cap));
+        window_min_counts(cfg->alpha_fraction, cfg->window_size, h->min_counts);
+        if (cfg->morph_kernel > 0) {
+            if (!chain_push(h->chain, DVC_MORPH_CLOSE, cfg->morph_shape, cfg->morph_kernel) ||
+                !chain_push(h->chain, DVC_MORPH_OPEN, cfg->morph_shape, cfg->morph_kernel))
+                return set_err(h->err, DVC_ERR_UNSUPPORTED, "morph_kernel %d: supported range is 1..%d", cfg->morph_kernel, MORPH_MAX_K);
+        }
+        if (cfg->kernel_size > 0 && !chain_push(h->chain, DVC_MORPH_DILATE, DVC_SHAPE_RECT, cfg->kernel_size))
+            return set_err(h->err, DVC_ERR_UNSUPPORTED, "kernel_size %d: supported range is 1..%d", cfg->kernel_size, MORPH_MAX_K);
+    }
+    return DVC_OK;
+}
+
+extern "C" int dvc_destroy(dvc_handle* h) {
+    if (!h) return DVC_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(h->prev_gray[0]); cudaFree(h->prev_gray[1]); cudaFree(h->acc); cudaFree(h->ring);
+    cudaFree(h->bits_a); cudaFree(h->bits_b); cudaFree(h->bits_c); cudaFree(h->blurred); cudaFree(h->counters_dev);
+    ccl_scratch_free(h->ccl);
+    if (h->staging) {
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(h->st_in[b]); cudaFree(h->st_ov[b]); cudaFree(h->st_cp[b]); cudaFree(h->st_mask[b]);
+            cudaEventDestroy(h->ev_h2d[b]); cudaEventDestroy(h->ev_comp[b]); cudaEventDestroy(h->ev_d2h[b]);
+        }
+        cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_comp); cudaStreamDestroy(h->s_d2h);
+    }
+    if (h->prof_recs) { for (ProfRec& r : *h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } delete h->prof_recs; }
+    delete h;
+    return DVC_OK;
+}
+
+extern "C" int dvc_create(const dvc_config* cfg, dvc_handle** out) {
+    if (!cfg || !out) return set_err(nullptr, DVC_ERR_INVALID, "dvc_create: null argument");
+    *out = nullptr;
+    if (cfg->width < 1 || cfg->height < 1 || cfg->max_batch < 1)
+        return set_err(nullptr, DVC_ERR_INVALID, "dvc_create: width, height and max_batch must be >= 1");
+    if (cfg->mode != DVC_MODE_FD && cfg->mode != DVC_MODE_WINDOW) return set_err(nullptr, DVC_ERR_INVALID, "dvc_create: unknown mode %d", cfg->mode);
+    if (cfg->block_size != 4 && cfg->block_size != 8)
+        return set_err(nullptr, DVC_ERR_UNSUPPORTED, "block_size %d: the GPU path implements 4 and 8", cfg->block_size);
+    if (!(cfg->quantization_level > 0.0f)) return set_err(nullptr, DVC_ERR_INVALID, "quantization_level must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(nullptr, DVC_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    dvc_handle* h = new dvc_handle();
+    memset(h, 0, sizeof(*h));
+    new (&h->ccl) CclScratch();
+    h->prof_recs = new std::vector<ProfRec>();
+    int rc = create_impl(cfg, h);
+    if (rc) {
+        char msg[512];
+        strncpy(msg, h->err, 511); msg[511] = 0;
+        dvc_destroy(h);
+        set_err(nullptr, rc, "%s", msg);
+        return rc;
+    }
+    *out = h;
+    return DVC_OK;
+}
+
+extern "C" int dvc_begin_stream(dvc_handle* h, const uint8_t* prev_gray_host) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h || !prev_gray_host) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_begin_stream: null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h->prev_gray[h->cur], prev_gray_host, h->plane_bytes, cudaMemcpyHostToDevice));
+    if (h->acc) CU(cudaMemset(h->acc, 0, h->plane_bytes));
+    if (h->ring) CU(cudaMemset(h->ring, 0, h->plane_words * 4 * h->ring_cap));
+    h->n_masks = 0;
+    return DVC_OK;
+}
+
+// ---- state blob: header | prev_gray | acc (FD)  or  K raw planes oldest..newest (WINDOW) ----------
+struct StateHeader { uint32_t magic, mode, W, H, K, reserved; int64_t n_masks; };
+static const uint32_t STATE_MAGIC = 0x31435644u;   // "DVC1"
+
+extern "C" size_t dvc_state_bytes(const dvc_handle* h) {
+    if (!h) return 0;
+    size_t n = sizeof(StateHeader) + h->plane_bytes;
+    n += h->cfg.mode == DVC_MODE_FD ? h->plane_bytes : (size_t)h->cfg.window_size * h->plane_words * 4;
+    return n;
+}
+
+extern "C" int dvc_get_state(dvc_handle* h, void* buf, size_t bytes) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h || !buf || bytes < dvc_state_bytes(h)) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_get_state: buffer too small");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    StateHeader hd = {STATE_MAGIC, (uint32_t)h->cfg.mode, (uint32_t)h->W, (uint32_t)h->H, (uint32_t)h->cfg.window_size, 0, h->n_masks};
+    uint8_t* p = (uint8_t*)buf;
+    memcpy(p, &hd, sizeof(hd)); p += sizeof(hd);
+    CU(cudaMemcpy(p, h->prev_gray[h->cur], h->plane_bytes, cudaMemcpyDeviceToHost)); p += h->plane_bytes;
+    if (h->cfg.mode == DVC_MODE_FD) {
+        CU(cudaMemcpy(p, h->acc, h->plane_bytes, cudaMemcpyDeviceToHost));
+    } else {
+        const int K = h->cfg.window_size;
+        for (int i = 0; i < K; ++i) {       // slot i holds mask n_masks-K+i (zeros if before the stream start)
+            const long long f = h->n_masks - K + i;
+            if (f >= 0) CU(cudaMemcpy(p, h->ring + (size_t)(f % h->ring_cap) * h->plane_words, h->plane_words * 4, cudaMemcpyDeviceToHost));
+            else memset(p, 0, h->plane_words * 4);
+            p += h->plane_words * 4;
+        }
+    }
+    return DVC_OK;
+}
+
+extern "C" int dvc_set_state(dvc_handle* h, const void* buf, size_t bytes) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h || !buf || bytes < dvc_state_bytes(h)) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_set_state: buffer too small");
+    StateHeader hd;
+    const uint8_t* p = (const uint8_t*)buf;
+    memcpy(&hd, p, sizeof(hd)); p += sizeof(hd);
+    if (hd.magic != STATE_MAGIC || hd.mode != (uint32_t)h->cfg.mode || hd.W != (uint32_t)h->W || hd.H != (uint32_t)h->H ||
+        (h->cfg.mode == DVC_MODE_WINDOW && hd.K != (uint32_t)h->cfg.window_size))
+        return set_err(h->err, DVC_ERR_INVALID, "dvc_set_state: blob does not match this handle's configuration");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h->prev_gray[h->cur], p, h->plane_bytes, cudaMemcpyHostToDevice)); p += h->plane_bytes;
+    h->n_masks = hd.n_masks;
+    if (h->cfg.mode == DVC_MODE_FD) {
+        CU(cudaMemcpy(h->acc, p, h->plane_bytes, cudaMemcpyHostToDevice));
+    } else {
+        const int K = h->cfg.window_size;
+        for (int i = 0; i < K; ++i) {
+            const long long f = h->n_masks - K + i;
+            if (f >= 0) CU(cudaMemcpy(h->ring + (size_t)(f % h->ring_cap) * h->plane_words, p, h->plane_words * 4, cudaMemcpyHostToDevice));
+            p += h->plane_words * 4;
+        }
+    }
+    return DVC_OK;
+}
+
+extern "C" int dvc_get_counters(dvc_handle* h, dvc_counters* out) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h || !out) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_get_counters: null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    Counters c;
+    CU(cudaMemcpy(&c, h->counters_dev, sizeof(c), cudaMemcpyDeviceToHost));
+    *out = h->counters_host;
+    out->motion_pixels = c.motion_pixels;
+    out->static_blocks = c.static_blocks;
+    return DVC_OK;
+}
+
+extern "C" int dvc_reset_counters(dvc_handle* h) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h) return set_err(nullptr, DVC_ERR_INVALID, "dvc_reset_counters: null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(h->counters_dev, 0, sizeof(Counters)));
+    memset(&h->counters_host, 0, sizeof(h->counters_host));
+    return DVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// profiling hooks (dvc_profile_*): per kernel group, CUDA-event time on the launching stream
+// ------------------------------------------------------------------------------------------------
+struct ProfScope {
+    dvc_handle* h; cudaStream_t st; int idx;
+    ProfScope(dvc_handle* h_, int kid, int launches, cudaStream_t st_) : h(h_), st(st_), idx(-1) {
+        h->launches += launches;
+        if (!h->prof) return;
+        ProfRec r; r.kid = kid; r.launches = launches;
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+        cudaEventRecord(r.a, st);
+        h->prof_recs->push_back(r);
+        idx = (int)h->prof_recs->size() - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord((*h->prof_recs)[idx].b, st); }
+};
+
+extern "C" int dvc_profile_enable(dvc_handle* h, int32_t on) {
+    if (!h) return set_err(nullptr, DVC_ERR_INVALID, "dvc_profile_enable: null handle");
+    h->prof = on != 0;
+    return DVC_OK;
+}
+
+extern "C" int dvc_profile_read(dvc_handle* h, double* ms_by_kernel, int64_t* launches_by_kernel, int32_t n_kernels) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h || !ms_by_kernel || !launches_by_kernel || n_kernels < DVC_PROF_KERNELS)
+        return set_err(ERRBUF, DVC_ERR_INVALID, "dvc_profile_read: need arrays of %d entries", DVC_PROF_KERNELS);
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < n_kernels; ++i) { ms_by_kernel[i] = 0.0; launches_by_kernel[i] = 0; }
+    for (ProfRec& r : *h->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ms_by_kernel[r.kid] += ms; launches_by_kernel[r.kid] += r.launches; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    h->prof_recs->clear();
+    return DVC_OK;
+}
+
+extern "C" int64_t dvc_launch_count(const dvc_handle* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// the loop body for one device-resident batch
+// ------------------------------------------------------------------------------------------------
+static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8_t* overlay, uint8_t* compressed,
+                              uint8_t* mask_out, cudaStream_t st) {
+    char* ERRBUF = h->err;
+    const int H = h->H, W = h->W, wpr = h->wpr;
+    const uint32_t thr = (uint32_t)std::max(0.0f, std::floor(h->cfg.motion_threshold));
+    const uint32_t* over127 = nullptr;
+    const uint32_t* nonzero = nullptr;
+    const unsigned g16 = cdiv((size_t)((W + 15) / 16) * H, 256);
+    if (h->cfg.mode == DVC_MODE_WINDOW) {
+        const int nseg = (T + h->seg_len - 1) / h->seg_len;
+        dim3 g1(g16, nseg);
+        uint8_t* pg_in = h->prev_gray[h->cur];
+        uint8_t* pg_out = h->prev_gray[h->cur ^ 1];
+        { ProfScope ps(h, DVC_PROF_FRONT, 1, st);
+        if (h->aligned)
+            k_gray_diff_thresh<true><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);
+        else
+            k_gray_diff_thresh<false><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);
+        }
+        CHECK_LAUNCH();
+        h->cur ^= 1;
+        dim3 g2(cdiv(h->plane_words, 256), nseg);
+        { ProfScope ps(h, DVC_PROF_VOTE, 1, st);
+        k_window_vote<<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, T, h->cfg.window_size, h->min_counts, h->bits_a, h->seg_len);
+        }
+        CHECK_LAUNCH();
+        const uint32_t* fin = h->bits_a;
+        if (h->chain.n) {
+            ProfScope ps(h, DVC_PROF_MORPH, 1, st);
+            int rc = launch_morph_chain(h->err, h->bits_a, h->bits_b, T, H, W, h->chain, st);
+            if (rc) return rc;
+            fin = h->bits_b;
+        }
+        over127 = nonzero = fin;
+        if (mask_out) {
+            dim3 gu(cdiv((size_t)((W + 3) / 4) * H, 256), T);
+            ProfScope ps(h, DVC_PROF_MISC, 1, st);
+            k_unpack_bits<<<gu, 256, 0, st>>>(fin, mask_out, H, W, wpr);
+            CHECK_LAUNCH();
+        }
+    } else {
+        dim3 gb((W + BL_TW - 1) / BL_TW, (H + BL_TH - 1) / BL_TH, T);
+        { ProfScope ps(h, DVC_PROF_FRONT, 1, st);
+        if (h->aligned) k_gray_blur5<true><<<gb, 256, 0, st>>>(frames, h->blurred, H, W);
+        else k_gray_blur5<false><<<gb, 256, 0, st>>>(frames, h->blurred, H, W);
+        }
+        CHECK_LAUNCH();
+        dim3 gd(g16, T);
+        { ProfScope ps(h, DVC_PROF_DIFF, 1, st);
+        if (h->aligned) k_diff_thresh_planes<true><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, h->bits_a, wpr, thr);
+        else k_diff_thresh_planes<false><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, h->bits_a, wpr, thr);
+        }
+        CHECK_LAUNCH();
+        CU(cudaMemcpyAsync(h->prev_gray[h->cur ^ 1], h->blurred + (size_t)(T - 1) * h->plane_bytes, h->plane_bytes, cudaMemcpyDeviceToDevice, st));
+        h->cur ^= 1;
+        int rc;
+        { ProfScope ps(h, DVC_PROF_CCL, 7 * ((T + h->ccl.frames - 1) / h->ccl.frames), st);
+        rc = launch_contour_filter(h->err, h->bits_a, h->bits_b, T, H, W, h->cfg.min_area, h->ccl, st);
+        }
+        if (rc) return rc;
+        { ProfScope ps(h, DVC_PROF_MORPH, 1, st);
+        rc = launch_morph_chain(h->err, h->bits_b, h->bits_a, T, H, W, h->chain, st);      // dilate -> bits_a
+        }
+        if (rc) return rc;
+        const float alpha = (float)h->cfg.release_factor, beta = (float)(1.0 - h->cfg.release_factor);
+        { ProfScope ps(h, DVC_PROF_EMA, 1, st);
+        if (h->aligned) k_ema<true><<<g16, 256, 0, st>>>(h->acc, h->bits_a, h->bits_b, h->bits_c, mask_out, T, H, W, wpr, alpha, beta);
+        else k_ema<false><<<g16, 256, 0, st>>>(h->acc, h->bits_a, h->bits_b, h->bits_c, mask_out, T, H, W, wpr, alpha, beta);
+        }
+        CHECK_LAUNCH();
+        over127 = h->bits_b;
+        nonzero = h->bits_c;
+    }
+    if (overlay || compressed) {
+        ProfScope ps(h, DVC_PROF_DEGRADE, 1, st);
+        int rc = launch_degrade(h->err, frames, over127, nonzero, compressed, overlay, T, H, W, h->cfg.block_size,
+                                h->cfg.quantization_level, DVC_DEGRADE_FD, h->counters_dev, st);
+        if (rc) return rc;
+    }
+    h->n_masks += T;
+    h->counters_host.frames += T;
+    h->counters_host.pixels += (uint64_t)T * H * W;
+    h->counters_host.blocks += (uint64_t)T * (H / h->cfg.block_size) * (W / h->cfg.block_size);
+    return DVC_OK;
+}
+
+extern "C" int dvc_process_batch(dvc_handle* h, const uint8_t* frames_dev, int32_t n_frames, uint8_t* overlay_dev,
+                                 uint8_t* compressed_dev, uint8_t* mask_dev, void* stream) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h) return set_err(nullptr, DVC_ERR_INVALID, "dvc_process_batch: null handle");
+    if (n_frames < 0 || n_frames > h->cfg.max_batch) return set_err(h->err, DVC_ERR_INVALID, "dvc_process_batch: n_frames %d outside 0..max_batch (%d)", n_frames, h->cfg.max_batch);
+    if (n_frames == 0) return DVC_OK;
+    if (!frames_dev) return set_err(h->err, DVC_ERR_INVALID, "dvc_process_batch: null frames");
+    CU(cudaSetDevice(h->cfg.device));
+    return process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, (cudaStream_t)stream);
+}
+
+extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64_t n_frames, uint8_t* overlay_host,
+                                uint8_t* compressed_host, uint8_t* mask_host) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h) return set_err(nullptr, DVC_ERR_INVALID, "dvc_process_host: null handle");
+    if (n_frames < 0) return set_err(h->err, DVC_ERR_INVALID, "dvc_process_host: negative n_frames");
+    if (n_frames == 0) return DVC_OK;
+    if (!frames_host) return set_err(h->err, DVC_ERR_INVALID, "dvc_process_host: null frames");
+    CU(cudaSetDevice(h->cfg.device));
+    int rc = alloc_staging(h);
+    if (rc) return rc;
+    const int Tc = h->cfg.max_batch;
+    const int64_t nchunks = (n_frames + Tc - 1) / Tc;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int b = (int)(c & 1);
+        const int64_t f0 = c * Tc;
+        const int T = (int)std::min<int64_t>(Tc, n_frames - f0);
+        // the input buffer is free once the compute that read it (chunk c-2) is done
+        if (c >= 2) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));
+        CU(cudaMemcpyAsync(h->st_in[b], frames_host + (size_t)f0 * h->frame_bytes, (size_t)T * h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+        CU(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
+        CU(cudaStreamWaitEvent(h->s_comp, h->ev_h2d[b], 0));
+        // the output buffers are free once their download (chunk c-2) is done
+        if (c >= 2) CU(cudaStreamWaitEvent(h->s_comp, h->ev_d2h[b], 0));
+        rc = process_batch_impl(h, h->st_in[b], T, overlay_host ? h->st_ov[b] : nullptr, compressed_host ? h->st_cp[b] : nullptr,
+                                mask_host ? h->st_mask[b] : nullptr, h->s_comp);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CU(cudaEventRecord(h->ev_comp[b], h->s_comp));
+        CU(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
+        if (overlay_host) CU(cudaMemcpyAsync(overlay_host + (size_t)f0 * h->frame_bytes, h->st_ov[b], (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (compressed_host) CU(cudaMemcpyAsync(compressed_host + (size_t)f0 * h->frame_bytes, h->st_cp[b], (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (mask_host) CU(cudaMemcpyAsync(mask_host + (size_t)f0 * h->plane_bytes, h->st_mask[b], (size_t)T * h->plane_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+        CU(cudaEventRecord(h->ev_d2h[b], h->s_d2h));
+    }
+    CU(cudaStreamSynchronize(h->s_d2h));
+    CU(cudaStreamSynchronize(h->s_comp));
+    return DVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level entry points (stateless; scratch from the stream-ordered allocator)
+// ------------------------------------------------------------------------------------------------
+struct ScopedAsyncBuf {
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit ScopedAsyncBuf(cudaStream_t s) : st(s) {}
+    cudaError_t alloc(size_t n) { return cudaMallocAsync(&p, n ? n : 1, st); }
+    ~ScopedAsyncBuf() { if (p) cudaFreeAsync(p, st); }
+};
+
+static int check_dims(int n, int H, int W, const char* who) {
+    if (n < 0 || H < 1 || W < 1) return set_err(nullptr, DVC_ERR_INVALID, "%s: bad dimensions n=%d H=%d W=%d", who, n, H, W);
+    return DVC_OK;
+}
+
+extern "C" int dvc_bgr2gray_u8(const uint8_t* bgr, uint8_t* gray, int32_t n, int32_t H, int32_t W, void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, H, W, "dvc_bgr2gray_u8");
+    if (rc || n == 0) return rc;
+    if (!bgr || !gray) return set_err(nullptr, DVC_ERR_INVALID, "dvc_bgr2gray_u8: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 g(cdiv((size_t)((W + 15) / 16) * H, 256), n);
+    if (W % 16 == 0) k_bgr2gray<true><<<g, 256, 0, st>>>(bgr, gray, H, W);
+    else k_bgr2gray<false><<<g, 256, 0, st>>>(bgr, gray, H, W);
+    CHECK_LAUNCH();
+    return DVC_OK;
+}
+
+extern "C" int dvc_gray_absdiff_thresh_u8(const uint8_t* bgr, const uint8_t* prev_gray, uint8_t* gray_out, uint8_t* mask_out,
+                                          int32_t n, int32_t H, int32_t W, float motion_threshold, int32_t blur5, void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, H, W, "dvc_gray_absdiff_thresh_u8");
+    if (rc || n == 0) return rc;
+    if (!bgr || !prev_gray) return set_err(nullptr, DVC_ERR_INVALID, "dvc_gray_absdiff_thresh_u8: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpr = words_per_row(W);
+    const size_t pw = (size_t)H * wpr, pb = (size_t)H * W;
+    const uint32_t thr = (uint32_t)std::max(0.0f, std::floor(motion_threshold));
+    const bool al = W % 16 == 0;
+    ScopedAsyncBuf bits(st), gray_tmp(st);
+    CU(bits.alloc(pw * 4 * n));
+    CU(cudaMemsetAsync(bits.p, 0, pw * 4 * n, st));
+    const unsigned g16 = cdiv((size_t)((W + 15) / 16) * H, 256);
+    if (!blur5) {
+        const int seg = 8, nseg = (n + seg - 1) / seg;
+        dim3 g1(g16, nseg);
+        if (al) k_gray_diff_thresh<true><<<g1, 256, 0, st>>>(bgr, n, H, W, prev_gray, nullptr, gray_out, (uint32_t*)bits.p, wpr, n, 0, thr, seg);
+        else k_gray_diff_thresh<false><<<g1, 256, 0, st>>>(bgr, n, H, W, prev_gray, nullptr, gray_out, (uint32_t*)bits.p, wpr, n, 0, thr, seg);
+        CHECK_LAUNCH();
+    } else {
+        uint8_t* bl = gray_out;
+        if (!bl) { CU(gray_tmp.alloc(pb * n)); bl = (uint8_t*)gray_tmp.p; }
+        dim3 gb((W + BL_TW - 1) / BL_TW, (H + BL_TH - 1) / BL_TH, n);
+        if (al) k_gray_blur5<true><<<gb, 256, 0, st>>>(bgr, bl, H, W);
+        else k_gray_blur5<false><<<gb, 256, 0, st>>>(bgr, bl, H, W);
+        CHECK_LAUNCH();
+        dim3 gd(g16, n);
+        if (al) k_diff_thresh_planes<true><<<gd, 256, 0, st>>>(bl, prev_gray, H, W, (uint32_t*)bits.p, wpr, thr);
+        else k_diff_thresh_planes<false><<<gd, 256, 0, st>>>(bl, prev_gray, H, W, (uint32_t*)bits.p, wpr, thr);
+        CHECK_LAUNCH();
+    }
+    if (mask_out) {
+        dim3 gu(cdiv((size_t)((W + 3) / 4) * H, 256), n);
+        k_unpack_bits<<<gu, 256, 0, st>>>((const uint32_t*)bits.p, mask_out, H, W, wpr);
+        CHECK_LAUNCH();
+    }
+    return DVC_OK;
+}
+
+static int pack_to_bits(const uint8_t* src, uint32_t* dst, int n, int H, int W, cudaStream_t st) {
+    char* ERRBUF = nullptr;
+    const int wpr = words_per_row(W);
+    dim3 g(cdiv((size_t)H * wpr, 256), n);
+    k_pack_bits<<<g, 256, 0, st>>>(src, dst, H, W, wpr);
+    CHECK_LAUNCH();
+    return DVC_OK;
+}
+static int unpack_from_bits(const uint32_t* src, uint8_t* dst, int n, int H, int W, cudaStream_t st) {
+    char* ERRBUF = nullptr;
+    const int wpr = words_per_row(W);
+    dim3 g(cdiv((size_t)((W + 3) / 4) * H, 256), n);
+    k_unpack_bits<<<g, 256, 0, st>>>(src, dst, H, W, wpr);
+    CHECK_LAUNCH();
+    return DVC_OK;
+}
+
+extern "C" int dvc_temporal_ring_u8(const uint8_t* masks, uint8_t* smoothed, int32_t n, int32_t H, int32_t W,
+                                    int32_t window_size, double alpha_fraction, void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, H, W, "dvc_temporal_ring_u8");
+    if (rc || n == 0) return rc;
+    if (!masks || !smoothed) return set_err(nullptr, DVC_ERR_INVALID, "dvc_temporal_ring_u8: null pointer");
+    if (window_size < 1 || window_size > 31) return set_err(nullptr, DVC_ERR_UNSUPPORTED, "window_size %d: supported range is 1..31", window_size);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpr = words_per_row(W);
+    const size_t pw = (size_t)H * wpr;
+    ScopedAsyncBuf ring(st), voted(st);
+    CU(ring.alloc(pw * 4 * n));
+    CU(voted.alloc(pw * 4 * n));
+    rc = pack_to_bits(masks, (uint32_t*)ring.p, n, H, W, st);
+    if (rc) return rc;
+    MinCounts mc;
+    window_min_counts(alpha_fraction, window_size, mc);
+    const int seg = 8, nseg = (n + seg - 1) / seg;
+    dim3 g(cdiv(pw, 256), nseg);
+    k_window_vote<<<g, 256, 0, st>>>((const uint32_t*)ring.p, n, H, W, wpr, 0, n, window_size, mc, (uint32_t*)voted.p, seg);
+    CHECK_LAUNCH();
+    return unpack_from_bits((const uint32_t*)voted.p, smoothed, n, H, W, st);
+}
+
+extern "C" int dvc_temporal_ema_u8(uint8_t* acc, const uint8_t* dilated, uint8_t* acc_all, int32_t n, int32_t H, int32_t W,
+                                   double release_factor, void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, H, W, "dvc_temporal_ema_u8");
+    if (rc || n == 0) return rc;
+    if (!acc || !dilated) return set_err(nullptr, DVC_ERR_INVALID, "dvc_temporal_ema_u8: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpr = words_per_row(W);
+    const size_t pw = (size_t)H * wpr;
+    ScopedAsyncBuf bits(st), f1(st), f2(st);
+    CU(bits.alloc(pw * 4 * n));
+    CU(f1.alloc(pw * 4 * n));
+    CU(f2.alloc(pw * 4 * n));
+    rc = pack_to_bits(dilated, (uint32_t*)bits.p, n, H, W, st);
+    if (rc) return rc;
+    const float alpha = (float)release_factor, beta = (float)(1.0 - release_factor);
+    const unsigned g16 = cdiv((size_t)((W + 15) / 16) * H, 256);
+    if (W % 16 == 0) k_ema<true><<<g16, 256, 0, st>>>(acc, (const uint32_t*)bits.p, (uint32_t*)f1.p, (uint32_t*)f2.p, acc_all, n, H, W, wpr, alpha, beta);
+    else k_ema<false><<<g16, 256, 0, st>>>(acc, (const uint32_t*)bits.p, (uint32_t*)f1.p, (uint32_t*)f2.p, acc_all, n, H, W, wpr, alpha, beta);
+    CHECK_LAUNCH();
+    return DVC_OK;
+}
+
+extern "C" int dvc_morph_u8(const uint8_t* src, uint8_t* dst, int32_t n, int32_t H, int32_t W, int32_t op, int32_t shape,
+                            int32_t k, void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, H, W, "dvc_morph_u8");
+    if (rc || n == 0) return rc;
+    if (!src || !dst) return set_err(nullptr, DVC_ERR_INVALID, "dvc_morph_u8: null pointer");
+    if (op < DVC_MORPH_ERODE || op > DVC_MORPH_CLOSE || (shape != DVC_SHAPE_RECT && shape != DVC_SHAPE_ELLIPSE))
+        return set_err(nullptr, DVC_ERR_INVALID, "dvc_morph_u8: bad op/shape");
+    MorphChain ch;
+    ch.n = 0; ch.halo_top = ch.halo_bot = 0;
+    if (!chain_push(ch, op, shape, k)) return set_err(nullptr, DVC_ERR_UNSUPPORTED, "dvc_morph_u8: kernel size %d outside 1..%d", k, MORPH_MAX_K);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pw = (size_t)H * words_per_row(W);
+    ScopedAsyncBuf a(st), b(st);
+    CU(a.alloc(pw * 4 * n));
+    CU(b.alloc(pw * 4 * n));
+    rc = pack_to_bits(src, (uint32_t*)a.p, n, H, W, st);
+    if (rc) return rc;
+    rc = launch_morph_chain(nullptr, (const uint32_t*)a.p, (uint32_t*)b.p, n, H, W, ch, st);
+    if (rc) return rc;
+    return unpack_from_bits((const uint32_t*)b.p, dst, n, H, W, st);
+}
+
+extern "C" int dvc_contour_filter_u8(const uint8_t* src, uint8_t* dst, int32_t n, int32_t H, int32_t W, double min_area,
+                                     void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, H, W, "dvc_contour_filter_u8");
+    if (rc || n == 0) return rc;
+    if (!src || !dst) return set_err(nullptr, DVC_ERR_INVALID, "dvc_contour_filter_u8: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pw = (size_t)H * words_per_row(W);
+    const size_t nodes = pw * 32 + 1;
+    const int fr = std::min(n, 8);
+    ScopedAsyncBuf a(st), b(st), pa(st), pb(st), ar(st), fl(st);
+    CU(a.alloc(pw * 4 * n));
+    CU(b.alloc(pw * 4 * n));
+    CU(pa.alloc(nodes * 4 * fr));
+    CU(pb.alloc(nodes * 4 * fr));
+    CU(ar.alloc(nodes * 4 * fr));
+    CU(fl.alloc(pw * 4 * fr));
+    CclScratch sc;
+    sc.parents_a = (int*)pa.p; sc.parents_b = (int*)pb.p; sc.areas = (int*)ar.p; sc.filled = (uint32_t*)fl.p; sc.frames = fr;
+    rc = pack_to_bits(src, (uint32_t*)a.p, n, H, W, st);
+    if (rc) return rc;
+    rc = launch_contour_filter(nullptr, (const uint32_t*)a.p, (uint32_t*)b.p, n, H, W, min_area, sc, st);
+    if (rc) return rc;
+    return unpack_from_bits((const uint32_t*)b.p, dst, n, H, W, st);
+}
+
+extern "C" int dvc_degrade_blend_u8(const uint8_t* bgr, const uint8_t* mask, uint8_t* compressed, uint8_t* overlay, int32_t n,
+                                    int32_t H, int32_t W, int32_t block_size, float q, int32_t flavour, uint64_t* counters,
+                                    void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, H, W, "dvc_degrade_blend_u8");
+    if (rc || n == 0) return rc;
+    if (!bgr || !mask) return set_err(nullptr, DVC_ERR_INVALID, "dvc_degrade_blend_u8: null pointer");
+    if (flavour != DVC_DEGRADE_FD && flavour != DVC_DEGRADE_MCO) return set_err(nullptr, DVC_ERR_INVALID, "dvc_degrade_blend_u8: bad flavour");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpr = words_per_row(W);
+    const size_t pw = (size_t)H * wpr;
+    ScopedAsyncBuf hi(st), nz(st);
+    CU(hi.alloc(pw * 4 * n));
+    CU(nz.alloc(pw * 4 * n));
+    dim3 g(cdiv(pw, 256), n);
+    k_flags_from_u8<<<g, 256, 0, st>>>(mask, (uint32_t*)hi.p, (uint32_t*)nz.p, H, W, wpr);
+    CHECK_LAUNCH();
+    rc = launch_degrade(nullptr, bgr, (const uint32_t*)hi.p, (const uint32_t*)nz.p, compressed, overlay, n, H, W, block_size, q,
+                        flavour, (Counters*)counters, st);
+    if (rc) return rc;
+    if (counters) {
+        k_counters_add<<<1, 1, 0, st>>>((Counters*)counters, (unsigned long long)n, (unsigned long long)n * H * W,
+                                         (unsigned long long)n * (H / block_size) * (W / block_size));
+        CHECK_LAUNCH();
+    }
+    return DVC_OK;
+}

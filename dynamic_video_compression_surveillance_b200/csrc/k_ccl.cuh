@@ -1,0 +1,212 @@
+// K-ccl: the contour filter of frame_differencing.py:100-104
+//     contours = findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)
+//     keep contours with contourArea > min_area, drawContours(FILLED)
+// restated without contour tracing (oracle/stage_ops.py::contour_filter,
+// pinned against cv2 in tests/test_oracle_vs_cv2.py):
+//   phase A  O = background 4-connected to the outside of the image;  F = not O (blobs + their holes)
+//   phase B  label F with 8-connectivity;  twice the polygon area of a label is 2*Q4 + Q3, the number
+//            of 2x2 windows holding 4 / 3 of its pixels;  keep labels with 2*area > 2*min_area.
+//
+// Both phases are a union-find over *bit runs*: the graph nodes are the maximal runs of set bits inside
+// each 32-bit word of the bit-plane (node id = 1 + pixel index of the run's first bit; id 0 is the
+// "outside" node in phase A), so an empty 1080p mask is 65 k nodes instead of 2 M pixels and a thread
+// owns one word.  Unions are lock-free (atomicMin on the larger root), finds use path halving.
+#pragma once
+#include "common.cuh"
+
+namespace dvc {
+
+DEVI int uf_find(int* P, int x) {
+    while (true) {
+        const int p = __ldcg(P + x);       // L2 reads: other SMs link roots with atomics at L2
+        if (p == x) return x;
+        const int gp = __ldcg(P + p);
+        if (gp == p) return p;
+        __stcg(P + x, gp);   // path halving; parents only ever move to smaller ancestors of the same set
+        x = gp;
+    }
+}
+DEVI void uf_union(int* P, int a, int b) {
+    while (true) {
+        a = uf_find(P, a);
+        b = uf_find(P, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&P[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// lowest run of set bits of m: returns its mask, lo = first bit
+DEVI uint32_t lowest_run(uint32_t m, int& lo) {
+    lo = __ffs(m) - 1;
+    const uint32_t t = m + (1u << lo);
+    return m & ~t;
+}
+// first bit of the run of u that contains bit p (bit p must be set)
+DEVI int run_start(uint32_t u, int p) {
+    const uint32_t z = ~u & ((1u << p) - 1u);
+    return z ? 32 - __clz(z) : 0;
+}
+DEVI uint32_t run_mask_from(uint32_t u, int start) { return u & ~(u + (1u << start)); }
+
+template <bool INVERT>
+DEVI uint32_t plane_word(const uint32_t* plane, int y, int j, int H, int W, int wpr) {
+    if (y < 0 || y >= H || j < 0 || j >= wpr) return 0u;
+    const uint32_t w = plane[(size_t)y * wpr + j];
+    return INVERT ? (~w & valid_mask(j, W)) : w;
+}
+
+// ---- init: every run becomes its own set -------------------------------------------------------
+template <bool INVERT>
+__global__ void __launch_bounds__(256)
+k_ccl_init(const uint32_t* __restrict__ planes, int* __restrict__ parents, int* __restrict__ areas, int H, int W,
+           int wpr) {
+    const size_t plane_words = (size_t)H * wpr;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane_words) return;
+    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
+    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    int* A = areas ? areas + (size_t)blockIdx.y * (plane_words * 32 + 1) : nullptr;
+    uint32_t m = plane_word<INVERT>(plane, y, j, H, W, wpr);
+    if (INVERT && idx == 0) P[0] = 0;
+    const int base = (int)idx * 32 + 1;
+    while (m) {
+        int lo;
+        const uint32_t run = lowest_run(m, lo);
+        P[base + lo] = base + lo;
+        if (A) A[base + lo] = 0;
+        m &= ~run;
+    }
+}
+
+// ---- unions: left neighbour word, row above (4- or 8-connected), image border (phase A) ----------
+template <bool INVERT, int CONN, bool BORDER>
+__global__ void __launch_bounds__(256)
+k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ parents, int H, int W, int wpr) {
+    const size_t plane_words = (size_t)H * wpr;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane_words) return;
+    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
+    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    const uint32_t cur = plane_word<INVERT>(plane, y, j, H, W, wpr);
+    if (!cur) return;
+    const int base = (int)idx * 32 + 1;
+    const uint32_t left = plane_word<INVERT>(plane, y, j - 1, H, W, wpr);
+    if ((cur & 1u) && (left >> 31)) uf_union(P, base, base - 32 + run_start(left, 31));
+    const uint32_t up = plane_word<INVERT>(plane, y - 1, j, H, W, wpr);
+    const uint32_t upl = CONN == 8 ? plane_word<INVERT>(plane, y - 1, j - 1, H, W, wpr) : 0u;
+    const uint32_t upr = CONN == 8 ? plane_word<INVERT>(plane, y - 1, j + 1, H, W, wpr) : 0u;
+    const int base_up = base - wpr * 32;
+    const int last_x = W - 1 - j * 32;                 // bit index of the image's last column in this word
+    uint32_t m = cur;
+    while (m) {
+        int lo;
+        const uint32_t run = lowest_run(m, lo);
+        m &= ~run;
+        const int id = base + lo;
+        const int hi = 31 - __clz(run);
+        if (BORDER) {
+            if (y == 0 || y == H - 1 || (j == 0 && lo == 0) || hi == last_x) uf_union(P, id, 0);
+        }
+        if (y > 0) {
+            uint32_t nm = run;
+            if (CONN == 8) nm |= (run << 1) | (run >> 1);
+            uint32_t n = up & nm;
+            while (n) {
+                const int p = __ffs(n) - 1;
+                const int s = run_start(up, p);
+                uf_union(P, id, base_up + s);
+                n &= ~run_mask_from(up, s);
+            }
+            if (CONN == 8) {
+                if (lo == 0 && (upl >> 31)) uf_union(P, id, base_up - 32 + run_start(upl, 31));
+                if (hi == 31 && (upr & 1u)) uf_union(P, id, base_up + 32);
+            }
+        }
+    }
+}
+
+// ---- phase A result: F = complement of the background reachable from outside ---------------------
+__global__ void __launch_bounds__(256)
+k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ parents, uint32_t* __restrict__ filled, int H,
+           int W, int wpr) {
+    const size_t plane_words = (size_t)H * wpr;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane_words) return;
+    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    uint32_t m = plane_word<true>(planes + (size_t)blockIdx.y * plane_words, y, j, H, W, wpr);
+    const int base = (int)idx * 32 + 1;
+    uint32_t outside = 0;
+    while (m) {
+        int lo;
+        const uint32_t run = lowest_run(m, lo);
+        m &= ~run;
+        if (uf_find(P, base + lo) == 0) outside |= run;
+    }
+    filled[(size_t)blockIdx.y * plane_words + idx] = ~outside & valid_mask(j, W);
+}
+
+// ---- phase B: 2*area = 2*Q4 + Q3 per label --------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ parents, int* __restrict__ areas, int H, int W,
+           int wpr) {
+    const size_t plane_words = (size_t)H * wpr;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane_words) return;
+    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    const uint32_t* F = filled + (size_t)blockIdx.y * plane_words;
+    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    int* A = areas + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    const uint32_t a = plane_word<false>(F, y, j, H, W, wpr), b = plane_word<false>(F, y + 1, j, H, W, wpr);
+    if (!(a | b)) return;
+    const uint32_t an = plane_word<false>(F, y, j + 1, H, W, wpr), bn = plane_word<false>(F, y + 1, j + 1, H, W, wpr);
+    const uint32_t a1 = (a >> 1) | (an << 31), b1 = (b >> 1) | (bn << 31);
+    const uint32_t q4 = a & a1 & b & b1;
+    const uint32_t q3a = a & ((a1 & b & ~b1) | (a1 & ~b & b1) | (~a1 & b & b1));   // top-left pixel in F
+    const uint32_t q3b = ~a & a1 & b & b1;                                         // top-left pixel not in F
+    const int base = (int)idx * 32 + 1;
+    uint32_t m = a;
+    while (m) {
+        int lo;
+        const uint32_t run = lowest_run(m, lo);
+        m &= ~run;
+        const int c = 2 * __popc(q4 & run) + __popc(q3a & run);
+        if (c) atomicAdd(&A[uf_find(P, base + lo)], c);
+    }
+    m = q3b ? b : 0u;
+    const int base_dn = base + wpr * 32;
+    while (m) {
+        int lo;
+        const uint32_t run = lowest_run(m, lo);
+        m &= ~run;
+        const int c = __popc(q3b & run);
+        if (c) atomicAdd(&A[uf_find(P, base_dn + lo)], c);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_select(const uint32_t* __restrict__ filled, int* __restrict__ parents, const int* __restrict__ areas,
+             uint32_t* __restrict__ out, int H, int W, int wpr, int twice_min_area_floor) {
+    const size_t plane_words = (size_t)H * wpr;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane_words) return;
+    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    const int* A = areas + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    uint32_t m = filled[(size_t)blockIdx.y * plane_words + idx];
+    const int base = (int)idx * 32 + 1;
+    uint32_t keep = 0;
+    while (m) {
+        int lo;
+        const uint32_t run = lowest_run(m, lo);
+        m &= ~run;
+        if (A[uf_find(P, base + lo)] > twice_min_area_floor) keep |= run;
+    }
+    out[(size_t)blockIdx.y * plane_words + idx] = keep;
+}
+
+}  // namespace dvc

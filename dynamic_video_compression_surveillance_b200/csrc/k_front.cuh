@@ -1,0 +1,266 @@
+// K1: the mask front end.
+//   k_gray_diff_thresh  BGR -> gray -> absdiff(prev) -> threshold, time loop inside the kernel
+//                       (frame_differencing.py:92,96-97 without the pre-blur; window mode)
+//   k_gray_blur5        BGR -> gray -> GaussianBlur(5,5),0 (frame_differencing.py:92-93; fd mode)
+//   k_diff_thresh_planes  absdiff + threshold on blurred gray planes (frame_differencing.py:96-97)
+//   k_bgr2gray, k_pack_bits, k_unpack_bits  stage-level helpers
+#pragma once
+#include "common.cuh"
+
+namespace dvc {
+
+// ------------------------------------------------------------------------------------------------
+// scalar fallbacks for widths whose BGR row pitch is not a multiple of 16 bytes
+// ------------------------------------------------------------------------------------------------
+DEVI void load_bgr16_generic(const uint8_t* row, int x0, int W, uint32_t (&w)[12]) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) w[i] = 0;
+    int nb = min(16, W - x0) * 3;
+    const uint8_t* p = row + (size_t)x0 * 3;
+    for (int i = 0; i < nb; ++i) w[i >> 2] |= (uint32_t)p[i] << ((i & 3) * 8);
+}
+DEVI void load_u8x16_generic(const uint8_t* row, int x0, int W, uint32_t (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = 0;
+    int nb = min(16, W - x0);
+    for (int i = 0; i < nb; ++i) v[i >> 2] |= (uint32_t)row[x0 + i] << ((i & 3) * 8);
+}
+DEVI void store_u8x16_generic(uint8_t* row, int x0, int W, const uint32_t (&v)[4]) {
+    int nb = min(16, W - x0);
+    for (int i = 0; i < nb; ++i) row[x0 + i] = (uint8_t)(v[i >> 2] >> ((i & 3) * 8));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (window mode).  One thread owns 16 horizontally adjacent pixels and walks a segment of frames,
+// keeping the previous gray values in registers: per frame it loads 48 B of BGR (3 x LDG.128),
+// and stores one 16-bit piece of the raw-mask bit-plane.  Algorithmic HBM bytes: 3 B/px read
+// (+ 1/8 B/px written); the previous gray never touches memory inside a segment.
+//
+// ring:   raw-mask ring buffer, plane of frame f lives in slot f % ring_cap
+// f0:     global index of frames[0] within the stream
+// ------------------------------------------------------------------------------------------------
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256)
+k_gray_diff_thresh(const uint8_t* __restrict__ frames, int T, int H, int W,
+                   const uint8_t* __restrict__ prev_gray_in, uint8_t* __restrict__ gray_state_out,
+                   uint8_t* __restrict__ gray_all_out, uint32_t* __restrict__ ring, int wpr, int ring_cap,
+                   long long f0, uint32_t thr, int seg_len) {
+    const int gpr = (W + 15) >> 4;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)gpr * H) return;
+    const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx << 4;
+    const int t0 = blockIdx.y * seg_len, t1 = min(T, t0 + seg_len);
+    const size_t frame_bytes = (size_t)H * W * 3, plane_bytes = (size_t)H * W;
+    const size_t row_off = (size_t)y * W * 3, px_off = (size_t)y * W + x0;
+    const size_t plane_words = (size_t)H * wpr;
+    const uint32_t vmask = (W - x0 >= 16) ? 0xffffu : ((1u << (W - x0)) - 1u);
+
+    uint32_t pg[4], w[12];
+    if (t0 == 0) {
+        if (ALIGNED) load16(prev_gray_in + px_off, pg);
+        else load_u8x16_generic(prev_gray_in + (size_t)y * W, x0, W, pg);
+    } else {
+        const uint8_t* fr = frames + (size_t)(t0 - 1) * frame_bytes + row_off;
+        if (ALIGNED) {
+            load16(fr + x0 * 3, *reinterpret_cast<uint32_t(*)[4]>(&w[0]));
+            load16(fr + x0 * 3 + 16, *reinterpret_cast<uint32_t(*)[4]>(&w[4]));
+            load16(fr + x0 * 3 + 32, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
+        } else load_bgr16_generic(fr, x0, W, w);
+        gray16(w, pg);
+    }
+    for (int t = t0; t < t1; ++t) {
+        const uint8_t* fr = frames + (size_t)t * frame_bytes + row_off;
+        if (ALIGNED) {
+            load16(fr + x0 * 3, *reinterpret_cast<uint32_t(*)[4]>(&w[0]));
+            load16(fr + x0 * 3 + 16, *reinterpret_cast<uint32_t(*)[4]>(&w[4]));
+            load16(fr + x0 * 3 + 32, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
+        } else load_bgr16_generic(fr, x0, W, w);
+        uint32_t g[4];
+        gray16(w, g);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bits |= diff_gt_bits4(g[q], pg[q], thr) << (4 * q);
+        bits &= vmask;
+        const int slot = (int)((f0 + t) % ring_cap);
+        reinterpret_cast<uint16_t*>(ring + (size_t)slot * plane_words + (size_t)y * wpr)[gx] = (uint16_t)bits;
+        if (gray_all_out) {
+            if (ALIGNED) store16(gray_all_out + (size_t)t * plane_bytes + px_off, g);
+            else store_u8x16_generic(gray_all_out + (size_t)t * plane_bytes + (size_t)y * W, x0, W, g);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pg[q] = g[q];
+    }
+    if (t1 == T && gray_state_out) {
+        if (ALIGNED) store16(gray_state_out + px_off, pg);
+        else store_u8x16_generic(gray_state_out + (size_t)y * W, x0, W, pg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage helper: BGR -> gray for n images
+// ------------------------------------------------------------------------------------------------
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256)
+k_bgr2gray(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, int H, int W) {
+    const int gpr = (W + 15) >> 4;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)gpr * H) return;
+    const int y = (int)(gid / gpr), x0 = (int)(gid % gpr) << 4;
+    const uint8_t* fr = bgr + (size_t)blockIdx.y * H * W * 3 + (size_t)y * W * 3;
+    uint8_t* out = gray + (size_t)blockIdx.y * H * W + (size_t)y * W;
+    uint32_t w[12], g[4];
+    if (ALIGNED) {
+        load16(fr + x0 * 3, *reinterpret_cast<uint32_t(*)[4]>(&w[0]));
+        load16(fr + x0 * 3 + 16, *reinterpret_cast<uint32_t(*)[4]>(&w[4]));
+        load16(fr + x0 * 3 + 32, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
+    } else load_bgr16_generic(fr, x0, W, w);
+    gray16(w, g);
+    if (ALIGNED) store16(out + x0, g);
+    else store_u8x16_generic(out, x0, W, g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (fd mode), part 1: BGR -> gray -> GaussianBlur(5,5),0.
+// cv2 evaluates the binomial kernel [1,4,6,4,1]/16 in 8.8 fixed point; the result is
+// (sum over the separable 5x5 integer kernel + 128) >> 8 with BORDER_REFLECT_101
+// (frame_differencing.py:93).  Tile 128 x 32 output pixels per CTA; gray of tile + 2-pixel halo is
+// built in shared memory (interior through 48-byte vector loads, halo columns scalar), then the
+// horizontal and vertical 5-tap passes run out of shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int BL_TW = 128, BL_TH = 32, BL_PAD = 16, BL_GP = BL_TW + 2 * BL_PAD;  // gray pitch, 16 B pad each side
+
+DEVI int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256)
+k_gray_blur5(const uint8_t* __restrict__ frames, uint8_t* __restrict__ blurred, int H, int W) {
+    __shared__ __align__(16) uint8_t sg[(BL_TH + 4) * BL_GP];      // gray, column c <-> x = x0 - BL_PAD + c
+    __shared__ __align__(16) uint16_t sh[(BL_TH + 4) * BL_TW];     // horizontal pass
+    const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
+    const uint8_t* fr = frames + (size_t)blockIdx.z * H * W * 3;
+    uint8_t* out = blurred + (size_t)blockIdx.z * H * W;
+    const int tid = threadIdx.x;
+
+    // phase 1a: interior gray, 16 pixels per task
+    for (int task = tid; task < (BL_TH + 4) * (BL_TW / 16); task += 256) {
+        const int r = task / (BL_TW / 16), g = task % (BL_TW / 16);
+        const int x = x0 + g * 16;
+        if (x >= W) continue;
+        const int yy = reflect101(y0 - 2 + r, H);
+        const uint8_t* row = fr + (size_t)yy * W * 3;
+        uint32_t w[12], gg[4];
+        if (ALIGNED && x + 16 <= W) {
+            load16(row + x * 3, *reinterpret_cast<uint32_t(*)[4]>(&w[0]));
+            load16(row + x * 3 + 16, *reinterpret_cast<uint32_t(*)[4]>(&w[4]));
+            load16(row + x * 3 + 32, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
+        } else load_bgr16_generic(row, x, W, w);
+        gray16(w, gg);
+        *reinterpret_cast<uint4*>(&sg[r * BL_GP + BL_PAD + g * 16]) = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+    }
+    __syncthreads();
+    // phase 1b: halo columns.  Left: x0-2, x0-1.  Right: the two columns after the last valid
+    // column of this tile (tile may be clipped by the image edge).
+    const int tw = min(BL_TW, W - x0);              // valid columns in this tile
+    for (int task = tid; task < (BL_TH + 4) * 4; task += 256) {
+        const int r = task >> 2, k = task & 3;
+        const int dx = k < 2 ? k - 2 : tw + (k - 2);   // column offset relative to x0
+        const int xx = reflect101(x0 + dx, W);
+        const int yy = reflect101(y0 - 2 + r, H);
+        uint8_t v;
+        if (xx >= x0 && xx < x0 + tw) v = sg[r * BL_GP + BL_PAD + (xx - x0)];   // reflected into this tile
+        else {
+            const uint8_t* p = fr + ((size_t)yy * W + xx) * 3;
+            v = (uint8_t)gray_of(p[0], p[1], p[2]);
+        }
+        sg[r * BL_GP + BL_PAD + dx] = v;
+    }
+    __syncthreads();
+    // phase 2: horizontal 5 taps, 4 pixels per task
+    for (int task = tid; task < (BL_TH + 4) * (BL_TW / 4); task += 256) {
+        const int r = task / (BL_TW / 4), c = (task % (BL_TW / 4)) * 4;
+        if (c >= tw) continue;
+        const uint8_t* g = &sg[r * BL_GP + BL_PAD + c];
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = g[i - 2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            sh[r * BL_TW + c + i] = (uint16_t)(v[i] + 4 * v[i + 1] + 6 * v[i + 2] + 4 * v[i + 3] + v[i + 4]);
+    }
+    __syncthreads();
+    // phase 3: vertical 5 taps + rounding, 16 pixels per task -> one 16-byte store
+    for (int task = tid; task < BL_TH * (BL_TW / 16); task += 256) {
+        const int r = task / (BL_TW / 16), c = (task % (BL_TW / 16)) * 16;
+        const int y = y0 + r;
+        if (y >= H || c >= tw) continue;
+        uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint16_t* h = &sh[r * BL_TW + c + i];
+            uint32_t v = h[0] + 4u * h[BL_TW] + 6u * h[2 * BL_TW] + 4u * h[3 * BL_TW] + h[4 * BL_TW];
+            o[i >> 2] |= ((v + 128u) >> 8) << ((i & 3) * 8);
+        }
+        if (ALIGNED && x0 + c + 16 <= W) store16(out + (size_t)y * W + x0 + c, o);
+        else store_u8x16_generic(out + (size_t)y * W, x0 + c, W, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (fd mode), part 2: absdiff + threshold between consecutive blurred planes -> raw-mask bit-planes.
+// planes[t] is differenced against planes[t-1]; planes[-1] is prev_gray (stream state).
+// ------------------------------------------------------------------------------------------------
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256)
+k_diff_thresh_planes(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ prev_gray, int H, int W,
+                     uint32_t* __restrict__ bits_out, int wpr, uint32_t thr) {
+    const int gpr = (W + 15) >> 4;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)gpr * H) return;
+    const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx << 4;
+    const int t = blockIdx.y;
+    const size_t plane_bytes = (size_t)H * W;
+    const uint8_t* cur = planes + (size_t)t * plane_bytes + (size_t)y * W;
+    const uint8_t* prv = (t == 0 ? prev_gray : planes + (size_t)(t - 1) * plane_bytes) + (size_t)y * W;
+    uint32_t a[4], b[4];
+    if (ALIGNED) { load16(cur + x0, a); load16(prv + x0, b); }
+    else { load_u8x16_generic(cur, x0, W, a); load_u8x16_generic(prv, x0, W, b); }
+    uint32_t bits = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bits |= diff_gt_bits4(a[q], b[q], thr) << (4 * q);
+    if (W - x0 < 16) bits &= (1u << (W - x0)) - 1u;
+    reinterpret_cast<uint16_t*>(bits_out + (size_t)t * H * wpr + (size_t)y * wpr)[gx] = (uint16_t)bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// u8 mask (0 / non-zero) <-> bit-plane, n images per launch (blockIdx.y)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pack_bits(const uint8_t* __restrict__ src, uint32_t* __restrict__ dst, int H, int W, int wpr) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)H * wpr) return;
+    const int y = (int)(gid / wpr), j = (int)(gid % wpr);
+    const uint8_t* row = src + (size_t)blockIdx.y * H * W + (size_t)y * W;
+    uint32_t bits = 0;
+    const int n = min(32, W - j * 32);
+    for (int i = 0; i < n; ++i) bits |= (row[j * 32 + i] != 0 ? 1u : 0u) << i;
+    dst[(size_t)blockIdx.y * H * wpr + gid] = bits;
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack_bits(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int wpr) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 pixels
+    const int qpr = (W + 3) >> 2;
+    if (gid >= (long long)H * qpr) return;
+    const int y = (int)(gid / qpr), x = (int)(gid % qpr) << 2;
+    const uint32_t word = src[(size_t)blockIdx.y * H * wpr + (size_t)y * wpr + (x >> 5)];
+    const uint32_t nib = (word >> (x & 31)) & 0xfu;
+    uint8_t* row = dst + (size_t)blockIdx.y * H * W + (size_t)y * W;
+    const int n = min(4, W - x);
+    for (int i = 0; i < n; ++i) row[x + i] = (nib >> i) & 1u ? 255 : 0;
+}
+
+}  // namespace dvc

@@ -1,0 +1,274 @@
+// K2 / K3: everything that happens to the motion mask between the threshold and the degrade kernel,
+// done on bit-planes (see common.cuh).
+//   k_window_vote   deque(maxlen=K) + np.sum + compare (motion_compression_opt.py:61,84-86):
+//                   ring buffer of raw masks in HBM/L2, running per-pixel count kept bit-sliced in
+//                   registers while a thread walks a segment of frames (add the new plane, subtract the
+//                   evicted one) instead of re-summing the window
+//   k_ema           cv2.addWeighted(acc, rf, dilated, 1-rf, 0) (frame_differencing.py:107): the uint8
+//                   accumulator plane is stream state; per frame the kernel emits the two bit-planes the
+//                   rest of the loop needs: acc > 127 (overlay, :111) and acc != 0 (block test, :120)
+//   k_morph_chain   cv2.erode / dilate / morphologyEx chains (frame_differencing.py:106,
+//                   motion_compression_opt.py:89-90): a row band plus halo is staged into shared memory
+//                   with one cp.async.bulk (TMA) copy, every primitive of the chain runs out of shared
+//                   memory (separable OR-doubling: the binary form of van Herk/Gil-Werman), one
+//                   write of the final band
+#pragma once
+#include "common.cuh"
+
+namespace dvc {
+
+// ------------------------------------------------------------------------------------------------
+// window vote
+// ------------------------------------------------------------------------------------------------
+struct MinCounts { uint8_t v[32]; };   // v[L-1] = smallest count that passes with L masks in the window
+
+constexpr int CNT_BITS = 5;            // window_size <= 31
+
+DEVI void bs_add(uint32_t (&c)[CNT_BITS], uint32_t x) {
+#pragma unroll
+    for (int i = 0; i < CNT_BITS; ++i) { uint32_t t = c[i] & x; c[i] ^= x; x = t; }
+}
+DEVI void bs_sub(uint32_t (&c)[CNT_BITS], uint32_t x) {
+#pragma unroll
+    for (int i = 0; i < CNT_BITS; ++i) { uint32_t t = ~c[i] & x; c[i] ^= x; x = t; }
+}
+DEVI uint32_t bs_ge(const uint32_t (&c)[CNT_BITS], uint32_t m) {   // per-lane count >= m
+    if (m >= (1u << CNT_BITS)) return 0u;
+    uint32_t ge = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < CNT_BITS; ++i) ge = ((m >> i) & 1u) ? (c[i] & ge) : (c[i] | ge);
+    return ge;
+}
+
+__global__ void __launch_bounds__(256)
+k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int wpr, long long f0, int T, int K,
+              MinCounts mc, uint32_t* __restrict__ voted, int seg_len) {
+    const size_t plane_words = (size_t)H * wpr;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane_words) return;
+    const int t0 = blockIdx.y * seg_len, t1 = min(T, t0 + seg_len);
+    const uint32_t vm = valid_mask((int)(idx % wpr), W);
+    uint32_t c[CNT_BITS] = {0, 0, 0, 0, 0};
+    const long long fs = f0 + t0;
+    for (long long f = max(0LL, fs - K + 1); f < fs; ++f) bs_add(c, ring[(size_t)(f % ring_cap) * plane_words + idx]);
+    for (int t = t0; t < t1; ++t) {
+        const long long f = f0 + t;
+        if (f - K >= 0) bs_sub(c, ring[(size_t)((f - K) % ring_cap) * plane_words + idx]);
+        bs_add(c, ring[(size_t)(f % ring_cap) * plane_words + idx]);
+        const int L = (int)min((long long)K, f + 1);
+        voted[(size_t)t * plane_words + idx] = bs_ge(c, mc.v[L - 1]) & vm;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// EMA (addWeighted).  cv2 computes, in float32: t = dilated * beta (rounded), s = fma(acc, alpha, t),
+// result = saturate(round-half-even(s)).  One thread owns 16 pixels, keeps their accumulator bytes in
+// registers over the whole batch.
+// ------------------------------------------------------------------------------------------------
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256)
+k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t* __restrict__ over127,
+      uint32_t* __restrict__ nonzero, uint8_t* __restrict__ acc_all, int T, int H, int W, int wpr, float alpha,
+      float beta) {
+    const int gpr = (W + 15) >> 4;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)gpr * H) return;
+    const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx << 4;
+    const size_t plane_words = (size_t)H * wpr, plane_bytes = (size_t)H * W;
+    const int npx = min(16, W - x0);
+    uint32_t a[4];
+    uint8_t* arow = acc + (size_t)y * W;
+    if (ALIGNED) { uint4 t = *reinterpret_cast<const uint4*>(arow + x0); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+    else { for (int i = 0; i < 4; ++i) a[i] = 0; for (int i = 0; i < npx; ++i) a[i >> 2] |= (uint32_t)arow[x0 + i] << ((i & 3) * 8); }
+    const float on = __fmul_rn(255.0f, beta);
+    for (int t = 0; t < T; ++t) {
+        const size_t woff = (size_t)t * plane_words + (size_t)y * wpr;
+        const uint32_t bits = reinterpret_cast<const uint16_t*>(dilated + woff)[gx];
+        uint32_t hi = 0, nz = 0;
+        if ((a[0] | a[1] | a[2] | a[3] | bits) != 0u) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t nw = 0;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int i = q * 4 + p;
+                    const float av = (float)((a[q] >> (8 * p)) & 0xffu);
+                    const float s = __fmaf_rn(av, alpha, ((bits >> i) & 1u) ? on : 0.0f);
+                    int v = __float2int_rn(s);
+                    v = max(0, min(255, v));
+                    nw |= (uint32_t)v << (8 * p);
+                    hi |= (v > 127 ? 1u : 0u) << i;
+                    nz |= (v != 0 ? 1u : 0u) << i;
+                }
+                a[q] = nw;
+            }
+            if (npx < 16) { const uint32_t m = (1u << npx) - 1u; hi &= m; nz &= m; }
+        }
+        reinterpret_cast<uint16_t*>(over127 + woff)[gx] = (uint16_t)hi;
+        reinterpret_cast<uint16_t*>(nonzero + woff)[gx] = (uint16_t)nz;
+        if (acc_all) {
+            uint8_t* o = acc_all + (size_t)t * plane_bytes + (size_t)y * W;
+            if (ALIGNED) *reinterpret_cast<uint4*>(o + x0) = make_uint4(a[0], a[1], a[2], a[3]);
+            else for (int i = 0; i < npx; ++i) o[x0 + i] = (uint8_t)(a[i >> 2] >> ((i & 3) * 8));
+        }
+    }
+    if (ALIGNED) *reinterpret_cast<uint4*>(arow + x0) = make_uint4(a[0], a[1], a[2], a[3]);
+    else for (int i = 0; i < npx; ++i) arow[x0 + i] = (uint8_t)(a[i >> 2] >> ((i & 3) * 8));
+}
+
+// acc plane (uint8) -> the two flag planes, for callers that hand in an arbitrary uint8 mask
+__global__ void __launch_bounds__(256)
+k_flags_from_u8(const uint8_t* __restrict__ src, uint32_t* __restrict__ over127, uint32_t* __restrict__ nonzero,
+                int H, int W, int wpr) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)H * wpr) return;
+    const int y = (int)(gid / wpr), j = (int)(gid % wpr);
+    const uint8_t* row = src + (size_t)blockIdx.y * H * W + (size_t)y * W;
+    uint32_t hi = 0, nz = 0;
+    const int n = min(32, W - j * 32);
+    for (int i = 0; i < n; ++i) {
+        const uint32_t v = row[j * 32 + i];
+        hi |= (v > 127 ? 1u : 0u) << i;
+        nz |= (v != 0 ? 1u : 0u) << i;
+    }
+    over127[(size_t)blockIdx.y * H * wpr + gid] = hi;
+    nonzero[(size_t)blockIdx.y * H * wpr + gid] = nz;
+}
+
+// ------------------------------------------------------------------------------------------------
+// morphology chain
+// ------------------------------------------------------------------------------------------------
+constexpr int MORPH_MAX_K = 33;        // kernel extent limit (one neighbour word each side)
+constexpr int MORPH_MAX_PRIMS = 6;
+
+struct MorphPrim {
+    int8_t erode;                      // 0 = dilate (OR), 1 = erode (AND; run as NOT dilate NOT)
+    int8_t separable;                  // all rows share one run and rows are contiguous
+    int8_t nrows;                      // rows of the structuring element that are non-empty
+    int8_t pad;
+    int8_t dy[MORPH_MAX_K];            // row offset (kernel row - anchor)
+    int8_t lo[MORPH_MAX_K];            // run of column offsets [lo, hi] in that row
+    int8_t hi[MORPH_MAX_K];
+};
+struct MorphChain {
+    int n;
+    int halo_top, halo_bot;            // rows of input needed above / below an output band
+    MorphPrim p[MORPH_MAX_PRIMS];
+};
+
+// OR over column offsets [lo, hi] of one bit row: out(x) = OR_d in(x + d).  -32 <= lo <= hi <= 32,
+// hi - lo + 1 <= 33.  Works on the 96-bit window (prev | cur | next) and log-doubles the OR.
+DEVI uint32_t hrun_or(uint32_t prev, uint32_t cur, uint32_t next, int lo, int hi) {
+    const unsigned __int128 v = (unsigned __int128)prev | ((unsigned __int128)cur << 32) | ((unsigned __int128)next << 64);
+    uint64_t r = (uint64_t)(v >> (32 + lo));
+    const int n = hi - lo + 1;
+    int c = 1;
+    while (2 * c <= n) { r |= r >> c; c *= 2; }
+    if (c < n) r |= r >> (n - c);
+    return (uint32_t)r;
+}
+
+DEVI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// grid: (bands, n_images); dynamic smem: 2 planes of ext_rows x wpr words + one mbarrier
+__global__ void __launch_bounds__(256)
+k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int H, int W, int wpr, int band_rows,
+              MorphChain ch) {
+    extern __shared__ __align__(128) uint32_t smem[];
+    const int ext_rows = band_rows + ch.halo_top + ch.halo_bot;
+    uint32_t* A = smem;
+    uint32_t* B = smem + (size_t)ext_rows * wpr;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)ext_rows * wpr);
+    const int y0 = blockIdx.x * band_rows;                    // first output row of this band
+    const int ey0 = y0 - ch.halo_top;                         // image row of ext row 0
+    const size_t plane_words = (size_t)H * wpr;
+    const uint32_t* sp = src + (size_t)blockIdx.y * plane_words;
+    uint32_t* dp = dst + (size_t)blockIdx.y * plane_words;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int nwords = ext_rows * wpr;
+
+    // stage rows [max(ey0,0), min(ey0+ext_rows,H)) with one bulk copy (rows are contiguous in the plane)
+    const int r_lo = max(0, -ey0), r_hi = min(ext_rows, H - ey0);     // ext rows that exist in the image
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < nwords; i += nt) {
+        const int r = i / wpr;
+        if (r < r_lo || r >= r_hi) A[i] = 0u;
+    }
+    __syncthreads();
+    if (tid == 0 && r_hi > r_lo) {
+        const uint32_t bytes = (uint32_t)(r_hi - r_lo) * wpr * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(A + (size_t)r_lo * wpr)), "l"(sp + (size_t)(ey0 + r_lo) * wpr), "r"(bytes),
+                       "r"(smem_u32(bar)) : "memory");
+    }
+    if (r_hi > r_lo) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+        }
+    }
+    __syncthreads();
+
+    for (int pi = 0; pi < ch.n; ++pi) {
+        const MorphPrim& P = ch.p[pi];
+        if (P.erode) {      // complement inside the image (outside stays 0 = ignored)
+            for (int i = tid; i < nwords; i += nt) {
+                const int r = i / wpr, j = i - r * wpr;
+                A[i] = (r >= r_lo && r < r_hi) ? (~A[i] & valid_mask(j, W)) : 0u;
+            }
+            __syncthreads();
+        }
+        if (P.separable) {
+            const int lo = P.lo[0], hi = P.hi[0];
+            for (int i = tid; i < nwords; i += nt) {            // horizontal: A -> B
+                const int r = i / wpr, j = i - r * wpr;
+                const uint32_t* row = A + (size_t)r * wpr;
+                B[i] = hrun_or(j > 0 ? row[j - 1] : 0u, row[j], j + 1 < wpr ? row[j + 1] : 0u, lo, hi) & valid_mask(j, W);
+            }
+            __syncthreads();
+            const int dy0 = P.dy[0], dy1 = P.dy[P.nrows - 1];
+            for (int i = tid; i < nwords; i += nt) {            // vertical: B -> A
+                const int r = i / wpr, j = i - r * wpr;
+                uint32_t acc = 0;
+                for (int d = dy0; d <= dy1; ++d) {
+                    const int rr = r + d;
+                    if (rr >= 0 && rr < ext_rows) acc |= B[(size_t)rr * wpr + j];
+                }
+                A[i] = (r >= r_lo && r < r_hi) ? acc : 0u;      // rows outside the image stay 'ignored'
+            }
+            __syncthreads();
+        } else {
+            for (int i = tid; i < nwords; i += nt) {            // generic: A -> B
+                const int r = i / wpr, j = i - r * wpr;
+                uint32_t acc = 0;
+                for (int k = 0; k < P.nrows; ++k) {
+                    const int rr = r + P.dy[k];
+                    if (rr < 0 || rr >= ext_rows) continue;
+                    const uint32_t* row = A + (size_t)rr * wpr;
+                    acc |= hrun_or(j > 0 ? row[j - 1] : 0u, row[j], j + 1 < wpr ? row[j + 1] : 0u, P.lo[k], P.hi[k]);
+                }
+                B[i] = (r >= r_lo && r < r_hi) ? (acc & valid_mask(j, W)) : 0u;
+            }
+            __syncthreads();
+            for (int i = tid; i < nwords; i += nt) A[i] = B[i];
+            __syncthreads();
+        }
+        if (P.erode) {
+            for (int i = tid; i < nwords; i += nt) {
+                const int r = i / wpr, j = i - r * wpr;
+                A[i] = (r >= r_lo && r < r_hi) ? (~A[i] & valid_mask(j, W)) : 0u;
+            }
+            __syncthreads();
+        }
+    }
+    // write the band
+    const int out_rows = min(band_rows, H - y0);
+    for (int i = tid; i < out_rows * wpr; i += nt) dp[(size_t)y0 * wpr + i] = A[(size_t)ch.halo_top * wpr + i];
+}
+
+}  // namespace dvc

@@ -425,3 +425,48 @@ def overlay_paint(bgr: np.ndarray, acc_mask: np.ndarray) -> np.ndarray:
     ov = bgr.copy()
     ov[acc_mask > 127] = (0, 0, 255)
     return ov
+
+
+# ----------------------------------------------------------------------------
+# closed form of cv2's float32 4-point DCT (recovered by search)
+# ----------------------------------------------------------------------------
+_C1 = np.float32(np.cos(np.pi / 8) / np.sqrt(2.0))
+_C3 = np.float32(np.cos(3 * np.pi / 8) / np.sqrt(2.0))
+_H = np.float32(0.5)
+
+
+def _fma(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64."""
+    return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)
+
+
+def dct4_rows_closed_form(x: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """The 1-D 4-point transform cv2.dct(..., DCT_ROWS) applies to each row of a float32 [N, 4] array, as
+    an explicit float32 operation sequence.  The CUDA kernel (csrc/k_degrade.cuh dct4_fwd / dct4_inv) is the
+    same sequence."""
+    x = np.asarray(x, np.float32)
+    x0, x1, x2, x3 = x[:, 0], x[:, 1], x[:, 2], x[:, 3]
+    if not inverse:
+        s0, s1, d0, d1 = x0 + x3, x1 + x2, x0 - x3, x1 - x2
+        y0 = (s0 + s1) * _H
+        y2 = (s0 - s1) * _H
+        y1 = _fma(d1, _C3, (_C1 * d0).astype(np.float32))
+        y3 = _fma(d0, _C3, -(_C1 * d1).astype(np.float32))
+        return np.stack([y0, y1, y2, y3], axis=1).astype(np.float32)
+    e0, e1 = (x0 + x2) * _H, (x0 - x2) * _H
+    o0 = _fma(x3, _C3, (_C1 * x1).astype(np.float32))
+    o1 = _fma(x1, _C3, -(_C1 * x3).astype(np.float32))
+    return np.stack([e0 + o0, e1 + o1, e1 - o1, e0 - o0], axis=1).astype(np.float32)
+
+
+def cv2_dct4_matches_closed_form(n: int = 20000) -> bool:
+    """Does this host's cv2 (its IPP code path depends on the CPU) agree bit for bit with the closed form?"""
+    import cv2
+    rng = np.random.default_rng(777)
+    x = (rng.standard_normal((n, 4)) * 60).astype(np.float32)
+    xi = rng.integers(-128, 128, (n, 4)).astype(np.float32)
+    ok = True
+    for arr in (x, xi):
+        ok &= np.array_equal(cv2.dct(arr, flags=cv2.DCT_ROWS), dct4_rows_closed_form(arr))
+        ok &= np.array_equal(cv2.dct(arr, flags=cv2.DCT_ROWS | cv2.DCT_INVERSE), dct4_rows_closed_form(arr, True))
+    return bool(ok)

@@ -1,0 +1,62 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/dvc_b200.h declares.  No compute call is made (there is no GPU here and no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dynamic_video_compression_surveillance_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from dynamic_video_compression_surveillance_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "dvc_b200.h")).read()
+    declared = set(re.findall(r"\b(dvc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_abi_version_and_defaults(lib):
+    from dynamic_video_compression_surveillance_b200._lib import DvcConfig
+    assert lib.dvc_abi_version() == 1
+    cfg = DvcConfig()
+    lib.dvc_default_config(ctypes.byref(cfg))
+    # the reference's defaults (frame_differencing.py:21-30; motion_compression_opt.py:29-31)
+    assert (cfg.block_size, cfg.kernel_size, cfg.window_size, cfg.morph_kernel) == (4, 7, 30, 2)
+    assert abs(cfg.motion_threshold - 0.5) < 1e-9 and cfg.min_area == 500 and cfg.release_factor == 0.5
+    assert cfg.quantization_level == 100 and cfg.alpha_fraction == 0.2
+
+
+def test_no_silent_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dynamic_video_compression_surveillance_b200 import pipeline
+    with pytest.raises(RuntimeError):
+        pipeline.FramePipeline(64, 64)
+    from dynamic_video_compression_surveillance_b200._lib import DvcConfig
+    cfg = DvcConfig()
+    lib.dvc_default_config(ctypes.byref(cfg))
+    cfg.width = cfg.height = 64
+    h = ctypes.c_void_p()
+    assert lib.dvc_create(ctypes.byref(cfg), ctypes.byref(h)) < 0
+    assert b"no CUDA device" in lib.dvc_last_error(None)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dynamic_video_compression_surveillance_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)

@@ -1,0 +1,351 @@
+"""GPU parity: every kernel behind the C ABI against the CPU oracle (run on the B200 box, `-m gpu`).
+
+Bar (BASELINE.json north_star): masks bit-exact; frames bit-exact where the reference uses integer OpenCV
+ops; DCT-degraded blocks bit-exact when this host's cv2 follows the recovered float32 sequence, otherwise
+within 1 grey level away from exact quantiser ties.
+"""
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from oracle import loops, stage_ops as so
+from tests.golden_util import FD_FIXTURES, load_fd, sha, unpack
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(1, 1), (1, 7), (5, 1), (2, 2), (3, 5), (17, 33), (48, 64), (101, 67), (96, 256), (130, 400)]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def P():
+    from dynamic_video_compression_surveillance_b200 import pipeline
+    return pipeline
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_bgr2gray(P, shape):
+    img = rng(1).integers(0, 256, (3,) + shape + (3,), dtype=np.uint8)
+    got = host(P.bgr2gray(dev(img)))
+    for i in range(3):
+        assert np.array_equal(got[i], so.bgr2gray(img[i]))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("blur5", [False, True])
+def test_gray_absdiff_thresh(P, shape, blur5):
+    r = rng(2)
+    n = 11
+    base = r.integers(0, 256, shape + (3,), dtype=np.uint8)
+    frames = np.stack([base.copy() for _ in range(n)])
+    for t in range(n):                                   # sparse changes so masks are not trivially full
+        m = r.random(shape) < 0.2
+        frames[t][m] = r.integers(0, 256, (int(m.sum()), 3), dtype=np.uint8)
+    prev = r.integers(0, 256, shape, dtype=np.uint8)
+    for thr in (0.5, 3.0):
+        gray, mask = P.gray_absdiff_thresh(dev(frames), dev(prev), thr, blur5)
+        gray, mask = host(gray), host(mask)
+        p = prev
+        for t in range(n):
+            g = so.bgr2gray(frames[t])
+            if blur5:
+                g = so.gaussian_blur5(g)
+            assert np.array_equal(gray[t], g), (t, "gray")
+            assert np.array_equal(mask[t], so.threshold_binary(so.absdiff(p, g), thr)), (t, "mask")
+            p = g
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (17, 33), (48, 70), (101, 130), (64, 300)])
+@pytest.mark.parametrize("kind,k", [("rect", 1), ("rect", 2), ("rect", 3), ("rect", 7), ("rect", 10), ("rect", 15),
+                                    ("rect", 33), ("ellipse", 2), ("ellipse", 3), ("ellipse", 5), ("ellipse", 9)])
+def test_morphology(P, shape, kind, k):
+    r = rng(5)
+    kernel = so.structuring_rect(k) if kind == "rect" else so.structuring_ellipse(k)
+    masks = np.stack([(r.random(shape) < d).astype(np.uint8) * 255 for d in (0.02, 0.5, 0.97, 0.0, 1.0)])
+    d = dev(masks)
+    for op, fn in (("dilate", so.dilate), ("erode", so.erode), ("close", so.morph_close), ("open", so.morph_open)):
+        got = host(P.morph(d, op, k, kind))
+        for i in range(len(masks)):
+            assert np.array_equal(got[i], fn(masks[i], kernel)), (op, i)
+
+
+def test_morphology_tall_image_bands(P):
+    r = rng(6)
+    masks = np.stack([(r.random((1200, 96)) < d).astype(np.uint8) * 255 for d in (0.01, 0.6)])
+    for kind, k in (("rect", 15), ("ellipse", 7)):
+        kernel = so.structuring_rect(k) if kind == "rect" else so.structuring_ellipse(k)
+        got = host(P.morph(dev(masks), "close", k, kind))
+        for i in range(2):
+            assert np.array_equal(got[i], cv2.morphologyEx(masks[i], cv2.MORPH_CLOSE, kernel))
+
+
+@pytest.mark.parametrize("alpha,K", [(0.2, 30), (0.2, 5), (0.5, 4), (0.34, 7), (1.0, 3), (0.0, 3), (0.2, 1), (0.9, 31)])
+def test_temporal_ring(P, alpha, K):
+    r = rng(7)
+    n, shape = 70, (37, 83)
+    masks = np.stack([(r.random(shape) < 0.3).astype(np.uint8) * 255 for _ in range(n)])
+    got = host(P.temporal_ring(dev(masks), K, alpha))
+    for t in range(n):
+        ref = so.window_vote(list(masks[max(0, t - K + 1):t + 1]), alpha)
+        assert np.array_equal(got[t], ref), t
+
+
+@pytest.mark.parametrize("rf", [0.5, 0.3, 0.1, 0.7, 0.9, 1 / 3])
+def test_temporal_ema(P, rf):
+    r = rng(8)
+    n, shape = 40, (33, 70)
+    dil = np.stack([(r.random(shape) < 0.4).astype(np.uint8) * 255 for _ in range(n)])
+    acc0 = r.integers(0, 256, shape, dtype=np.uint8)
+    acc = dev(acc0.copy())
+    got = host(P.temporal_ema(acc, dev(dil), rf))
+    a = acc0
+    for t in range(n):
+        a = cv2.addWeighted(a, rf, dil[t], 1 - rf, 0)
+        assert np.array_equal(got[t], a), t
+    assert np.array_equal(host(acc), a)
+
+
+def test_temporal_ema_all_accumulator_values(P):
+    a0 = np.tile(np.arange(256, dtype=np.uint8), (2, 1))           # [2,256]: row 0 sees dil=0, row 1 dil=255
+    dil = np.stack([np.stack([np.zeros(256, np.uint8), np.full(256, 255, np.uint8)])])
+    for rf in (0.5, 0.3, 0.05, 0.95, 0.7):
+        acc = dev(a0.copy())
+        got = host(P.temporal_ema(acc, dev(dil), rf))[0]
+        assert np.array_equal(got, cv2.addWeighted(a0, rf, dil[0], 1 - rf, 0)), rf
+
+
+def _blob_mask(r, shape, n):
+    m = np.zeros(shape, np.uint8)
+    h, w = shape
+    for _ in range(n):
+        kind = r.integers(0, 3)
+        cx, cy = int(r.integers(0, w)), int(r.integers(0, h))
+        if kind == 0:
+            cv2.circle(m, (cx, cy), int(r.integers(1, 25)), 255, int(r.choice([-1, 1, 2, 3])))
+        elif kind == 1:
+            cv2.rectangle(m, (cx, cy), (cx + int(r.integers(1, 40)), cy + int(r.integers(1, 40))), 255, int(r.choice([-1, 1, 2])))
+        else:
+            cv2.line(m, (cx, cy), (int(r.integers(0, w)), int(r.integers(0, h))), 255, int(r.integers(1, 4)))
+    noise = r.random(shape) < 0.02
+    m[noise] = 255 - m[noise]
+    return m
+
+
+@pytest.mark.parametrize("shape", [(96, 128), (61, 83), (120, 160), (32, 200), (7, 5), (1, 40)])
+def test_contour_filter(P, shape):
+    r = rng(9)
+    masks = [_blob_mask(r, shape, int(r.integers(1, 12))) for _ in range(10)]
+    masks += [(r.random(shape) < d).astype(np.uint8) * 255 for d in (0.3, 0.5, 0.6, 0.8, 0.0, 1.0)]
+    masks = np.stack(masks)
+    for min_area in (0, 5, 20, 100, 500):
+        got = host(P.contour_filter(dev(masks), min_area))
+        for i in range(len(masks)):
+            assert np.array_equal(got[i], so.contour_filter_cv2(masks[i], min_area)), (i, min_area)
+
+
+def test_contour_filter_1080p_blobs(P):
+    r = rng(10)
+    m = np.zeros((1080, 1920), np.uint8)
+    for _ in range(60):
+        cx, cy = int(r.integers(0, 1920)), int(r.integers(0, 1080))
+        cv2.ellipse(m, (cx, cy), (int(r.integers(3, 120)), int(r.integers(3, 80))), float(r.integers(0, 180)), 0, 360, 255,
+                    int(r.choice([-1, 2, 5])))
+    noise = r.random(m.shape) < 0.01
+    m[noise] = 255 - m[noise]
+    got = host(P.contour_filter(dev(m[None]), 500))[0]
+    assert np.array_equal(got, so.contour_filter_cv2(m, 500))
+
+
+def _check_degraded(got, ref, frame, acc, bs, q, exact):
+    """Integer pixels must match; DCT blocks exactly (exact=True) or within 1 LSB away from ties."""
+    if exact:
+        assert np.array_equal(got, ref)
+        return
+    static = so.block_all_zero(acc, bs)
+    h, w = acc.shape
+    st_px = np.repeat(np.repeat(static, bs, 0), bs, 1)[:h, :w]
+    assert np.array_equal(got[~st_px], ref[~st_px])
+    ycc = so.bgr2ycrcb(frame)
+    tie = so.tie_blocks(ycc[..., 0], static, bs, q)
+    tie_px = np.repeat(np.repeat(tie, bs, 0), bs, 1)[:h, :w]
+    d = np.abs(got.astype(int) - ref.astype(int))
+    assert d[st_px & ~tie_px].max(initial=0) <= 1
+    assert (d[st_px & ~tie_px] > 0).mean() < 0.02
+
+
+@pytest.mark.parametrize("shape,bs", [((48, 64), 4), ((96, 128), 4), ((44, 60), 4), ((48, 64), 8), ((40, 72), 8)])
+def test_degrade_fd(P, shape, bs):
+    r = rng(11)
+    exact = bs == 4 and so.cv2_dct4_matches_closed_form()
+    frames = r.integers(0, 256, (3,) + shape + (3,), dtype=np.uint8)
+    frames[1] = (frames[1] // 16) * 16                                    # flatter content: DC-dominated blocks
+    frames[2, :, :, :] = np.linspace(0, 255, shape[1], dtype=np.uint8)[None, :, None]
+    acc = np.zeros((3,) + shape, np.uint8)
+    acc[:, 10:30, 20:40] = r.integers(0, 256, (3, 20, 20), dtype=np.uint8)
+    acc[1, 5, 7] = 1
+    cnt = torch.zeros(5, dtype=torch.int64, device="cuda")
+    comp, ov = P.degrade_blend(dev(frames), dev(acc), bs, 100, "fd", True, cnt)
+    comp, ov = host(comp), host(ov)
+    n_static = 0
+    for i in range(3):
+        assert np.array_equal(ov[i], so.overlay_paint(frames[i], acc[i]))
+        _check_degraded(comp[i], so.degrade_fd(frames[i], acc[i], bs, 100), frames[i], acc[i], bs, 100, exact)
+        n_static += int(so.block_all_zero(acc[i], bs).sum())
+    c = host(cnt)
+    assert c[0] == 3 and c[1] == 3 * shape[0] * shape[1]
+    assert c[2] == int((acc > 127).sum())
+    assert c[3] == 3 * (shape[0] // bs) * (shape[1] // bs) and c[4] == n_static
+
+
+def test_degrade_mco(P):
+    r = rng(12)
+    shape = (64, 96)
+    frames = r.integers(0, 256, (2,) + shape + (3,), dtype=np.uint8)
+    masks = np.zeros((2,) + shape, np.uint8)
+    masks[0, 8:40, 16:50] = 255
+    masks[1, 3, 90] = 3
+    comp, _ = P.degrade_blend(dev(frames), dev(masks), 8, 100, "mco", False)
+    comp = host(comp)
+    for i in range(2):
+        ref = so.degrade_mco(frames[i], masks[i])
+        static = so.block_all_zero(masks[i], 8, full_blocks_only=True)
+        st_px = np.repeat(np.repeat(static, 8, 0), 8, 1)
+        assert np.array_equal(comp[i][~st_px], ref[~st_px])
+        d = np.abs(comp[i].astype(int) - ref.astype(int))[st_px]
+        # three quantised channels feed one grey value: allow 2 LSB off ties, report the rest
+        assert np.mean(d <= 2) > 0.97, np.mean(d <= 2)
+
+
+def test_unsupported_is_loud(P):
+    from dynamic_video_compression_surveillance_b200._lib import DvcUnsupported
+    frames = torch.zeros((1, 30, 50, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(DvcUnsupported):
+        P.degrade_blend(frames, torch.zeros((1, 30, 50), dtype=torch.uint8, device="cuda"), 4, 100, "fd")
+    with pytest.raises(NotImplementedError):
+        P.FramePipeline(64, 64, "fd", block_size=6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole loop
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", FD_FIXTURES)
+@pytest.mark.parametrize("max_batch", [4, 16])
+def test_fd_loop_against_reference_fixture(P, name, max_batch):
+    """The fd-exact loop against outputs of the UNMODIFIED reference (tests/golden/*.npz)."""
+    z, frames, kw, (h, w, n) = load_fd(name)
+    bs = kw.get("block_size", 4)
+    exact = bs == 4 and so.cv2_dct4_matches_closed_form()
+    pipe = P.FramePipeline(w, h, "fd", max_batch=max_batch, **kw)
+    pipe.begin_stream(loops.first_frame_gray_fd(frames[0]))
+    ov = np.empty((n - 1, h, w, 3), np.uint8)
+    cp = np.empty_like(ov)
+    acc = np.empty((n - 1, h, w), np.uint8)
+    pipe.process_host(np.ascontiguousarray(frames[1:]), ov, cp, acc)
+    assert np.array_equal(acc, z["acc"])
+    assert [sha(x) for x in ov] == list(z["overlay_sha"])
+    if exact:
+        assert [sha(x) for x in cp] == list(z["compressed_sha"])
+    assert np.array_equal(ov[-2:], z["overlay_tail"])
+    for i in (-2, -1):
+        _check_degraded(cp[i], z["compressed_tail"][i], frames[n + i], z["acc"][i], bs, kw.get("quantization_level", 100), exact)
+    c = pipe.counters()
+    assert c["frames"] == n - 1 and c["motion_pixels"] == int((z["acc"] > 127).sum())
+    pipe.close()
+
+
+@pytest.mark.parametrize("cfg", [dict(window_size=5, alpha_fraction=0.2, morph_kernel=2, kernel_size=7),
+                                 dict(window_size=30, alpha_fraction=0.2, morph_kernel=2, kernel_size=0),
+                                 dict(window_size=4, alpha_fraction=0.5, morph_kernel=3, morph_shape="rect", kernel_size=15),
+                                 dict(window_size=7, alpha_fraction=0.34, morph_kernel=0, kernel_size=3)])
+@pytest.mark.parametrize("noise", [False, True])
+def test_window_loop_against_oracle(P, cfg, noise):
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n = 120, 176, 45
+    frames = make_clip((h, w), n, seed=5, temporal_noise=noise).frames()
+    thr = 6.0 if noise else 0.5
+    ref = loops.window_loop(list(frames), motion_threshold=thr, **cfg)
+    pipe = P.FramePipeline(w, h, "window", motion_threshold=thr, max_batch=8, **cfg)
+    pipe.begin_stream(so.bgr2gray(frames[0]))
+    d_frames = dev(frames[1:])
+    ov = torch.empty_like(d_frames); cp = torch.empty_like(d_frames)
+    mk = torch.empty(d_frames.shape[:3], dtype=torch.uint8, device="cuda")
+    for i in range(0, n - 1, 8):
+        pipe.process_device(d_frames[i:i + 8], ov[i:i + 8], cp[i:i + 8], mk[i:i + 8])
+    torch.cuda.synchronize()
+    ov, cp, mk = host(ov), host(cp), host(mk)
+    exact = so.cv2_dct4_matches_closed_form()
+    for t in range(n - 1):
+        assert np.array_equal(mk[t], ref["mask"][t]), t
+        assert np.array_equal(ov[t], ref["overlay"][t]), t
+        _check_degraded(cp[t], ref["compressed"][t], frames[t + 1], ref["mask"][t], 4, 100, exact)
+    pipe.close()
+
+
+def test_state_handoff_between_handles(P):
+    """Frame-chunk sharding: a second handle continues a stream from a state blob."""
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n = 96, 128, 31
+    frames = make_clip((h, w), n, seed=8).frames()
+    for mode, kw in (("fd", {}), ("window", dict(window_size=5))):
+        seed = loops.first_frame_gray_fd(frames[0]) if mode == "fd" else so.bgr2gray(frames[0])
+        whole = P.FramePipeline(w, h, mode, max_batch=8, **kw)
+        whole.begin_stream(seed)
+        cp_ref = np.empty((n - 1, h, w, 3), np.uint8); mk_ref = np.empty((n - 1, h, w), np.uint8)
+        whole.process_host(np.ascontiguousarray(frames[1:]), None, cp_ref, mk_ref)
+        a = P.FramePipeline(w, h, mode, max_batch=8, **kw)
+        b = P.FramePipeline(w, h, mode, max_batch=8, **kw)
+        a.begin_stream(seed)
+        cp = np.empty_like(cp_ref); mk = np.empty_like(mk_ref)
+        cut = 13
+        a.process_host(np.ascontiguousarray(frames[1:1 + cut]), None, cp[:cut], mk[:cut])
+        b.set_state(a.get_state())
+        b.process_host(np.ascontiguousarray(frames[1 + cut:]), None, cp[cut:], mk[cut:])
+        assert np.array_equal(mk, mk_ref), mode
+        assert np.array_equal(cp, cp_ref), mode
+        for p in (whole, a, b):
+            p.close()
+
+
+def test_full_size_properties_1080p(P):
+    """At BASELINE's 1080p size the oracle is too slow for every frame: check size-independent properties and
+    spot-check two frames against the oracle."""
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n = 1080, 1920, 17
+    frames = make_clip("1080p", n, seed=0).frames()
+    cfg = dict(window_size=5, alpha_fraction=0.2, morph_kernel=2, kernel_size=7)
+    pipe = P.FramePipeline(w, h, "window", max_batch=16, **cfg)
+    pipe.begin_stream(so.bgr2gray(frames[0]))
+    d = dev(frames[1:])
+    ov = torch.empty_like(d); cp = torch.empty_like(d)
+    mk = torch.empty(d.shape[:3], dtype=torch.uint8, device="cuda")
+    pipe.process_device(d, ov, cp, mk)
+    torch.cuda.synchronize()
+    ov, cp, mk = host(ov), host(cp), host(mk)
+    assert set(np.unique(mk)) <= {0, 255}
+    moving = mk > 127
+    # overlay is the frame except where the mask says motion, where it is pure red
+    assert np.array_equal(ov[~moving], frames[1:][~moving])
+    assert (ov[moving] == np.array([0, 0, 255], np.uint8)).all()
+    # static blocks come out grey (B == G == R); the counters agree with the mask
+    static_px = np.repeat(np.repeat(~(mk.reshape(n - 1, h // 4, 4, w // 4, 4) != 0).any(axis=(2, 4)), 4, 1), 4, 2)
+    assert (cp[static_px][:, 0] == cp[static_px][:, 1]).all() and (cp[static_px][:, 1] == cp[static_px][:, 2]).all()
+    c = pipe.counters()
+    assert c["motion_pixels"] == int(moving.sum()) and c["static_blocks"] == int(static_px.sum()) // 16
+    ref = loops.window_loop(list(frames[:8]), **cfg)
+    exact = so.cv2_dct4_matches_closed_form()
+    for t in (2, 6):
+        assert np.array_equal(mk[t], ref["mask"][t])
+        _check_degraded(cp[t], ref["compressed"][t], frames[t + 1], ref["mask"][t], 4, 100, exact)
+    pipe.close()
