@@ -133,10 +133,18 @@ static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, 
         g_morph_smem_limit = lim;
     }
     const int halo = ch.halo_top + ch.halo_bot;
-    // band height: as tall as fits in ~96 KB (two planes), at least 8 rows beyond the halo
-    const size_t budget = std::min<size_t>((size_t)g_morph_smem_limit - 64, 96 * 1024);
-    int band = (int)(budget / (2 * (size_t)wpr * 4)) - halo;
-    if (band < 8) band = (int)(((size_t)g_morph_smem_limit - 64) / (2 * (size_t)wpr * 4)) - halo;
+    for (int i = 0; i < ch.n; ++i)
+        for (int k = 0; k < ch.p[i].nrows; ++k)
+            if (ch.p[i].lo[k] > 0 || ch.p[i].hi[k] < 0)
+                return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "structuring element row that does not span its anchor column");
+    if (wpr > 256) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "frames wider than 8192 pixels are not supported by the morphology kernel");
+    // Band height: ~36 KB of shared memory per CTA (two planes) keeps ~6 CTAs resident per SM; chains with a
+    // large halo get bands at least twice the halo so the redundant rows stay under a third.
+    const size_t row_bytes = 2 * (size_t)wpr * 4;
+    const size_t limit = (size_t)g_morph_smem_limit - 64;
+    int band = (int)(36 * 1024 / row_bytes) - halo;
+    band = std::max(band, std::max(16, 2 * halo));
+    band = std::min<int>(band, (int)(limit / row_bytes) - halo);
     if (band < 1) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "morphology chain halo %d rows x %d words does not fit in shared memory", halo, wpr);
     band = std::min(band, H);
     const int nbands = (H + band - 1) / band;

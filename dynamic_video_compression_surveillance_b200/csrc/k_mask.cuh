@@ -53,7 +53,7 @@ k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int
     for (long long f = max(0LL, fs - K + 1); f < fs; ++f) bs_add(c, ring[(size_t)(f % ring_cap) * plane_words + idx]);
     for (int t = t0; t < t1; ++t) {
         const long long f = f0 + t;
-        if (f - K >= 0) bs_sub(c, ring[(size_t)((f - K) % ring_cap) * plane_words + idx]);
+        if (t > t0 && f - K >= 0) bs_sub(c, ring[(size_t)((f - K) % ring_cap) * plane_words + idx]);
         bs_add(c, ring[(size_t)(f % ring_cap) * plane_words + idx]);
         const int L = (int)min((long long)K, f + 1);
         voted[(size_t)t * plane_words + idx] = bs_ge(c, mc.v[L - 1]) & vm;
@@ -156,21 +156,34 @@ struct MorphChain {
     MorphPrim p[MORPH_MAX_PRIMS];
 };
 
-// OR over column offsets [lo, hi] of one bit row: out(x) = OR_d in(x + d).  -32 <= lo <= hi <= 32,
-// hi - lo + 1 <= 33.  Works on the 96-bit window (prev | cur | next) and log-doubles the OR.
+// OR over column offsets [lo, hi] of one bit row: out(x) = OR_d in(x + d), lo <= 0 <= hi, both within
+// +-32.  Pixels to the right are higher bits: the right reach works on (next:cur), the left reach on
+// (cur:prev), each log-doubled on a 64-bit value.
 DEVI uint32_t hrun_or(uint32_t prev, uint32_t cur, uint32_t next, int lo, int hi) {
-    const unsigned __int128 v = (unsigned __int128)prev | ((unsigned __int128)cur << 32) | ((unsigned __int128)next << 64);
-    uint64_t r = (uint64_t)(v >> (32 + lo));
-    const int n = hi - lo + 1;
-    int c = 1;
-    while (2 * c <= n) { r |= r >> c; c *= 2; }
-    if (c < n) r |= r >> (n - c);
-    return (uint32_t)r;
+    uint32_t res = cur;
+    if (hi > 0) {
+        uint64_t a = ((uint64_t)next << 32) | cur;
+        int c = 1;
+        const int n = hi + 1;
+        while (2 * c <= n) { a |= a >> c; c *= 2; }
+        if (c < n) a |= a >> (n - c);
+        res |= (uint32_t)a;
+    }
+    if (lo < 0) {
+        uint64_t b = ((uint64_t)cur << 32) | prev;
+        int c = 1;
+        const int n = 1 - lo;
+        while (2 * c <= n) { b |= b << c; c *= 2; }
+        if (c < n) b |= b << (n - c);
+        res |= (uint32_t)(b >> 32);
+    }
+    return res;
 }
 
 DEVI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// grid: (bands, n_images); dynamic smem: 2 planes of ext_rows x wpr words + one mbarrier
+// grid: (bands, n_images); dynamic smem: 2 planes of ext_rows x wpr words + one mbarrier.
+// Thread t owns word column (t % wpr) of rows (t / wpr), (t / wpr) + rows_per_pass, ...
 __global__ void __launch_bounds__(256)
 k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int H, int W, int wpr, int band_rows,
               MorphChain ch) {
@@ -186,6 +199,11 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
     uint32_t* dp = dst + (size_t)blockIdx.y * plane_words;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nwords = ext_rows * wpr;
+    // column-major-in-thread mapping without a division per element
+    const int rows_per_pass = nt / wpr;                       // >= 1 (host guarantees wpr <= blockDim)
+    const int j = tid % wpr, r_first = tid / wpr;
+    const bool lane_on = r_first < rows_per_pass;
+    const uint32_t vm = valid_mask(j, W);
 
     // stage rows [max(ey0,0), min(ey0+ext_rows,H)) with one bulk copy (rows are contiguous in the plane)
     const int r_lo = max(0, -ey0), r_hi = min(ext_rows, H - ey0);     // ext rows that exist in the image
@@ -194,76 +212,72 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < nwords; i += nt) {
-        const int r = i / wpr;
-        if (r < r_lo || r >= r_hi) A[i] = 0u;
+        if (i < r_lo * wpr || i >= r_hi * wpr) A[i] = 0u;
     }
     __syncthreads();
-    if (tid == 0 && r_hi > r_lo) {
+    if (tid == 0) {
         const uint32_t bytes = (uint32_t)(r_hi - r_lo) * wpr * 4u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(A + (size_t)r_lo * wpr)), "l"(sp + (size_t)(ey0 + r_lo) * wpr), "r"(bytes),
                        "r"(smem_u32(bar)) : "memory");
     }
-    if (r_hi > r_lo) {
+    {
         uint32_t done = 0;
         while (!done) {
             asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
                          : "=r"(done) : "r"(smem_u32(bar)) : "memory");
         }
     }
-    __syncthreads();
 
+    // Erosion runs as NOT dilate NOT: the complement is folded into the first read and the last write of the
+    // primitive.  Rows outside the image and bits beyond W are 'ignored' pixels: they read as 0 in the
+    // dilation domain of either polarity.
     for (int pi = 0; pi < ch.n; ++pi) {
         const MorphPrim& P = ch.p[pi];
-        if (P.erode) {      // complement inside the image (outside stays 0 = ignored)
-            for (int i = tid; i < nwords; i += nt) {
-                const int r = i / wpr, j = i - r * wpr;
-                A[i] = (r >= r_lo && r < r_hi) ? (~A[i] & valid_mask(j, W)) : 0u;
-            }
-            __syncthreads();
-        }
+        const uint32_t flip = P.erode ? 0xffffffffu : 0u;
         if (P.separable) {
             const int lo = P.lo[0], hi = P.hi[0];
-            for (int i = tid; i < nwords; i += nt) {            // horizontal: A -> B
-                const int r = i / wpr, j = i - r * wpr;
-                const uint32_t* row = A + (size_t)r * wpr;
-                B[i] = hrun_or(j > 0 ? row[j - 1] : 0u, row[j], j + 1 < wpr ? row[j + 1] : 0u, lo, hi) & valid_mask(j, W);
-            }
+            if (lane_on)
+                for (int r = r_first; r < ext_rows; r += rows_per_pass) {      // horizontal: A -> B
+                    const uint32_t* row = A + (size_t)r * wpr;
+                    const bool in_img = r >= r_lo && r < r_hi;
+                    const uint32_t pm = j > 0 ? valid_mask(j - 1, W) : 0u, nm = j + 1 < wpr ? valid_mask(j + 1, W) : 0u;
+                    const uint32_t p = in_img && j > 0 ? (row[j - 1] ^ flip) & pm : 0u;
+                    const uint32_t c = in_img ? (row[j] ^ flip) & vm : 0u;
+                    const uint32_t n = in_img && j + 1 < wpr ? (row[j + 1] ^ flip) & nm : 0u;
+                    B[(size_t)r * wpr + j] = hrun_or(p, c, n, lo, hi) & vm;
+                }
             __syncthreads();
             const int dy0 = P.dy[0], dy1 = P.dy[P.nrows - 1];
-            for (int i = tid; i < nwords; i += nt) {            // vertical: B -> A
-                const int r = i / wpr, j = i - r * wpr;
-                uint32_t acc = 0;
-                for (int d = dy0; d <= dy1; ++d) {
-                    const int rr = r + d;
-                    if (rr >= 0 && rr < ext_rows) acc |= B[(size_t)rr * wpr + j];
+            if (lane_on)
+                for (int r = r_first; r < ext_rows; r += rows_per_pass) {      // vertical: B -> A
+                    uint32_t acc = 0;
+                    const int ra = max(r + dy0, 0), rb = min(r + dy1, ext_rows - 1);
+                    for (int rr = ra; rr <= rb; ++rr) acc |= B[(size_t)rr * wpr + j];
+                    const bool in_img = r >= r_lo && r < r_hi;
+                    A[(size_t)r * wpr + j] = in_img ? (acc ^ flip) & vm : 0u;
                 }
-                A[i] = (r >= r_lo && r < r_hi) ? acc : 0u;      // rows outside the image stay 'ignored'
-            }
             __syncthreads();
         } else {
-            for (int i = tid; i < nwords; i += nt) {            // generic: A -> B
-                const int r = i / wpr, j = i - r * wpr;
-                uint32_t acc = 0;
-                for (int k = 0; k < P.nrows; ++k) {
-                    const int rr = r + P.dy[k];
-                    if (rr < 0 || rr >= ext_rows) continue;
-                    const uint32_t* row = A + (size_t)rr * wpr;
-                    acc |= hrun_or(j > 0 ? row[j - 1] : 0u, row[j], j + 1 < wpr ? row[j + 1] : 0u, P.lo[k], P.hi[k]);
+            if (lane_on)
+                for (int r = r_first; r < ext_rows; r += rows_per_pass) {      // generic: A -> B
+                    uint32_t acc = 0;
+                    for (int k = 0; k < P.nrows; ++k) {
+                        const int rr = r + P.dy[k];
+                        if (rr < r_lo || rr >= r_hi) continue;
+                        const uint32_t* row = A + (size_t)rr * wpr;
+                        const uint32_t pm = j > 0 ? valid_mask(j - 1, W) : 0u, nm = j + 1 < wpr ? valid_mask(j + 1, W) : 0u;
+                        const uint32_t p = j > 0 ? (row[j - 1] ^ flip) & pm : 0u;
+                        const uint32_t c = (row[j] ^ flip) & vm;
+                        const uint32_t n = j + 1 < wpr ? (row[j + 1] ^ flip) & nm : 0u;
+                        acc |= hrun_or(p, c, n, P.lo[k], P.hi[k]);
+                    }
+                    const bool in_img = r >= r_lo && r < r_hi;
+                    B[(size_t)r * wpr + j] = in_img ? (acc ^ flip) & vm : 0u;
                 }
-                B[i] = (r >= r_lo && r < r_hi) ? (acc & valid_mask(j, W)) : 0u;
-            }
             __syncthreads();
-            for (int i = tid; i < nwords; i += nt) A[i] = B[i];
-            __syncthreads();
-        }
-        if (P.erode) {
-            for (int i = tid; i < nwords; i += nt) {
-                const int r = i / wpr, j = i - r * wpr;
-                A[i] = (r >= r_lo && r < r_hi) ? (~A[i] & valid_mask(j, W)) : 0u;
-            }
-            __syncthreads();
+            uint32_t* t = A; A = B; B = t;
         }
     }
     // write the band
