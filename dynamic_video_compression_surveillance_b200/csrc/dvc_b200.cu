@@ -224,9 +224,15 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
     if (flavour == DVC_DEGRADE_FD && (H % bs || W % bs))
         return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "frame %dx%d is not a multiple of block_size %d (clipped edge blocks are not implemented)", W, H, bs);
     if (n <= 0) return DVC_OK;
-    if (flavour == DVC_DEGRADE_FD && bs == 4 && W % 16 == 0) {
-        dim3 grid(cdiv((size_t)(W / 16) * (H / 4), 128), n);
-        k_degrade4<<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, q, counters);
+    if (flavour == DVC_DEGRADE_FD && bs == 4 && W % 8 == 0) {
+        QuantConsts qc;
+        const float iq = 1.0f / q;
+        qc.k[0] = iq; qc.k[1] = iq * 0.5f; qc.k[2] = iq * 0.25f;
+        qc.o[0] = q; qc.o[1] = q * 0.5f; qc.o[2] = q * 0.25f;
+        qc.q = q;
+        qc.fast = q >= 8.0f && q <= 1.0e6f;
+        dim3 grid(cdiv((size_t)(W / 8) * (H / 4), 256), n);
+        k_degrade4<<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
     } else {
         int rc = ensure_dct8(ERRBUF);
         if (rc) return rc;
@@ -585,7 +591,7 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         h->cur ^= 1;
         dim3 g2(cdiv(h->plane_words, 256), nseg);
         { ProfScope ps(h, DVC_PROF_VOTE, 1, st);
-        k_window_vote<<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, T, h->cfg.window_size, h->min_counts, h->bits_a, h->seg_len);
+        k_window_vote<<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, (int)(h->n_masks % h->ring_cap), T, h->cfg.window_size, h->min_counts, h->bits_a, h->seg_len);
         }
         CHECK_LAUNCH();
         const uint32_t* fin = h->bits_a;
@@ -803,7 +809,7 @@ extern "C" int dvc_temporal_ring_u8(const uint8_t* masks, uint8_t* smoothed, int
     window_min_counts(alpha_fraction, window_size, mc);
     const int seg = 8, nseg = (n + seg - 1) / seg;
     dim3 g(cdiv(pw, 256), nseg);
-    k_window_vote<<<g, 256, 0, st>>>((const uint32_t*)ring.p, n, H, W, wpr, 0, n, window_size, mc, (uint32_t*)voted.p, seg);
+    k_window_vote<<<g, 256, 0, st>>>((const uint32_t*)ring.p, n, H, W, wpr, 0, 0, n, window_size, mc, (uint32_t*)voted.p, seg);
     CHECK_LAUNCH();
     return unpack_from_bits((const uint32_t*)voted.p, smoothed, n, H, W, st);
 }

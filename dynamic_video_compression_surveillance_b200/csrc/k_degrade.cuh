@@ -86,121 +86,189 @@ __global__ void k_counters_add(Counters* c, unsigned long long frames, unsigned 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fast path: block_size 4, W % 16 == 0, H % 4 == 0.  One thread owns 16 pixels x 4 rows = four 4x4
-// blocks = 4 x 48 contiguous bytes: twelve 16-byte loads in flight per thread, twelve (or twenty-four
-// with the overlay) 16-byte streaming stores.  Algorithmic HBM bytes: 3 read + 3 (+3) written per pixel
-// plus 2/8 of mask bits.
-// grid: (ceil(W/16 * H/4 / 128), n_frames)
+// Fast path: block_size 4, W % 8 == 0, H % 4 == 0.  One thread owns 8 pixels x 4 rows = two 4x4 blocks
+// = 4 x 24 contiguous bytes (twelve 8-byte streaming loads in flight, 64 registers -> 32 warps per SM).
+// Algorithmic HBM bytes: 3 read + 3 (+3) written per pixel plus the mask bit-plane(s).
+//
+// Instruction diet for the static-block path (97 % of blocks on surveillance content):
+//  * the x0.5 factors of the DCT butterflies are exact power-of-two scalings, so they are folded into the
+//    quantiser constants instead of being multiplied out (bitwise identical results);
+//  * round(d / q) is computed as magic-number rounding of d * (1/q); only coefficients that land within
+//    1e-3 of a rounding tie (where the float32 division's own rounding can matter) take the exact
+//    IEEE-division path, so the result equals np.round(d / q) always;
+//  * float <-> byte conversions avoid the conversion (XU) pipe: bytes enter as 2^23 + b bit patterns, leave
+//    through a round-down add of 2^23 whose low mantissa byte is floor(v), picked up by PRMT.
+// grid: (ceil(W/8 * H/4 / 256), n_frames)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+struct QuantConsts {
+    float k[3];     // (1/q) * {1, 1/2, 1/4}: forward scale by number of even indices among (row, col)
+    float o[3];     // q * {1, 1/2, 1/4}: output scale (pre-applies the inverse butterflies' x0.5)
+    float q;
+    int fast;       // magic-number path valid (q large enough that |d/q| * 2^-22 << tie band)
+};
+
+// forward 4-point DCT without the x0.5 on outputs 0 and 2 (folded into QuantConsts::k)
+DEVI void dct4_fwd_ns(float& x0, float& x1, float& x2, float& x3) {
+    const float s0 = __fadd_rn(x0, x3), s1 = __fadd_rn(x1, x2);
+    const float d0 = __fsub_rn(x0, x3), d1 = __fsub_rn(x1, x2);
+    x0 = __fadd_rn(s0, s1);
+    x2 = __fsub_rn(s0, s1);
+    x1 = __fmaf_rn(DVC_C3, d1, __fmul_rn(DVC_C1, d0));
+    x3 = __fmaf_rn(DVC_C3, d0, -__fmul_rn(DVC_C1, d1));
+}
+// inverse 4-point DCT whose inputs 0 and 2 arrive pre-multiplied by 0.5 (QuantConsts::o)
+DEVI void dct4_inv_ps(float& x0, float& x1, float& x2, float& x3) {
+    const float e0 = __fadd_rn(x0, x2), e1 = __fsub_rn(x0, x2);
+    const float o0 = __fmaf_rn(DVC_C3, x3, __fmul_rn(DVC_C1, x1));
+    const float o1 = __fmaf_rn(DVC_C3, x1, -__fmul_rn(DVC_C1, x3));
+    x0 = __fadd_rn(e0, o0);
+    x3 = __fsub_rn(e0, o0);
+    x1 = __fadd_rn(e1, o1);
+    x2 = __fsub_rn(e1, o1);
+}
+
+template <int NE>   // NE = number of even indices among (row, col): pending scale 2^-NE
+DEVI float quantise_scaled(float d, const QuantConsts& qc) {
+    const float magic = 12582912.0f;                      // 1.5 * 2^23: add/sub rounds half to even
+    const float t = __fmul_rn(d, qc.k[NE]);
+    float n = __fsub_rn(__fadd_rn(t, magic), magic);
+    if (!qc.fast || fabsf(__fsub_rn(t, n)) > 0.499f)      // near a tie (or tiny q): exact IEEE division
+        n = rintf(__fdiv_rn(__fmul_rn(d, NE == 0 ? 1.0f : (NE == 1 ? 0.5f : 0.25f)), qc.q));
+    return __fmul_rn(n, qc.o[NE]);
+}
+
+DEVI void degrade_block4_fast(float (&v)[4][4], const QuantConsts& qc) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dct4_fwd_ns(v[r][0], v[r][1], v[r][2], v[r][3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dct4_fwd_ns(v[0][c], v[1][c], v[2][c], v[3][c]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if ((r & 1) == 0) {
+            v[r][0] = quantise_scaled<2>(v[r][0], qc); v[r][1] = quantise_scaled<1>(v[r][1], qc);
+            v[r][2] = quantise_scaled<2>(v[r][2], qc); v[r][3] = quantise_scaled<1>(v[r][3], qc);
+        } else {
+            v[r][0] = quantise_scaled<1>(v[r][0], qc); v[r][1] = quantise_scaled<0>(v[r][1], qc);
+            v[r][2] = quantise_scaled<1>(v[r][2], qc); v[r][3] = quantise_scaled<0>(v[r][3], qc);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dct4_inv_ps(v[r][0], v[r][1], v[r][2], v[r][3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dct4_inv_ps(v[0][c], v[1][c], v[2][c], v[3][c]);
+}
+
+// luma - 128 as float without the conversion pipe: (2^23 | y) read as float is 2^23 + y exactly
+DEVI float luma_m128_f(uint32_t b, uint32_t g, uint32_t r) {
+    const uint32_t y = (1868u * b + 9617u * g + 4899u * r + 8192u) >> 14;
+    return __fsub_rn(__uint_as_float(0x4B000000u | y), 8388736.0f);      // 2^23 + 128
+}
+// np.clip(v + 128, 0, 255) stored to uint8: returns a word whose low byte is the result
+DEVI uint32_t out_byte_bits(float v) {
+    const float s = fminf(fmaxf(__fadd_rn(v, 128.0f), 0.0f), 255.0f);
+    return __float_as_uint(__fadd_rd(s, 8388608.0f));                    // 2^23 + floor(s): low mantissa byte
+}
+
+__global__ void __launch_bounds__(256, 4)
 k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127,
            const uint32_t* __restrict__ nonzero, uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay,
-           int H, int W, int wpr, float q, Counters* __restrict__ counters) {
-    const int gpr = W >> 4, nbr = H >> 2;
+           int H, int W, int wpr, QuantConsts qc, Counters* __restrict__ counters) {
+    const int gpr = W >> 3, nbr = H >> 2;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = gid < gpr * nbr;
     unsigned n_motion = 0, n_static = 0;
-    if (active) {
+    if (gid < gpr * nbr) {
         const int br = gid / gpr, gx = gid - br * gpr;
         const size_t frame_off = (size_t)blockIdx.y * H * W * 3;
         const size_t plane_off = (size_t)blockIdx.y * H * wpr;
-        const size_t base = frame_off + ((size_t)(br * 4) * W + (size_t)gx * 16) * 3;
+        const size_t base = frame_off + ((size_t)(br * 4) * W + (size_t)gx * 8) * 3;
         const size_t pitch = (size_t)W * 3;
-        uint32_t w[4][12];
+        uint32_t w[4][6];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            load16_cs(frames + base + r * pitch, &w[r][0]);
-            load16_cs(frames + base + r * pitch + 16, &w[r][4]);
-            load16_cs(frames + base + r * pitch + 32, &w[r][8]);
-        }
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const uint2 t = __ldcs(reinterpret_cast<const uint2*>(frames + base + r * pitch + 8 * i));
+                w[r][2 * i] = t.x; w[r][2 * i + 1] = t.y;
+            }
         uint32_t hi[4], nz = 0;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const size_t wo = plane_off + (size_t)(br * 4 + r) * wpr;
-            hi[r] = reinterpret_cast<const uint16_t*>(over127 + wo)[gx];
-            nz |= reinterpret_cast<const uint16_t*>(nonzero + wo)[gx];
+            hi[r] = reinterpret_cast<const uint8_t*>(over127 + wo)[gx];
+            nz |= reinterpret_cast<const uint8_t*>(nonzero + wo)[gx];
         }
         // ---- overlay: paint (B,G,R) = (0,0,255) where acc > 127 ----
         if (overlay) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                uint32_t o[12];
+                uint32_t o[6];
 #pragma unroll
-                for (int i = 0; i < 12; ++i) o[i] = w[r][i];
+                for (int i = 0; i < 6; ++i) o[i] = w[r][i];
                 if (hi[r]) {
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
+                    for (int b = 0; b < 2; ++b) {
                         const uint32_t m = hi[r] >> (4 * b);
                         if (m & 1u) { o[3 * b] = (o[3 * b] & 0xff000000u) | 0x00ff0000u; }
                         if (m & 2u) { o[3 * b] &= 0x00ffffffu; o[3 * b + 1] = (o[3 * b + 1] & 0xffff0000u) | 0x0000ff00u; }
                         if (m & 4u) { o[3 * b + 1] &= 0x0000ffffu; o[3 * b + 2] = (o[3 * b + 2] & 0xffffff00u) | 0x000000ffu; }
                         if (m & 8u) { o[3 * b + 2] = (o[3 * b + 2] & 0x000000ffu) | 0xff000000u; }
                     }
-                    n_motion += __popc(hi[r]);
                 }
-                store16_cs(overlay + base + r * pitch, &o[0]);
-                store16_cs(overlay + base + r * pitch + 16, &o[4]);
-                store16_cs(overlay + base + r * pitch + 32, &o[8]);
-            }
-        } else {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) n_motion += __popc(hi[r]);
+                for (int i = 0; i < 3; ++i)
+                    __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(o[2 * i], o[2 * i + 1]));
+            }
         }
+        n_motion = __popc(hi[0]) + __popc(hi[1]) + __popc(hi[2]) + __popc(hi[3]);
         // ---- compressed: per 4x4 block ----
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const bool is_static = ((nz >> (4 * b)) & 0xfu) == 0u;
+            n_static += is_static ? 1u : 0u;
+            if (!compressed) continue;
+            if (is_static) {
+                float v[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t w0 = w[r][3 * b], w1 = w[r][3 * b + 1], w2 = w[r][3 * b + 2];
+                    v[r][0] = luma_m128_f(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+                    v[r][1] = luma_m128_f(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
+                    v[r][2] = luma_m128_f((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
+                    v[r][3] = luma_m128_f((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
+                }
+                degrade_block4_fast(v, qc);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t y0 = out_byte_bits(v[r][0]), y1 = out_byte_bits(v[r][1]);
+                    const uint32_t y2 = out_byte_bits(v[r][2]), y3 = out_byte_bits(v[r][3]);
+                    w[r][3 * b] = __byte_perm(y0, y1, 0x4000);          // y0 y0 y0 y1
+                    w[r][3 * b + 1] = __byte_perm(y1, y2, 0x4400);      // y1 y1 y2 y2
+                    w[r][3 * b + 2] = __byte_perm(y2, y3, 0x4440);      // y2 y3 y3 y3
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    uint32_t o[3] = {0, 0, 0};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const int i = 12 * b + 3 * p;
+                        int bb = byte_at(w[r], i), gg = byte_at(w[r], i + 1), rr = byte_at(w[r], i + 2);
+                        ycc_roundtrip(bb, gg, rr);
+                        const int j = 3 * p;
+                        o[j >> 2] |= (uint32_t)bb << ((j & 3) * 8);
+                        o[(j + 1) >> 2] |= (uint32_t)gg << (((j + 1) & 3) * 8);
+                        o[(j + 2) >> 2] |= (uint32_t)rr << (((j + 2) & 3) * 8);
+                    }
+                    w[r][3 * b] = o[0]; w[r][3 * b + 1] = o[1]; w[r][3 * b + 2] = o[2];
+                }
+            }
+        }
         if (compressed) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const bool is_static = ((nz >> (4 * b)) & 0xfu) == 0u;
-                if (is_static) {
-                    ++n_static;
-                    float v[4][4];
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const uint32_t (&ww)[12] = w[r];
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const int i = 12 * b + 3 * p;
-                            v[r][p] = (float)(luma_of(byte_at(ww, i), byte_at(ww, i + 1), byte_at(ww, i + 2)) - 128);
-                        }
-                    }
-                    degrade_block4(v, q);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const uint32_t y0 = clip_trunc_u8(__fadd_rn(v[r][0], 128.0f));
-                        const uint32_t y1 = clip_trunc_u8(__fadd_rn(v[r][1], 128.0f));
-                        const uint32_t y2 = clip_trunc_u8(__fadd_rn(v[r][2], 128.0f));
-                        const uint32_t y3 = clip_trunc_u8(__fadd_rn(v[r][3], 128.0f));
-                        w[r][3 * b] = y0 * 0x00010101u | (y1 << 24);
-                        w[r][3 * b + 1] = y1 * 0x00000101u | (y2 * 0x01010000u);
-                        w[r][3 * b + 2] = y2 | (y3 * 0x01010100u);
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        uint32_t o[3] = {0, 0, 0};
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const int i = 12 * b + 3 * p;
-                            int bb = byte_at(w[r], i), gg = byte_at(w[r], i + 1), rr = byte_at(w[r], i + 2);
-                            ycc_roundtrip(bb, gg, rr);
-                            const int j = 3 * p;
-                            o[j >> 2] |= (uint32_t)bb << ((j & 3) * 8);
-                            o[(j + 1) >> 2] |= (uint32_t)gg << (((j + 1) & 3) * 8);
-                            o[(j + 2) >> 2] |= (uint32_t)rr << (((j + 2) & 3) * 8);
-                        }
-                        w[r][3 * b] = o[0]; w[r][3 * b + 1] = o[1]; w[r][3 * b + 2] = o[2];
-                    }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                store16_cs(compressed + base + r * pitch, &w[r][0]);
-                store16_cs(compressed + base + r * pitch + 16, &w[r][4]);
-                store16_cs(compressed + base + r * pitch + 32, &w[r][8]);
-            }
-        } else {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) n_static += ((nz >> (4 * b)) & 0xfu) == 0u ? 1u : 0u;
+                for (int i = 0; i < 3; ++i)
+                    __stcs(reinterpret_cast<uint2*>(compressed + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
         }
     }
     // ---- statistics: warp shuffle reduction, one atomic pair per warp ----

@@ -40,9 +40,13 @@ DEVI uint32_t bs_ge(const uint32_t (&c)[CNT_BITS], uint32_t m) {   // per-lane c
     return ge;
 }
 
+// slot0 = slot of frame f0 in the ring; all slot arithmetic is 32-bit with wrap-around compares
 __global__ void __launch_bounds__(256)
-k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int wpr, long long f0, int T, int K,
-              MinCounts mc, uint32_t* __restrict__ voted, int seg_len) {
+k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int wpr, long long f0, int slot0, int T,
+              int K, MinCounts mc, uint32_t* __restrict__ voted, int seg_len) {
+    __shared__ uint8_t s_mc[32];
+    if (threadIdx.x < 32) s_mc[threadIdx.x] = mc.v[threadIdx.x];
+    __syncthreads();
     const size_t plane_words = (size_t)H * wpr;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= plane_words) return;
@@ -50,13 +54,24 @@ k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int
     const uint32_t vm = valid_mask((int)(idx % wpr), W);
     uint32_t c[CNT_BITS] = {0, 0, 0, 0, 0};
     const long long fs = f0 + t0;
-    for (long long f = max(0LL, fs - K + 1); f < fs; ++f) bs_add(c, ring[(size_t)(f % ring_cap) * plane_words + idx]);
+    int s_new = (slot0 + t0) % ring_cap;
+    const int nh = (int)min((long long)(K - 1), fs);       // history planes fs-nh .. fs-1
+    int s = s_new - nh;
+    if (s < 0) s += ring_cap;
+    for (int i = 0; i < nh; ++i) {
+        bs_add(c, ring[(size_t)s * plane_words + idx]);
+        s = s + 1 == ring_cap ? 0 : s + 1;
+    }
+    int s_old = s_new - K;                                  // slot of the plane leaving the window
+    if (s_old < 0) s_old += ring_cap;
+    int L = nh;                                             // masks in the window before adding frame t
     for (int t = t0; t < t1; ++t) {
-        const long long f = f0 + t;
-        if (t > t0 && f - K >= 0) bs_sub(c, ring[(size_t)((f - K) % ring_cap) * plane_words + idx]);
-        bs_add(c, ring[(size_t)(f % ring_cap) * plane_words + idx]);
-        const int L = (int)min((long long)K, f + 1);
-        voted[(size_t)t * plane_words + idx] = bs_ge(c, mc.v[L - 1]) & vm;
+        if (L == K) { if (t > t0) bs_sub(c, ring[(size_t)s_old * plane_words + idx]); }
+        else ++L;
+        bs_add(c, ring[(size_t)s_new * plane_words + idx]);
+        voted[(size_t)t * plane_words + idx] = bs_ge(c, s_mc[L - 1]) & vm;
+        s_new = s_new + 1 == ring_cap ? 0 : s_new + 1;
+        s_old = s_old + 1 == ring_cap ? 0 : s_old + 1;
     }
 }
 
@@ -156,25 +171,37 @@ struct MorphChain {
     MorphPrim p[MORPH_MAX_PRIMS];
 };
 
-// OR over column offsets [lo, hi] of one bit row: out(x) = OR_d in(x + d), lo <= 0 <= hi, both within
-// +-32.  Pixels to the right are higher bits: the right reach works on (next:cur), the left reach on
-// (cur:prev), each log-doubled on a 64-bit value.
-DEVI uint32_t hrun_or(uint32_t prev, uint32_t cur, uint32_t next, int lo, int hi) {
+// OR over column offsets [-L, R] of one bit row: out(x) = OR_d in(x + d).  Pixels to the right are higher
+// bits: the right reach works on (next:cur), the left reach on (cur:prev), each log-doubled on a 64-bit
+// value with a shift schedule precomputed on the host (MorphPrim::rsh / lsh).
+struct HRun { int nr, nl; };      // window sizes: nr = hi + 1 (right reach + centre), nl = 1 - lo
+
+DEVI HRun make_hrun(int lo, int hi) { HRun h; h.nr = hi + 1; h.nl = 1 - lo; return h; }
+
+DEVI uint32_t hrun_or(uint32_t prev, uint32_t cur, uint32_t next, const HRun& h) {
     uint32_t res = cur;
-    if (hi > 0) {
+    if (h.nr > 1) {
         uint64_t a = ((uint64_t)next << 32) | cur;
+        const int n = h.nr;
         int c = 1;
-        const int n = hi + 1;
-        while (2 * c <= n) { a |= a >> c; c *= 2; }
-        if (c < n) a |= a >> (n - c);
+        if (n >= 2) { a |= a >> 1; c = 2; }
+        if (n >= 4) { a |= a >> 2; c = 4; }
+        if (n >= 8) { a |= a >> 4; c = 8; }
+        if (n >= 16) { a |= a >> 8; c = 16; }
+        if (n >= 32) { a |= a >> 16; c = 32; }
+        if (n > c) a |= a >> (n - c);
         res |= (uint32_t)a;
     }
-    if (lo < 0) {
+    if (h.nl > 1) {
         uint64_t b = ((uint64_t)cur << 32) | prev;
+        const int n = h.nl;
         int c = 1;
-        const int n = 1 - lo;
-        while (2 * c <= n) { b |= b << c; c *= 2; }
-        if (c < n) b |= b << (n - c);
+        if (n >= 2) { b |= b << 1; c = 2; }
+        if (n >= 4) { b |= b << 2; c = 4; }
+        if (n >= 8) { b |= b << 4; c = 8; }
+        if (n >= 16) { b |= b << 8; c = 16; }
+        if (n >= 32) { b |= b << 16; c = 32; }
+        if (n > c) b |= b << (n - c);
         res |= (uint32_t)(b >> 32);
     }
     return res;
@@ -184,6 +211,9 @@ DEVI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_share
 
 // grid: (bands, n_images); dynamic smem: 2 planes of ext_rows x wpr words + one mbarrier.
 // Thread t owns word column (t % wpr) of rows (t / wpr), (t / wpr) + rows_per_pass, ...
+// Erosion runs as NOT dilate NOT: the complement is folded into the first read and the last write of the
+// primitive.  Rows outside the image and bits beyond W are 'ignored' pixels: they read as 0 in the dilation
+// domain of either polarity, so only rows [r_lo, r_hi) of the staged band are ever computed.
 __global__ void __launch_bounds__(256)
 k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int H, int W, int wpr, int band_rows,
               MorphChain ch) {
@@ -199,23 +229,25 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
     uint32_t* dp = dst + (size_t)blockIdx.y * plane_words;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nwords = ext_rows * wpr;
-    // column-major-in-thread mapping without a division per element
     const int rows_per_pass = nt / wpr;                       // >= 1 (host guarantees wpr <= blockDim)
     const int j = tid % wpr, r_first = tid / wpr;
     const bool lane_on = r_first < rows_per_pass;
     const uint32_t vm = valid_mask(j, W);
+    const uint32_t pm = j > 0 ? valid_mask(j - 1, W) : 0u, nm = j + 1 < wpr ? valid_mask(j + 1, W) : 0u;
+    const int jp = j > 0 ? j - 1 : j, jn = j + 1 < wpr ? j + 1 : j;      // clamped neighbour columns (masked by pm / nm)
 
-    // stage rows [max(ey0,0), min(ey0+ext_rows,H)) with one bulk copy (rows are contiguous in the plane)
     const int r_lo = max(0, -ey0), r_hi = min(ext_rows, H - ey0);     // ext rows that exist in the image
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < nwords; i += nt) {
-        if (i < r_lo * wpr || i >= r_hi * wpr) A[i] = 0u;
+        const bool outside = i < r_lo * wpr || i >= r_hi * wpr;
+        if (outside) A[i] = 0u;
+        if (outside) B[i] = 0u;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {       // stage rows [r_lo, r_hi): contiguous in the plane, one bulk (TMA) copy
         const uint32_t bytes = (uint32_t)(r_hi - r_lo) * wpr * 4u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -229,52 +261,48 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
                          : "=r"(done) : "r"(smem_u32(bar)) : "memory");
         }
     }
+    // first row owned by this thread inside [r_lo, r_hi)
+    int r_start = r_first;
+    if (r_start < r_lo) r_start += ((r_lo - r_start + rows_per_pass - 1) / rows_per_pass) * rows_per_pass;
 
-    // Erosion runs as NOT dilate NOT: the complement is folded into the first read and the last write of the
-    // primitive.  Rows outside the image and bits beyond W are 'ignored' pixels: they read as 0 in the
-    // dilation domain of either polarity.
     for (int pi = 0; pi < ch.n; ++pi) {
         const MorphPrim& P = ch.p[pi];
         const uint32_t flip = P.erode ? 0xffffffffu : 0u;
+        const int nrows = P.nrows;
         if (P.separable) {
-            const int lo = P.lo[0], hi = P.hi[0];
+            const HRun hr = make_hrun(P.lo[0], P.hi[0]);
             if (lane_on)
-                for (int r = r_first; r < ext_rows; r += rows_per_pass) {      // horizontal: A -> B
-                    const uint32_t* row = A + (size_t)r * wpr;
-                    const bool in_img = r >= r_lo && r < r_hi;
-                    const uint32_t pm = j > 0 ? valid_mask(j - 1, W) : 0u, nm = j + 1 < wpr ? valid_mask(j + 1, W) : 0u;
-                    const uint32_t p = in_img && j > 0 ? (row[j - 1] ^ flip) & pm : 0u;
-                    const uint32_t c = in_img ? (row[j] ^ flip) & vm : 0u;
-                    const uint32_t n = in_img && j + 1 < wpr ? (row[j + 1] ^ flip) & nm : 0u;
-                    B[(size_t)r * wpr + j] = hrun_or(p, c, n, lo, hi) & vm;
+                for (int r = r_start; r < r_hi; r += rows_per_pass) {         // horizontal: A -> B
+                    const uint32_t* row = A + r * wpr;
+                    const uint32_t p = (row[jp] ^ flip) & pm, c = (row[j] ^ flip) & vm, n = (row[jn] ^ flip) & nm;
+                    B[r * wpr + j] = (p | c | n) ? hrun_or(p, c, n, hr) & vm : 0u;
                 }
             __syncthreads();
-            const int dy0 = P.dy[0], dy1 = P.dy[P.nrows - 1];
+            const int dy0 = P.dy[0], dy1 = P.dy[nrows - 1];
             if (lane_on)
-                for (int r = r_first; r < ext_rows; r += rows_per_pass) {      // vertical: B -> A
+                for (int r = r_start; r < r_hi; r += rows_per_pass) {         // vertical: B -> A
                     uint32_t acc = 0;
-                    const int ra = max(r + dy0, 0), rb = min(r + dy1, ext_rows - 1);
-                    for (int rr = ra; rr <= rb; ++rr) acc |= B[(size_t)rr * wpr + j];
-                    const bool in_img = r >= r_lo && r < r_hi;
-                    A[(size_t)r * wpr + j] = in_img ? (acc ^ flip) & vm : 0u;
+                    const int ra = max(r + dy0, r_lo), rb = min(r + dy1, r_hi - 1);
+                    for (int rr = ra; rr <= rb; ++rr) acc |= B[rr * wpr + j];
+                    A[r * wpr + j] = (acc ^ flip) & vm;
                 }
             __syncthreads();
         } else {
             if (lane_on)
-                for (int r = r_first; r < ext_rows; r += rows_per_pass) {      // generic: A -> B
+                for (int r = r_start; r < r_hi; r += rows_per_pass) {         // generic: A -> B
                     uint32_t acc = 0;
-                    for (int k = 0; k < P.nrows; ++k) {
+                    for (int k = 0; k < nrows; ++k) {
                         const int rr = r + P.dy[k];
                         if (rr < r_lo || rr >= r_hi) continue;
-                        const uint32_t* row = A + (size_t)rr * wpr;
-                        const uint32_t pm = j > 0 ? valid_mask(j - 1, W) : 0u, nm = j + 1 < wpr ? valid_mask(j + 1, W) : 0u;
-                        const uint32_t p = j > 0 ? (row[j - 1] ^ flip) & pm : 0u;
+                        const uint32_t* row = A + rr * wpr;
+                        const int lo = P.lo[k], hi = P.hi[k];
                         const uint32_t c = (row[j] ^ flip) & vm;
-                        const uint32_t n = j + 1 < wpr ? (row[j + 1] ^ flip) & nm : 0u;
-                        acc |= hrun_or(p, c, n, P.lo[k], P.hi[k]);
+                        if (lo == 0 && hi == 0) { acc |= c; continue; }
+                        const uint32_t p = (row[jp] ^ flip) & pm, n = (row[jn] ^ flip) & nm;
+                        if (lo == -1 && hi == 0) { acc |= c | (c << 1) | (p >> 31); continue; }
+                        if (p | c | n) acc |= hrun_or(p, c, n, make_hrun(lo, hi));
                     }
-                    const bool in_img = r >= r_lo && r < r_hi;
-                    B[(size_t)r * wpr + j] = in_img ? (acc ^ flip) & vm : 0u;
+                    B[r * wpr + j] = (acc ^ flip) & vm;
                 }
             __syncthreads();
             uint32_t* t = A; A = B; B = t;
@@ -282,7 +310,7 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
     }
     // write the band
     const int out_rows = min(band_rows, H - y0);
-    for (int i = tid; i < out_rows * wpr; i += nt) dp[(size_t)y0 * wpr + i] = A[(size_t)ch.halo_top * wpr + i];
+    for (int i = tid; i < out_rows * wpr; i += nt) dp[(size_t)y0 * wpr + i] = A[ch.halo_top * wpr + i];
 }
 
 }  // namespace dvc

@@ -209,6 +209,44 @@ def test_degrade_fd(P, shape, bs):
     assert c[3] == 3 * (shape[0] // bs) * (shape[1] // bs) and c[4] == n_static
 
 
+@pytest.mark.parametrize("q", [100, 100.0, 33.3, 8, 7.5, 1, 250, 0.25])
+def test_degrade_fd_quantiser_ties_and_levels(P, q):
+    """Blocks built to sit exactly on quantiser ties (d/q = n + 1/2) and a sweep of quantisation levels,
+    including levels small enough to disable the fast rounding path."""
+    if not so.cv2_dct4_matches_closed_form():
+        pytest.skip("host cv2 does not follow the recovered float32 DCT sequence; covered by tolerance tests")
+    r = rng(21)
+    h, w = 64, 96                                       # W % 16 == 0
+    frames = np.empty((4, h, w, 3), np.uint8)
+    # grey frames: Y == value.  4x4 blocks whose DC = sum(Y-128)/4 is an exact multiple of q/2 when q = 100
+    base = r.integers(100, 160, (h // 4, w // 4), dtype=np.int64)
+    img = np.repeat(np.repeat(base, 4, 0), 4, 1)
+    pat = np.zeros((4, 4), np.int64); pat[:2] = 1          # 8 pixels +1 -> sum shifts by 8
+    img = img + np.tile(pat, (h // 4, w // 4))
+    frames[0] = np.clip(img, 0, 255).astype(np.uint8)[..., None]
+    frames[1] = r.integers(0, 256, (h, w, 1), dtype=np.uint8)
+    frames[2] = r.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    frames[3] = (r.integers(0, 4, (h, w, 3)) * 85).astype(np.uint8)
+    acc = np.zeros((4, h, w), np.uint8)
+    comp, _ = P.degrade_blend(dev(frames), dev(acc), 4, q, "fd", False)
+    comp = host(comp)
+    for i in range(4):
+        assert np.array_equal(comp[i], so.degrade_fd(frames[i], acc[i], 4, q)), (q, i)
+
+
+@pytest.mark.parametrize("shape", [(48, 72), (8, 8), (4, 24), (100, 104)])
+def test_degrade_fd_widths_multiple_of_8(P, shape):
+    r = rng(22)
+    exact = so.cv2_dct4_matches_closed_form()
+    frames = r.integers(0, 256, (2,) + shape + (3,), dtype=np.uint8)
+    acc = (r.random((2,) + shape) < 0.01).astype(np.uint8) * r.integers(1, 256, (2,) + shape, dtype=np.uint8)
+    comp, ov = P.degrade_blend(dev(frames), dev(acc), 4, 100, "fd", True)
+    comp, ov = host(comp), host(ov)
+    for i in range(2):
+        assert np.array_equal(ov[i], so.overlay_paint(frames[i], acc[i]))
+        _check_degraded(comp[i], so.degrade_fd(frames[i], acc[i], 4, 100), frames[i], acc[i], 4, 100, exact)
+
+
 def test_degrade_mco(P):
     r = rng(12)
     shape = (64, 96)
