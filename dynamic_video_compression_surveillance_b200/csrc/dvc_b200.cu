@@ -80,6 +80,14 @@ static bool make_prim(int shape, int k, bool erode, MorphPrim& p) {
     for (int i = 1; i < n; ++i)
         if (p.lo[i] != p.lo[0] || p.hi[i] != p.hi[0] || p.dy[i] != p.dy[i - 1] + 1) sep = false;
     p.separable = sep;
+    // 3x3-bounded, non-separable elements get the unrolled path
+    bool small = !sep;
+    for (int i = 0; i < n; ++i)
+        if (p.dy[i] < -1 || p.dy[i] > 1 || p.lo[i] < -1 || p.hi[i] > 1 || p.lo[i] > 0 || p.hi[i] < 0) small = false;
+    p.small = small;
+    if (small)
+        for (int i = 0; i < n; ++i)
+            p.small_rows[p.dy[i] + 1] = (int8_t)(1 | (p.lo[i] == -1 ? 2 : 0) | (p.hi[i] == 1 ? 4 : 0));
     return true;
 }
 

@@ -127,35 +127,60 @@ DEVI void dct4_inv_ps(float& x0, float& x1, float& x2, float& x3) {
     x2 = __fsub_rn(e1, o1);
 }
 
-template <int NE>   // NE = number of even indices among (row, col): pending scale 2^-NE
-DEVI float quantise_scaled(float d, const QuantConsts& qc) {
+// NE = number of even indices among (row, col): the coefficient carries a pending scale 2^-NE.
+template <int NE>
+DEVI float quantise_fast(float d, const QuantConsts& qc, float& tie_dist) {
     const float magic = 12582912.0f;                      // 1.5 * 2^23: add/sub rounds half to even
     const float t = __fmul_rn(d, qc.k[NE]);
-    float n = __fsub_rn(__fadd_rn(t, magic), magic);
-    if (!qc.fast || fabsf(__fsub_rn(t, n)) > 0.499f)      // near a tie (or tiny q): exact IEEE division
-        n = rintf(__fdiv_rn(__fmul_rn(d, NE == 0 ? 1.0f : (NE == 1 ? 0.5f : 0.25f)), qc.q));
+    const float n = __fsub_rn(__fadd_rn(t, magic), magic);
+    tie_dist = fmaxf(tie_dist, fabsf(__fsub_rn(t, n)));   // 0.5 = on a rounding tie
+    return __fmul_rn(n, qc.o[NE]);
+}
+template <int NE>
+DEVI float quantise_exact(float d, const QuantConsts& qc) {   // np.round(d / q) with the IEEE division
+    const float n = rintf(__fdiv_rn(__fmul_rn(d, NE == 0 ? 1.0f : (NE == 1 ? 0.5f : 0.25f)), qc.q));
     return __fmul_rn(n, qc.o[NE]);
 }
 
-DEVI void degrade_block4_fast(float (&v)[4][4], const QuantConsts& qc) {
+DEVI void fwd_dct_block(float (&v)[4][4]) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) dct4_fwd_ns(v[r][0], v[r][1], v[r][2], v[r][3]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) dct4_fwd_ns(v[0][c], v[1][c], v[2][c], v[3][c]);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        if ((r & 1) == 0) {
-            v[r][0] = quantise_scaled<2>(v[r][0], qc); v[r][1] = quantise_scaled<1>(v[r][1], qc);
-            v[r][2] = quantise_scaled<2>(v[r][2], qc); v[r][3] = quantise_scaled<1>(v[r][3], qc);
-        } else {
-            v[r][0] = quantise_scaled<1>(v[r][0], qc); v[r][1] = quantise_scaled<0>(v[r][1], qc);
-            v[r][2] = quantise_scaled<1>(v[r][2], qc); v[r][3] = quantise_scaled<0>(v[r][3], qc);
-        }
-    }
+}
+DEVI void inv_dct_block(float (&v)[4][4]) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) dct4_inv_ps(v[r][0], v[r][1], v[r][2], v[r][3]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) dct4_inv_ps(v[0][c], v[1][c], v[2][c], v[3][c]);
+}
+// returns the largest distance of any coefficient from its rounded value (the caller redoes the block with
+// quantise_block_exact when that is close to 1/2)
+DEVI float quantise_block_fast(float (&v)[4][4], const QuantConsts& qc) {
+    float tie = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if ((r & 1) == 0) {
+            v[r][0] = quantise_fast<2>(v[r][0], qc, tie); v[r][1] = quantise_fast<1>(v[r][1], qc, tie);
+            v[r][2] = quantise_fast<2>(v[r][2], qc, tie); v[r][3] = quantise_fast<1>(v[r][3], qc, tie);
+        } else {
+            v[r][0] = quantise_fast<1>(v[r][0], qc, tie); v[r][1] = quantise_fast<0>(v[r][1], qc, tie);
+            v[r][2] = quantise_fast<1>(v[r][2], qc, tie); v[r][3] = quantise_fast<0>(v[r][3], qc, tie);
+        }
+    }
+    return tie;
+}
+DEVI void quantise_block_exact(float (&v)[4][4], const QuantConsts& qc) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if ((r & 1) == 0) {
+            v[r][0] = quantise_exact<2>(v[r][0], qc); v[r][1] = quantise_exact<1>(v[r][1], qc);
+            v[r][2] = quantise_exact<2>(v[r][2], qc); v[r][3] = quantise_exact<1>(v[r][3], qc);
+        } else {
+            v[r][0] = quantise_exact<1>(v[r][0], qc); v[r][1] = quantise_exact<0>(v[r][1], qc);
+            v[r][2] = quantise_exact<1>(v[r][2], qc); v[r][3] = quantise_exact<0>(v[r][3], qc);
+        }
+    }
 }
 
 // luma - 128 as float without the conversion pipe: (2^23 | y) read as float is 2^23 + y exactly
@@ -163,10 +188,18 @@ DEVI float luma_m128_f(uint32_t b, uint32_t g, uint32_t r) {
     const uint32_t y = (1868u * b + 9617u * g + 4899u * r + 8192u) >> 14;
     return __fsub_rn(__uint_as_float(0x4B000000u | y), 8388736.0f);      // 2^23 + 128
 }
-// np.clip(v + 128, 0, 255) stored to uint8: returns a word whose low byte is the result
+// luma - 128 of the four pixels held in three packed BGR words
+DEVI void luma_row4(uint32_t w0, uint32_t w1, uint32_t w2, float (&v)[4]) {
+    v[0] = luma_m128_f(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+    v[1] = luma_m128_f(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
+    v[2] = luma_m128_f((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
+    v[3] = luma_m128_f((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
+}
+// np.clip(v + 128, 0, 255) stored to uint8 (truncation): one saturating round-toward-zero conversion
 DEVI uint32_t out_byte_bits(float v) {
-    const float s = fminf(fmaxf(__fadd_rn(v, 128.0f), 0.0f), 255.0f);
-    return __float_as_uint(__fadd_rd(s, 8388608.0f));                    // 2^23 + floor(s): low mantissa byte
+    uint32_t r;
+    asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(__fadd_rn(v, 128.0f)));
+    return r;
 }
 
 __global__ void __launch_bounds__(256, 4)
@@ -201,10 +234,16 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
         if (overlay) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
+                if (hi[r] == 0u) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
+                    continue;
+                }
                 uint32_t o[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) o[i] = w[r][i];
-                if (hi[r]) {
+                {
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         const uint32_t m = hi[r] >> (4 * b);
@@ -229,14 +268,16 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
             if (is_static) {
                 float v[4][4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const uint32_t w0 = w[r][3 * b], w1 = w[r][3 * b + 1], w2 = w[r][3 * b + 2];
-                    v[r][0] = luma_m128_f(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
-                    v[r][1] = luma_m128_f(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
-                    v[r][2] = luma_m128_f((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
-                    v[r][3] = luma_m128_f((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
+                for (int r = 0; r < 4; ++r) luma_row4(w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2], v[r]);
+                fwd_dct_block(v);
+                const float tie = quantise_block_fast(v, qc);
+                if (!qc.fast || tie > 0.499f) {          // rare: a coefficient within 1e-3 of a tie (or tiny q)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) luma_row4(w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2], v[r]);
+                    fwd_dct_block(v);
+                    quantise_block_exact(v, qc);
                 }
-                degrade_block4_fast(v, qc);
+                inv_dct_block(v);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const uint32_t y0 = out_byte_bits(v[r][0]), y1 = out_byte_bits(v[r][1]);

@@ -160,7 +160,8 @@ struct MorphPrim {
     int8_t erode;                      // 0 = dilate (OR), 1 = erode (AND; run as NOT dilate NOT)
     int8_t separable;                  // all rows share one run and rows are contiguous
     int8_t nrows;                      // rows of the structuring element that are non-empty
-    int8_t pad;
+    int8_t small;                      // fits in 3x3 around the anchor: small_rows[] holds per-row flags
+    int8_t small_rows[3];              // dy = -1, 0, +1: bit0 present, bit1 dx=-1 present, bit2 dx=+1 present
     int8_t dy[MORPH_MAX_K];            // row offset (kernel row - anchor)
     int8_t lo[MORPH_MAX_K];            // run of column offsets [lo, hi] in that row
     int8_t hi[MORPH_MAX_K];
@@ -287,6 +288,28 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
                     A[r * wpr + j] = (acc ^ flip) & vm;
                 }
             __syncthreads();
+        } else if (P.small) {
+            // 3x3-bounded element (e.g. MORPH_ELLIPSE 2 or 3): rows dy in {-1,0,1}, reach <= 1 pixel.
+            // flags per row: bit0 present, bit1 pixel to the left (dx=-1), bit2 pixel to the right (dx=+1)
+            const int f_up = P.small_rows[0], f_mid = P.small_rows[1], f_dn = P.small_rows[2];
+            if (lane_on)
+                for (int r = r_start; r < r_hi; r += rows_per_pass) {         // A -> B
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int f = k == 0 ? f_up : (k == 1 ? f_mid : f_dn);
+                        const int rr = r + k - 1;
+                        if (!(f & 1) || rr < r_lo || rr >= r_hi) continue;
+                        const uint32_t* row = A + rr * wpr;
+                        const uint32_t c = (row[j] ^ flip) & vm;
+                        acc |= c;
+                        if (f & 2) acc |= __funnelshift_l((row[jp] ^ flip) & pm, c, 1);
+                        if (f & 4) acc |= __funnelshift_r(c, (row[jn] ^ flip) & nm, 1);
+                    }
+                    B[r * wpr + j] = (acc ^ flip) & vm;
+                }
+            __syncthreads();
+            uint32_t* t = A; A = B; B = t;
         } else {
             if (lane_on)
                 for (int r = r_start; r < r_hi; r += rows_per_pass) {         // generic: A -> B
@@ -295,12 +318,8 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
                         const int rr = r + P.dy[k];
                         if (rr < r_lo || rr >= r_hi) continue;
                         const uint32_t* row = A + rr * wpr;
-                        const int lo = P.lo[k], hi = P.hi[k];
-                        const uint32_t c = (row[j] ^ flip) & vm;
-                        if (lo == 0 && hi == 0) { acc |= c; continue; }
-                        const uint32_t p = (row[jp] ^ flip) & pm, n = (row[jn] ^ flip) & nm;
-                        if (lo == -1 && hi == 0) { acc |= c | (c << 1) | (p >> 31); continue; }
-                        if (p | c | n) acc |= hrun_or(p, c, n, make_hrun(lo, hi));
+                        const uint32_t p = (row[jp] ^ flip) & pm, c = (row[j] ^ flip) & vm, n = (row[jn] ^ flip) & nm;
+                        if (p | c | n) acc |= hrun_or(p, c, n, make_hrun(P.lo[k], P.hi[k]));
                     }
                     B[r * wpr + j] = (acc ^ flip) & vm;
                 }

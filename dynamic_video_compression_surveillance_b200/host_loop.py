@@ -1,0 +1,151 @@
+"""Host side of the per-video pipelines: decode -> pinned chunk -> GPU loop -> encode, plus the reporting the
+reference's GUI and performance_analysis.py depend on (file names, ``execution_times.txt`` layout, log lines).
+
+Design (not the reference's): a ``ChunkedReader`` fills a pinned batch buffer from cv2.VideoCapture, the GPU
+loop runs per batch through ``FramePipeline.process_host`` (upload / kernels / download double-buffered inside
+the library), a ``FrameSink`` pair writes the results.  What stays on the host is what SURVEY.md section 8 leaves
+there: codecs, the optional resize (frame_differencing.py:74,91), the first frame's heavy blur (:77), Farneback
+flow (motion_compression_opt.py:72-82) and contour -> rectangle drawing (:93-97).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import time
+from dataclasses import dataclass, field
+
+import cv2
+import numpy as np
+import torch
+
+from . import pipeline as P
+
+FOURCC = "mp4v"                                              # frame_differencing.py:62, motion_compression_opt.py:49
+FD_OVERLAY_NAME = "dilated_motion_mask_video.mp4"            # frame_differencing.py:52 (performance_analysis.py:146)
+FD_COMPRESSED_NAME = "compressed_final_video.mp4"            # frame_differencing.py:53 (performance_analysis.py:147)
+TIMES_NAME = "execution_times.txt"                           # parsed by performance_analysis.py:9-113
+
+
+def video_stem(path: str) -> str:
+    return os.path.splitext(os.path.basename(path))[0]
+
+
+@dataclass
+class StageTiming:
+    title: str
+    frames: int = 0
+    total_s: float = 0.0
+    avg_s: float = 0.0
+
+    def lines(self):
+        return [f"{self.title}:\n", f"  Frames processed: {self.frames}\n", f"  Total time: {self.total_s:.2f} seconds\n",
+                f"  Average time per frame: {self.avg_s:.4f} seconds\n\n"]
+
+
+def write_execution_times(path: str, stages: list[StageTiming], total_s: float) -> None:
+    """The text layout performance_analysis.py parses (frame_differencing.py:152-157;
+    motion_compression_opt.py:235-244)."""
+    with open(path, "w") as f:
+        for st in stages:
+            f.writelines(st.lines())
+        f.write(f"Total video processing time: {total_s:.2f} seconds\n")
+
+
+class ChunkedReader:
+    """cv2.VideoCapture -> batches of frames written straight into a pinned [B,H,W,3] buffer."""
+
+    def __init__(self, cap, size_wh, batch: int):
+        self.cap, self.size, self.batch = cap, size_wh, batch
+        w, h = size_wh
+        self.buf = P.pinned_empty((batch, h, w, 3))
+        self.view = self.buf.numpy()
+        self.done = False
+
+    def next_chunk(self) -> int:
+        n = 0
+        w, h = self.size
+        while n < self.batch and not self.done:
+            ok, frame = self.cap.read()
+            if not ok:
+                self.done = True
+                break
+            if (frame.shape[1], frame.shape[0]) != (w, h):
+                frame = cv2.resize(frame, (w, h))             # scale_factor != 1 (frame_differencing.py:91)
+            self.view[n] = frame
+            n += 1
+        return n
+
+
+@dataclass
+class FdRun:
+    frames: int = 0
+    per_frame_s: list = field(default_factory=list)
+    counters: dict = field(default_factory=dict)
+
+
+def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int, device, progress_callback) -> FdRun:
+    """The loop of frame_differencing.py:73-138 for one opened capture.  ``sinks`` = (overlay writer, compressed
+    writer).  Raises on failure; the caller owns the reference's swallow-and-log policy."""
+    w, h = size_wh
+    seed = cv2.GaussianBlur(cv2.cvtColor(cv2.resize(first_frame, (w, h)), cv2.COLOR_BGR2GRAY), (25, 25), 30)
+    run = FdRun()
+    with P.FramePipeline(w, h, "fd", max_batch=max_batch, device=device, **params) as pipe:
+        pipe.begin_stream(seed)
+        reader = ChunkedReader(cap, size_wh, max_batch)
+        out_ov, out_cp = P.pinned_empty(reader.buf.shape), P.pinned_empty(reader.buf.shape)
+        v_ov, v_cp = out_ov.numpy(), out_cp.numpy()
+        while True:
+            t0 = time.time()
+            n = reader.next_chunk()
+            if n == 0:
+                break
+            pipe.process_host(reader.buf[:n], out_ov[:n], out_cp[:n])
+            for i in range(n):
+                sinks[0].write(v_ov[i])
+                sinks[1].write(v_cp[i])
+                run.frames += 1
+                if progress_callback is not None and run.frames % 50 == 0:      # frame_differencing.py:137-138
+                    progress_callback(run.frames)
+            run.per_frame_s.extend([(time.time() - t0) / n] * n)
+        run.counters = pipe.counters()
+    return run
+
+
+def smooth_masks_gpu(raw_masks: list, history: list, window_size: int, alpha_fraction: float, morph_kernel: int):
+    """Window vote (motion_compression_opt.py:84-86) + close/open (:89-90) for a chunk of raw 0/255 masks.
+    ``history`` = raw masks of the stream before this chunk (all of them while the stream is shorter than the
+    window, else the last window_size-1), so the vote sees exactly the reference's deque."""
+    stack = torch.from_numpy(np.stack(history + raw_masks)).cuda()
+    voted = P.temporal_ring(stack, window_size, alpha_fraction)[len(history):].contiguous()
+    closed = P.morph(voted, "close", morph_kernel, "ellipse")
+    return P.morph(closed, "open", morph_kernel, "ellipse").cpu().numpy()
+
+
+def degrade_mco_gpu(frames: list, masks: list) -> np.ndarray:
+    """compress_with_motion's arithmetic (motion_compression_opt.py:152-183) for a chunk."""
+    comp, _ = P.degrade_blend(torch.from_numpy(np.stack(frames)).cuda(), torch.from_numpy(np.stack(masks)).cuda(),
+                              8, 100, "mco", want_overlay=False)
+    return comp.cpu().numpy()
+
+
+def rectangles_from_mask(mask: np.ndarray) -> np.ndarray:
+    """contours -> bounding rectangles (motion_compression_opt.py:93-97); host, SURVEY.md section 8f rank 2."""
+    out = np.zeros_like(mask)
+    contours, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    for c in contours:
+        x, y, w, h = cv2.boundingRect(c)
+        cv2.rectangle(out, (x, y), (x + w, y + h), 255, -1)
+    return out
+
+
+def attach_file_log(output_dir: str) -> str:
+    """Add a processing.log FileHandler to the root logger unless one for that file is already attached
+    (motion_compression_opt.py:8-27 behaviour)."""
+    path = os.path.join(output_dir, "processing.log")
+    root = logging.getLogger()
+    if not any(isinstance(h, logging.FileHandler) and h.baseFilename == os.path.abspath(path) for h in root.handlers):
+        fh = logging.FileHandler(path, mode="w")
+        fh.setFormatter(logging.Formatter("%(asctime)s - %(levelname)s - %(message)s"))
+        root.addHandler(fh)
+    root.setLevel(logging.INFO)
+    return path

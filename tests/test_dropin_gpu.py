@@ -1,0 +1,153 @@
+"""The drop-in entry points (windows.py:13-14,151,154 contracts) end to end on real mp4v files."""
+import logging
+import os
+import re
+import sys
+
+import cv2
+import numpy as np
+import pytest
+
+from dynamic_video_compression_surveillance_b200.synth import make_clip
+from oracle import loops
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "dynamic_video_compression_surveillance_b200", "dropin")
+
+
+@pytest.fixture()
+def dropin_modules(monkeypatch):
+    monkeypatch.syspath_prepend(DROPIN)
+    for m in ("frame_differencing", "motion_compression_opt"):
+        sys.modules.pop(m, None)
+    import frame_differencing
+    import motion_compression_opt
+    yield frame_differencing, motion_compression_opt
+    root = logging.getLogger()
+    for h in list(root.handlers):
+        if isinstance(h, logging.FileHandler):
+            root.removeHandler(h)
+            h.close()
+    for m in ("frame_differencing", "motion_compression_opt"):
+        sys.modules.pop(m, None)
+
+
+def _write_clip(path, frames, fps=30):
+    h, w = frames[0].shape[:2]
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), fps, (w, h))
+    assert wr.isOpened()
+    for f in frames:
+        wr.write(f)
+    wr.release()
+
+
+def _read_all(path):
+    cap = cv2.VideoCapture(path)
+    out = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        out.append(f)
+    cap.release()
+    return out
+
+
+def _smooth_clip(h, w, n, seed):
+    """Codec-friendly content: smooth background + moving rectangles (noise would turn into motion after mp4v)."""
+    clip = make_clip((h, w), n, seed=seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    bg = np.stack([(xx * 255 // w), (yy * 255 // h), ((xx + yy) * 255 // (w + h))], -1).astype(np.uint8)
+    clip.background = bg
+    return clip.frames()
+
+
+def test_process_single_video_fd(tmp_path, dropin_modules):
+    fd, _ = dropin_modules
+    h, w, n = 96, 128, 110
+    src = str(tmp_path / "cam0.mp4")
+    _write_clip(src, _smooth_clip(h, w, n, 3))
+    decoded = _read_all(src)
+    assert len(decoded) == n
+    calls = []
+    stats = {}
+    out_dir = str(tmp_path / "out")
+    fd.filter_and_dilate_movements(src, out_dir, progress_callback=calls.append, stats_out=stats, max_batch=16)
+    vdir = os.path.join(out_dir, "cam0")
+    for name in ("processing.log", "dilated_motion_mask_video.mp4", "compressed_final_video.mp4", "execution_times.txt"):
+        assert os.path.exists(os.path.join(vdir, name)), name
+    assert calls == [50, 100]                                            # frame_differencing.py:137-138
+    assert len(_read_all(os.path.join(vdir, "dilated_motion_mask_video.mp4"))) == n - 1
+    assert len(_read_all(os.path.join(vdir, "compressed_final_video.mp4"))) == n - 1
+    txt = open(os.path.join(vdir, "execution_times.txt")).read().splitlines()
+    assert txt[0] == "Frame Differencing:"
+    assert re.fullmatch(r"  Frames processed: (\d+)", txt[1]).group(1) == str(n - 1)
+    assert re.fullmatch(r"  Total time: [\d\.]+ seconds", txt[2])
+    assert re.fullmatch(r"  Average time per frame: [\d\.]+ seconds", txt[3])
+    assert txt[4] == "" and re.fullmatch(r"Total video processing time: [\d\.]+ seconds", txt[5])
+    # the arithmetic, against the oracle on the decoded frames (what the loop actually saw)
+    ref = loops.fd_loop(decoded)
+    assert stats["frames"] == n - 1
+    assert stats["motion_pixels"] == int(sum((a > 127).sum() for a in ref["acc"]))
+    # and the full entry point with its banner
+    fd.process_single_video_fd(src, str(tmp_path / "out2"))
+    log = open(os.path.join(str(tmp_path / "out2"), "cam0", "processing.log")).read()
+    assert "Execution statistics saved in" in log
+
+
+def test_fd_error_convention(tmp_path, dropin_modules):
+    fd, _ = dropin_modules
+    assert fd.process_single_video_fd(str(tmp_path / "missing.mp4"), str(tmp_path / "o")) is None     # logs, never raises
+    # unsupported configuration: logged and swallowed inside the loop, outputs finalised, timing file written
+    src = str(tmp_path / "c.mp4")
+    _write_clip(src, _smooth_clip(64, 96, 6, 1))
+    fd.filter_and_dilate_movements(src, str(tmp_path / "o3"), block_size=6)
+    txt = open(os.path.join(str(tmp_path / "o3"), "c", "execution_times.txt")).read()
+    assert "Frames processed: 0" in txt
+
+
+def test_process_single_video_of(tmp_path, dropin_modules):
+    _, mco = dropin_modules
+    h, w, n = 96, 128, 40
+    src = str(tmp_path / "cam1.mp4")
+    _write_clip(src, _smooth_clip(h, w, n, 5))
+    out_dir = str(tmp_path / "out")
+    mco.process_single_video_of(src, out_dir)
+    vdir = os.path.join(out_dir, "cam1")
+    for name in ("overlay.mp4", "mask.mp4", "compressed.mp4", "execution_times.txt", "processing.log"):
+        assert os.path.exists(os.path.join(vdir, name)), name
+    txt = open(os.path.join(vdir, "execution_times.txt")).read()
+    assert txt.startswith("Motion Detection:\n  Frames processed: %d\n" % (n - 1))
+    assert "\nCompression:\n  Frames processed: %d\n" % (n - 1) in txt
+    # compress_with_motion's arithmetic vs the oracle on the decoded overlay/mask videos
+    frames, masks = _read_all(os.path.join(vdir, "overlay.mp4")), _read_all(os.path.join(vdir, "mask.mp4"))
+    from dynamic_video_compression_surveillance_b200 import host_loop
+    got = host_loop.degrade_mco_gpu(frames[:4], [cv2.cvtColor(m, cv2.COLOR_BGR2GRAY) for m in masks[:4]])
+    ref = loops.mco_compress(frames[:4], masks[:4])
+    d = np.abs(got.astype(int) - np.stack(ref).astype(int))
+    assert np.mean(d <= 2) > 0.97
+
+
+def test_of_window_vote_chunking_matches_reference_statements(dropin_modules):
+    """temporal_smoothing_flow feeds the vote in chunks with carried history: must equal the deque semantics."""
+    from dynamic_video_compression_surveillance_b200 import host_loop
+    from collections import deque
+    r = np.random.default_rng(3)
+    raws = [(r.random((40, 72)) < 0.25).astype(np.uint8) * 255 for _ in range(75)]
+    K, alpha, mk = 30, 0.2, 2
+    kernel = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (mk, mk))
+    q, ref = deque(maxlen=K), []
+    for m in raws:
+        q.append(m)
+        sm = (np.sum(np.array(q), axis=0) >= alpha * len(q) * 255).astype(np.uint8) * 255
+        ref.append(cv2.morphologyEx(cv2.morphologyEx(sm, cv2.MORPH_CLOSE, kernel), cv2.MORPH_OPEN, kernel))
+    got, history, seen = [], [], 0
+    for i in range(0, len(raws), 16):
+        chunk = raws[i:i + 16]
+        got.extend(host_loop.smooth_masks_gpu(chunk, history, K, alpha, mk))
+        allm = history + chunk
+        seen += len(chunk)
+        history = allm if seen < K else allm[-(K - 1):]
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
