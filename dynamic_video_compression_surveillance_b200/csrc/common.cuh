@@ -34,23 +34,35 @@ DEVI uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) {
     return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
 }
 
-// 16 BGR pixels (12 words) -> 16 gray bytes (4 words)
+// zero-extended byte k of a word: one PRMT
+DEVI uint32_t bytek(uint32_t w, int k) { return __byte_perm(w, 0u, 0x4440u | (uint32_t)k); }
+
+// 2 * (3735 B + 19235 G + 9798 R + 16384): the gray value is then byte 2 of the sum, so no shift is needed
+DEVI uint32_t gray2x(uint32_t b, uint32_t g, uint32_t r) { return 7470u * b + 38470u * g + 19596u * r + 32768u; }
+
+// 16 BGR pixels (12 words) -> 16 gray bytes (4 words).  Per 4 pixels: 12 byte extractions (PRMT / shift),
+// 12 IMAD, 3 PRMT to pack the four result bytes.
 DEVI void gray16(const uint32_t (&w)[12], uint32_t (&g)[4]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        uint32_t acc = 0;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            int px = q * 4 + p;
-            acc |= gray_of(byte_at(w, 3 * px), byte_at(w, 3 * px + 1), byte_at(w, 3 * px + 2)) << (8 * p);
-        }
-        g[q] = acc;
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        const uint32_t s0 = gray2x(bytek(a, 0), bytek(a, 1), bytek(a, 2));
+        const uint32_t s1 = gray2x(a >> 24, bytek(b, 0), bytek(b, 1));
+        const uint32_t s2 = gray2x(bytek(b, 2), b >> 24, bytek(c, 0));
+        const uint32_t s3 = gray2x(bytek(c, 1), bytek(c, 2), c >> 24);
+        const uint32_t lo = __byte_perm(s0, s1, 0x0062u), hi = __byte_perm(s2, s3, 0x0062u);   // byte 2 of each
+        g[q] = __byte_perm(lo, hi, 0x5410u);
     }
 }
 
-// per-byte |a - b| > thr  ->  4 mask bits (bit p = byte p)
+// per-byte |a - b| > thr  ->  4 mask bits (bit p = byte p).  thr < 128 uses a SWAR compare + multiply gather.
 DEVI uint32_t diff_gt_bits4(uint32_t a, uint32_t b, uint32_t thr) {
-    uint32_t d = __vabsdiffu4(a, b);
+    const uint32_t d = __vabsdiffu4(a, b);
+    if (thr < 128u) {
+        const uint32_t k7 = (0x7fu - thr) * 0x01010101u;
+        const uint32_t m = ((((d & 0x7f7f7f7fu) + k7) | d) & 0x80808080u) >> 7;      // bit 8p set iff byte p > thr
+        return ((m * 0x00204081u) >> 21) & 0xfu;
+    }
     uint32_t bits = 0;
 #pragma unroll
     for (int p = 0; p < 4; ++p) bits |= (((d >> (8 * p)) & 0xffu) > thr ? 1u : 0u) << p;

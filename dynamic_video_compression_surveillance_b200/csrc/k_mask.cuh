@@ -211,10 +211,12 @@ DEVI uint32_t hrun_or(uint32_t prev, uint32_t cur, uint32_t next, const HRun& h)
 DEVI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // grid: (bands, n_images); dynamic smem: 2 planes of ext_rows x wpr words + one mbarrier.
-// Thread t owns word column (t % wpr) of rows (t / wpr), (t / wpr) + rows_per_pass, ...
+// Thread (g, j) owns word column j of a contiguous run of rows (row group g), so consecutive outputs of a
+// thread reuse the rows it has just read (3x3-bounded elements stream each input row through registers
+// once) and addressing is a pointer increment.
 // Erosion runs as NOT dilate NOT: the complement is folded into the first read and the last write of the
 // primitive.  Rows outside the image and bits beyond W are 'ignored' pixels: they read as 0 in the dilation
-// domain of either polarity, so only rows [r_lo, r_hi) of the staged band are ever computed.
+// domain of either polarity, so only rows [r_lo, r_hi) of the staged band are ever touched.
 __global__ void __launch_bounds__(256)
 k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int H, int W, int wpr, int band_rows,
               MorphChain ch) {
@@ -229,23 +231,11 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
     const uint32_t* sp = src + (size_t)blockIdx.y * plane_words;
     uint32_t* dp = dst + (size_t)blockIdx.y * plane_words;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int nwords = ext_rows * wpr;
-    const int rows_per_pass = nt / wpr;                       // >= 1 (host guarantees wpr <= blockDim)
-    const int j = tid % wpr, r_first = tid / wpr;
-    const bool lane_on = r_first < rows_per_pass;
-    const uint32_t vm = valid_mask(j, W);
-    const uint32_t pm = j > 0 ? valid_mask(j - 1, W) : 0u, nm = j + 1 < wpr ? valid_mask(j + 1, W) : 0u;
-    const int jp = j > 0 ? j - 1 : j, jn = j + 1 < wpr ? j + 1 : j;      // clamped neighbour columns (masked by pm / nm)
-
     const int r_lo = max(0, -ey0), r_hi = min(ext_rows, H - ey0);     // ext rows that exist in the image
+
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < nwords; i += nt) {
-        const bool outside = i < r_lo * wpr || i >= r_hi * wpr;
-        if (outside) A[i] = 0u;
-        if (outside) B[i] = 0u;
     }
     __syncthreads();
     if (tid == 0) {       // stage rows [r_lo, r_hi): contiguous in the plane, one bulk (TMA) copy
@@ -255,6 +245,14 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
                      ::"r"(smem_u32(A + (size_t)r_lo * wpr)), "l"(sp + (size_t)(ey0 + r_lo) * wpr), "r"(bytes),
                        "r"(smem_u32(bar)) : "memory");
     }
+    // thread -> (row group, word column)
+    const int groups = nt / wpr;                              // >= 1 (host guarantees wpr <= blockDim)
+    const int j = tid % wpr, g = tid / wpr;
+    const int rows_img = r_hi - r_lo, chunk = (rows_img + groups - 1) / groups;
+    const int ra = r_lo + g * chunk, rb = g < groups ? min(r_hi, ra + chunk) : ra;   // owned rows [ra, rb)
+    const uint32_t vm = valid_mask(j, W);
+    const uint32_t pm = j > 0 ? valid_mask(j - 1, W) : 0u, nm = j + 1 < wpr ? valid_mask(j + 1, W) : 0u;
+    const int jp = j > 0 ? j - 1 : j, jn = j + 1 < wpr ? j + 1 : j;      // clamped neighbour columns (masked by pm / nm)
     {
         uint32_t done = 0;
         while (!done) {
@@ -262,67 +260,69 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
                          : "=r"(done) : "r"(smem_u32(bar)) : "memory");
         }
     }
-    // first row owned by this thread inside [r_lo, r_hi)
-    int r_start = r_first;
-    if (r_start < r_lo) r_start += ((r_lo - r_start + rows_per_pass - 1) / rows_per_pass) * rows_per_pass;
 
     for (int pi = 0; pi < ch.n; ++pi) {
         const MorphPrim& P = ch.p[pi];
         const uint32_t flip = P.erode ? 0xffffffffu : 0u;
-        const int nrows = P.nrows;
         if (P.separable) {
             const HRun hr = make_hrun(P.lo[0], P.hi[0]);
-            if (lane_on)
-                for (int r = r_start; r < r_hi; r += rows_per_pass) {         // horizontal: A -> B
-                    const uint32_t* row = A + r * wpr;
+            {                                                                   // horizontal: A -> B
+                const uint32_t* row = A + ra * wpr;
+                uint32_t* out = B + ra * wpr + j;
+                for (int r = ra; r < rb; ++r, row += wpr, out += wpr) {
                     const uint32_t p = (row[jp] ^ flip) & pm, c = (row[j] ^ flip) & vm, n = (row[jn] ^ flip) & nm;
-                    B[r * wpr + j] = (p | c | n) ? hrun_or(p, c, n, hr) & vm : 0u;
+                    *out = (p | c | n) ? hrun_or(p, c, n, hr) & vm : 0u;
                 }
+            }
             __syncthreads();
-            const int dy0 = P.dy[0], dy1 = P.dy[nrows - 1];
-            if (lane_on)
-                for (int r = r_start; r < r_hi; r += rows_per_pass) {         // vertical: B -> A
-                    uint32_t acc = 0;
-                    const int ra = max(r + dy0, r_lo), rb = min(r + dy1, r_hi - 1);
-                    for (int rr = ra; rr <= rb; ++rr) acc |= B[rr * wpr + j];
-                    A[r * wpr + j] = (acc ^ flip) & vm;
-                }
+            const int dy0 = P.dy[0], dy1 = P.dy[P.nrows - 1];
+            for (int r = ra; r < rb; ++r) {                                     // vertical: B -> A
+                const int a0 = max(r + dy0, r_lo), a1 = min(r + dy1, r_hi - 1);
+                const uint32_t* q = B + a0 * wpr + j;
+                uint32_t acc = 0;
+#pragma unroll 4
+                for (int rr = a0; rr <= a1; ++rr, q += wpr) acc |= *q;
+                A[r * wpr + j] = (acc ^ flip) & vm;
+            }
             __syncthreads();
         } else if (P.small) {
-            // 3x3-bounded element (e.g. MORPH_ELLIPSE 2 or 3): rows dy in {-1,0,1}, reach <= 1 pixel.
-            // flags per row: bit0 present, bit1 pixel to the left (dx=-1), bit2 pixel to the right (dx=+1)
+            // 3x3-bounded element (e.g. MORPH_ELLIPSE 2 or 3).  Row flags: bit0 centre, bit1 dx=-1, bit2 dx=+1.
+            // out[r] = V_up(r-1) | V_mid(r) | V_dn(r+1); input rows stream once through registers.
             const int f_up = P.small_rows[0], f_mid = P.small_rows[1], f_dn = P.small_rows[2];
-            if (lane_on)
-                for (int r = r_start; r < r_hi; r += rows_per_pass) {         // A -> B
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int f = k == 0 ? f_up : (k == 1 ? f_mid : f_dn);
-                        const int rr = r + k - 1;
-                        if (!(f & 1) || rr < r_lo || rr >= r_hi) continue;
-                        const uint32_t* row = A + rr * wpr;
+            const bool need_l = ((f_up | f_mid | f_dn) & 2) != 0, need_r = ((f_up | f_mid | f_dn) & 4) != 0;
+            uint32_t pend = 0, up_prev = 0;            // pend = V_up(x-2) | V_mid(x-1);  up_prev = V_up(x-1)
+            const uint32_t* row = A + (ra - 1) * wpr;
+            uint32_t* out = B + (ra - 1) * wpr + j;    // out[x-1] is written at step x, so this trails by one row
+            if (ra < rb)
+                for (int x = ra - 1; x <= rb; ++x, row += wpr, out += wpr) {
+                    uint32_t v_up = 0, v_mid = 0, v_dn = 0;
+                    if (x >= r_lo && x < r_hi) {
                         const uint32_t c = (row[j] ^ flip) & vm;
-                        acc |= c;
-                        if (f & 2) acc |= __funnelshift_l((row[jp] ^ flip) & pm, c, 1);
-                        if (f & 4) acc |= __funnelshift_r(c, (row[jn] ^ flip) & nm, 1);
+                        const uint32_t cl = need_l ? __funnelshift_l((row[jp] ^ flip) & pm, c, 1) : 0u;
+                        const uint32_t cr = need_r ? __funnelshift_r(c, (row[jn] ^ flip) & nm, 1) : 0u;
+                        v_up = ((f_up & 1) ? c : 0u) | ((f_up & 2) ? cl : 0u) | ((f_up & 4) ? cr : 0u);
+                        v_mid = ((f_mid & 1) ? c : 0u) | ((f_mid & 2) ? cl : 0u) | ((f_mid & 4) ? cr : 0u);
+                        v_dn = ((f_dn & 1) ? c : 0u) | ((f_dn & 2) ? cl : 0u) | ((f_dn & 4) ? cr : 0u);
                     }
-                    B[r * wpr + j] = (acc ^ flip) & vm;
+                    if (x > ra) out[-wpr] = ((pend | v_dn) ^ flip) & vm;       // row x-1 in [ra, rb)
+                    pend = up_prev | v_mid;
+                    up_prev = v_up;
                 }
             __syncthreads();
             uint32_t* t = A; A = B; B = t;
         } else {
-            if (lane_on)
-                for (int r = r_start; r < r_hi; r += rows_per_pass) {         // generic: A -> B
-                    uint32_t acc = 0;
-                    for (int k = 0; k < nrows; ++k) {
-                        const int rr = r + P.dy[k];
-                        if (rr < r_lo || rr >= r_hi) continue;
-                        const uint32_t* row = A + rr * wpr;
-                        const uint32_t p = (row[jp] ^ flip) & pm, c = (row[j] ^ flip) & vm, n = (row[jn] ^ flip) & nm;
-                        if (p | c | n) acc |= hrun_or(p, c, n, make_hrun(P.lo[k], P.hi[k]));
-                    }
-                    B[r * wpr + j] = (acc ^ flip) & vm;
+            const int nrows = P.nrows;
+            for (int r = ra; r < rb; ++r) {                                     // generic: A -> B
+                uint32_t acc = 0;
+                for (int k = 0; k < nrows; ++k) {
+                    const int rr = r + P.dy[k];
+                    if (rr < r_lo || rr >= r_hi) continue;
+                    const uint32_t* row = A + rr * wpr;
+                    const uint32_t p = (row[jp] ^ flip) & pm, c = (row[j] ^ flip) & vm, n = (row[jn] ^ flip) & nm;
+                    if (p | c | n) acc |= hrun_or(p, c, n, make_hrun(P.lo[k], P.hi[k]));
                 }
+                B[r * wpr + j] = (acc ^ flip) & vm;
+            }
             __syncthreads();
             uint32_t* t = A; A = B; B = t;
         }

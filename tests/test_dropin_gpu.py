@@ -93,8 +93,10 @@ def test_process_single_video_fd(tmp_path, dropin_modules):
     assert stats["motion_pixels"] == int(sum((a > 127).sum() for a in ref["acc"]))
     # and the full entry point with its banner
     fd.process_single_video_fd(src, str(tmp_path / "out2"))
-    log = open(os.path.join(str(tmp_path / "out2"), "cam0", "processing.log")).read()
-    assert "Execution statistics saved in" in log
+    # (logging.basicConfig is a no-op once the root logger has handlers -- true of the reference too,
+    # frame_differencing.py:13-14 -- so only the file's existence is part of the contract)
+    assert os.path.exists(os.path.join(str(tmp_path / "out2"), "cam0", "processing.log"))
+    assert os.path.exists(os.path.join(str(tmp_path / "out2"), "cam0", "execution_times.txt"))
 
 
 def test_fd_error_convention(tmp_path, dropin_modules):
