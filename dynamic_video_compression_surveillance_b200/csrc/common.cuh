@@ -55,6 +55,26 @@ DEVI void gray16(const uint32_t (&w)[12], uint32_t (&g)[4]) {
     }
 }
 
+// Same result through IDP.4A: each coefficient of 2*(3735, 19235, 9798) is split into a high and a low byte,
+// s = 256 * dot(px, hi) + dot(px, lo) + 32768; pixels that straddle two words chain two dot products.
+DEVI void gray16_dp4a(const uint32_t (&w)[12], uint32_t (&g)[4]) {
+    // little-endian coefficient words for a pixel whose B byte sits at byte 0 / 3 / 2 / 1 of its first word
+    const uint32_t L0 = 46u | (70u << 8) | (140u << 16), H0 = 29u | (150u << 8) | (76u << 16);          // B G R .
+    const uint32_t L1a = 46u << 24, H1a = 29u << 24, L1b = 70u | (140u << 8), H1b = 150u | (76u << 8);   // ...B | G R
+    const uint32_t L2a = (46u << 16) | (70u << 24), H2a = (29u << 16) | (150u << 24), L2b = 140u, H2b = 76u;   // ..BG | R
+    const uint32_t L3 = (46u << 8) | (70u << 16) | (140u << 24), H3 = (29u << 8) | (150u << 16) | (76u << 24); // .BGR
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        const uint32_t s0 = (__dp4a(a, H0, 0u) << 8) + __dp4a(a, L0, 32768u);
+        const uint32_t s1 = (__dp4a(b, H1b, __dp4a(a, H1a, 0u)) << 8) + __dp4a(b, L1b, __dp4a(a, L1a, 32768u));
+        const uint32_t s2 = (__dp4a(c, H2b, __dp4a(b, H2a, 0u)) << 8) + __dp4a(c, L2b, __dp4a(b, L2a, 32768u));
+        const uint32_t s3 = (__dp4a(c, H3, 0u) << 8) + __dp4a(c, L3, 32768u);
+        const uint32_t lo = __byte_perm(s0, s1, 0x0062u), hi = __byte_perm(s2, s3, 0x0062u);
+        g[q] = __byte_perm(lo, hi, 0x5410u);
+    }
+}
+
 // per-byte |a - b| > thr  ->  4 mask bits (bit p = byte p).  thr < 128 uses a SWAR compare + multiply gather.
 DEVI uint32_t diff_gt_bits4(uint32_t a, uint32_t b, uint32_t thr) {
     const uint32_t d = __vabsdiffu4(a, b);

@@ -274,6 +274,7 @@ struct dvc_handle {
     bool aligned;                 // W % 16 == 0: vector paths
     long long n_masks;            // masks produced so far in this stream
     int seg_len;
+    bool gray_dp4a;               // DVC_GRAY_DP4A=1: IDP.4A variant of the gray conversion
     // state
     uint8_t* prev_gray[2];
     int cur;
@@ -353,6 +354,8 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     const int T = cfg->max_batch;
     const char* sl = getenv("DVC_SEG_LEN");
     h->seg_len = sl ? std::max(1, atoi(sl)) : 8;
+    const char* gd = getenv("DVC_GRAY_DP4A");
+    h->gray_dp4a = gd && atoi(gd) != 0;
     CU(cudaSetDevice(cfg->device));
     for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&h->prev_gray[i], h->plane_bytes)); CU(cudaMemset(h->prev_gray[i], 0, h->plane_bytes)); }
     CU(cudaMalloc(&h->bits_a, h->plane_words * 4 * T));
@@ -590,7 +593,9 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         uint8_t* pg_in = h->prev_gray[h->cur];
         uint8_t* pg_out = h->prev_gray[h->cur ^ 1];
         { ProfScope ps(h, DVC_PROF_FRONT, 1, st);
-        if (h->aligned)
+        if (h->aligned && h->gray_dp4a)
+            k_gray_diff_thresh<true, true><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);
+        else if (h->aligned)
             k_gray_diff_thresh<true><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);
         else
             k_gray_diff_thresh<false><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);

@@ -253,13 +253,14 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
     const uint32_t vm = valid_mask(j, W);
     const uint32_t pm = j > 0 ? valid_mask(j - 1, W) : 0u, nm = j + 1 < wpr ? valid_mask(j + 1, W) : 0u;
     const int jp = j > 0 ? j - 1 : j, jn = j + 1 < wpr ? j + 1 : j;      // clamped neighbour columns (masked by pm / nm)
-    {
+    if (tid == 0) {       // one waiter; everybody else parks at the barrier below instead of spinning
         uint32_t done = 0;
         while (!done) {
             asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
                          : "=r"(done) : "r"(smem_u32(bar)) : "memory");
         }
     }
+    __syncthreads();
 
     for (int pi = 0; pi < ch.n; ++pi) {
         const MorphPrim& P = ch.p[pi];

@@ -331,6 +331,26 @@ def test_window_loop_against_oracle(P, cfg, noise):
     pipe.close()
 
 
+def test_window_front_end_dp4a_variant(P, monkeypatch):
+    """DVC_GRAY_DP4A=1 selects the IDP.4A gray conversion in K1: masks must not change (random frames make
+    every gray value matter, threshold 3 keeps the mask non-trivial)."""
+    r = rng(31)
+    h, w, n = 64, 160, 12
+    frames = r.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    frames[1::2] = np.clip(frames[0:-1:2].astype(int) + r.integers(-4, 5, frames[1::2].shape), 0, 255).astype(np.uint8)
+    cfg = dict(window_size=3, alpha_fraction=0.5, morph_kernel=0, kernel_size=0, motion_threshold=3.0)
+    ref = loops.window_loop(list(frames), degrade=False, **cfg)
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DVC_GRAY_DP4A", flag)
+        pipe = P.FramePipeline(w, h, "window", max_batch=16, **cfg)
+        pipe.begin_stream(so.bgr2gray(frames[0]))
+        mk = torch.empty((n - 1, h, w), dtype=torch.uint8, device="cuda")
+        pipe.process_device(dev(frames[1:]), None, None, mk)
+        torch.cuda.synchronize()
+        assert np.array_equal(host(mk), np.stack(ref["mask"])), flag
+        pipe.close()
+
+
 def test_state_handoff_between_handles(P):
     """Frame-chunk sharding: a second handle continues a stream from a state blob."""
     from dynamic_video_compression_surveillance_b200.synth import make_clip
