@@ -88,6 +88,11 @@ static bool make_prim(int shape, int k, bool erode, MorphPrim& p) {
     if (small)
         for (int i = 0; i < n; ++i)
             p.small_rows[p.dy[i] + 1] = (int8_t)(1 | (p.lo[i] == -1 ? 2 : 0) | (p.hi[i] == 1 ? 4 : 0));
+    // kernels specialised at compile time (k_mask.cuh: rect_pass<K>, small_pass<FU,FM,FD>)
+    p.kind = 0;
+    if (sep && shape == DVC_SHAPE_RECT && (k & 1) && k >= 3 && k <= 15) p.kind = (int16_t)(100 + k);
+    if (small && p.small_rows[0] == 1 && p.small_rows[1] == 3 && p.small_rows[2] == 0) p.kind = 1;
+    if (small && p.small_rows[0] == 1 && p.small_rows[1] == 7 && p.small_rows[2] == 1) p.kind = 2;
     return true;
 }
 
@@ -238,7 +243,11 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         qc.k[0] = iq; qc.k[1] = iq * 0.5f; qc.k[2] = iq * 0.25f;
         qc.o[0] = q; qc.o[1] = q * 0.5f; qc.o[2] = q * 0.25f;
         qc.q = q;
-        qc.fast = q >= 8.0f && q <= 1.0e6f;
+        // |t - fl(d/q)| <= 1.5 * 2^-23 * |d/q| and |d/q| <= 512/q (orthonormal 4x4 DCT of values in [-128,127]):
+        // outside a band of 4x that bound around the ties the fast rounding provably equals np.round(d/q).
+        const float band = std::max(1.0e-5f, 4.0f * 1.8e-7f * (512.0f / q));
+        qc.tie_lo = 0.5f - band;
+        qc.fast = band <= 0.01f && q <= 1.0e6f;
         dim3 grid(cdiv((size_t)(W / 8) * (H / 4), 256), n);
         k_degrade4<<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
     } else {

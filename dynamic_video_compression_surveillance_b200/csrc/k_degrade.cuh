@@ -104,7 +104,8 @@ struct QuantConsts {
     float k[3];     // (1/q) * {1, 1/2, 1/4}: forward scale by number of even indices among (row, col)
     float o[3];     // q * {1, 1/2, 1/4}: output scale (pre-applies the inverse butterflies' x0.5)
     float q;
-    int fast;       // magic-number path valid (q large enough that |d/q| * 2^-22 << tie band)
+    float tie_lo;   // coefficients whose distance from the rounded value exceeds this are re-done exactly
+    int fast;       // magic-number path valid (q large enough for tie_lo to be meaningful)
 };
 
 // forward 4-point DCT without the x0.5 on outputs 0 and 2 (folded into QuantConsts::k)
@@ -154,19 +155,26 @@ DEVI void inv_dct_block(float (&v)[4][4]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) dct4_inv_ps(v[0][c], v[1][c], v[2][c], v[3][c]);
 }
-// returns the largest distance of any coefficient from its rounded value (the caller redoes the block with
-// quantise_block_exact when that is close to 1/2)
+// Fast quantiser for a whole block.  The four coefficients with even row and column index are exact
+// integers / 4 (their basis is +-1/2), so real ties (d/q = n + 1/2 exactly) do occur there: they are checked
+// and redone with the IEEE division individually.  The other twelve have irrational basis functions; a value
+// within tie_lo of a rounding tie is a ~1e-5 event, reported through the return value (the caller then redoes
+// the block exactly).
 DEVI float quantise_block_fast(float (&v)[4][4], const QuantConsts& qc) {
-    float tie = 0.0f;
+    float tie = 0.0f, tie_r = 0.0f;
+    const float d00 = v[0][0], d02 = v[0][2], d20 = v[2][0], d22 = v[2][2];
+    v[0][0] = quantise_fast<2>(d00, qc, tie_r); v[0][2] = quantise_fast<2>(d02, qc, tie_r);
+    v[2][0] = quantise_fast<2>(d20, qc, tie_r); v[2][2] = quantise_fast<2>(d22, qc, tie_r);
+    if (tie_r > qc.tie_lo) {
+        v[0][0] = quantise_exact<2>(d00, qc); v[0][2] = quantise_exact<2>(d02, qc);
+        v[2][0] = quantise_exact<2>(d20, qc); v[2][2] = quantise_exact<2>(d22, qc);
+    }
+    v[0][1] = quantise_fast<1>(v[0][1], qc, tie); v[0][3] = quantise_fast<1>(v[0][3], qc, tie);
+    v[2][1] = quantise_fast<1>(v[2][1], qc, tie); v[2][3] = quantise_fast<1>(v[2][3], qc, tie);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        if ((r & 1) == 0) {
-            v[r][0] = quantise_fast<2>(v[r][0], qc, tie); v[r][1] = quantise_fast<1>(v[r][1], qc, tie);
-            v[r][2] = quantise_fast<2>(v[r][2], qc, tie); v[r][3] = quantise_fast<1>(v[r][3], qc, tie);
-        } else {
-            v[r][0] = quantise_fast<1>(v[r][0], qc, tie); v[r][1] = quantise_fast<0>(v[r][1], qc, tie);
-            v[r][2] = quantise_fast<1>(v[r][2], qc, tie); v[r][3] = quantise_fast<0>(v[r][3], qc, tie);
-        }
+    for (int r = 1; r < 4; r += 2) {
+        v[r][0] = quantise_fast<1>(v[r][0], qc, tie); v[r][1] = quantise_fast<0>(v[r][1], qc, tie);
+        v[r][2] = quantise_fast<1>(v[r][2], qc, tie); v[r][3] = quantise_fast<0>(v[r][3], qc, tie);
     }
     return tie;
 }
@@ -188,12 +196,30 @@ DEVI float luma_m128_f(uint32_t b, uint32_t g, uint32_t r) {
     const uint32_t y = (1868u * b + 9617u * g + 4899u * r + 8192u) >> 14;
     return __fsub_rn(__uint_as_float(0x4B000000u | y), 8388736.0f);      // 2^23 + 128
 }
-// luma - 128 of the four pixels held in three packed BGR words
+// luma - 128 of the four pixels held in three packed BGR words.
+// Y << 14 = 1868 B + 9617 G + 4899 R + 8192 is evaluated with IDP.4A on the packed words (no byte extraction):
+// each coefficient is split into a high and a low byte, sum = 256 * dot(px, hi) + dot(px, lo).
+DEVI float luma_from_sum(uint32_t hi, uint32_t lo) {
+    const uint32_t y = ((hi << 8) + lo) >> 14;
+    return __fsub_rn(__uint_as_float(0x4B000000u | y), 8388736.0f);      // 2^23 + 128
+}
 DEVI void luma_row4(uint32_t w0, uint32_t w1, uint32_t w2, float (&v)[4]) {
+#ifdef DVC_LUMA_NO_DP4A
     v[0] = luma_m128_f(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
     v[1] = luma_m128_f(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
     v[2] = luma_m128_f((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
     v[3] = luma_m128_f((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
+#else
+    // 1868 = 7*256+76, 9617 = 37*256+145, 4899 = 19*256+35
+    const uint32_t L0 = 76u | (145u << 8) | (35u << 16), H0 = 7u | (37u << 8) | (19u << 16);            // B G R .
+    const uint32_t L1a = 76u << 24, H1a = 7u << 24, L1b = 145u | (35u << 8), H1b = 37u | (19u << 8);     // ...B | G R
+    const uint32_t L2a = (76u << 16) | (145u << 24), H2a = (7u << 16) | (37u << 24), L2b = 35u, H2b = 19u;  // ..BG | R
+    const uint32_t L3 = (76u << 8) | (145u << 16) | (35u << 24), H3 = (7u << 8) | (37u << 16) | (19u << 24); // .BGR
+    v[0] = luma_from_sum(__dp4a(w0, H0, 0u), __dp4a(w0, L0, 8192u));
+    v[1] = luma_from_sum(__dp4a(w1, H1b, __dp4a(w0, H1a, 0u)), __dp4a(w1, L1b, __dp4a(w0, L1a, 8192u)));
+    v[2] = luma_from_sum(__dp4a(w2, H2b, __dp4a(w1, H2a, 0u)), __dp4a(w2, L2b, __dp4a(w1, L2a, 8192u)));
+    v[3] = luma_from_sum(__dp4a(w2, H3, 0u), __dp4a(w2, L3, 8192u));
+#endif
 }
 // np.clip(v + 128, 0, 255) stored to uint8 (truncation): one saturating round-toward-zero conversion
 DEVI uint32_t out_byte_bits(float v) {
@@ -271,7 +297,7 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
                 for (int r = 0; r < 4; ++r) luma_row4(w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2], v[r]);
                 fwd_dct_block(v);
                 const float tie = quantise_block_fast(v, qc);
-                if (!qc.fast || tie > 0.499f) {          // rare: a coefficient within 1e-3 of a tie (or tiny q)
+                if (!qc.fast || tie > qc.tie_lo) {       // rare (~1e-4 of blocks): near-tie on an irrational coefficient
 #pragma unroll
                     for (int r = 0; r < 4; ++r) luma_row4(w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2], v[r]);
                     fwd_dct_block(v);

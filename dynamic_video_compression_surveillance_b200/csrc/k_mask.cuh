@@ -161,6 +161,7 @@ struct MorphPrim {
     int8_t separable;                  // all rows share one run and rows are contiguous
     int8_t nrows;                      // rows of the structuring element that are non-empty
     int8_t small;                      // fits in 3x3 around the anchor: small_rows[] holds per-row flags
+    int16_t kind;                      // 0 = runtime paths; 1xx = rect_pass<xx>; 1, 2 = small_pass specialisations
     int8_t small_rows[3];              // dy = -1, 0, +1: bit0 present, bit1 dx=-1 present, bit2 dx=+1 present
     int8_t dy[MORPH_MAX_K];            // row offset (kernel row - anchor)
     int8_t lo[MORPH_MAX_K];            // run of column offsets [lo, hi] in that row
@@ -209,6 +210,89 @@ DEVI uint32_t hrun_or(uint32_t prev, uint32_t cur, uint32_t next, const HRun& h)
 }
 
 DEVI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Shared per-thread view of the staged band used by the primitive passes.
+struct BandCtx {
+    int wpr, j, jp, jn, ra, rb, r_lo, r_hi;
+    uint32_t vm, pm, nm;
+};
+
+// OR over a compile-time window: NR = right reach + 1 (bits x .. x+NR-1), NL = left reach + 1
+template <int NR, int NL>
+DEVI uint32_t hrun_or_c(uint32_t prev, uint32_t cur, uint32_t next) {
+    uint32_t res = cur;
+    if (NR > 1) {
+        uint64_t a = ((uint64_t)next << 32) | cur;
+        int c = 1;
+#pragma unroll
+        for (int s = 1; s <= 16; s *= 2) if (NR >= 2 * s) { a |= a >> s; c = 2 * s; }
+        if (NR > c) a |= a >> (NR - c);
+        res |= (uint32_t)a;
+    }
+    if (NL > 1) {
+        uint64_t b = ((uint64_t)cur << 32) | prev;
+        int c = 1;
+#pragma unroll
+        for (int s = 1; s <= 16; s *= 2) if (NL >= 2 * s) { b |= b << s; c = 2 * s; }
+        if (NL > c) b |= b << (NL - c);
+        res |= (uint32_t)(b >> 32);
+    }
+    return res;
+}
+
+// k x k rectangle, k odd (anchor in the middle): horizontal pass A -> B, vertical pass B -> A
+template <int K>
+DEVI void rect_pass(uint32_t* A, uint32_t* B, const BandCtx& c, uint32_t flip) {
+    constexpr int R = K / 2;
+    {
+        const uint32_t* row = A + c.ra * c.wpr;
+        uint32_t* out = B + c.ra * c.wpr + c.j;
+        for (int r = c.ra; r < c.rb; ++r, row += c.wpr, out += c.wpr) {
+            const uint32_t p = (row[c.jp] ^ flip) & c.pm, x = (row[c.j] ^ flip) & c.vm, n = (row[c.jn] ^ flip) & c.nm;
+            *out = hrun_or_c<R + 1, R + 1>(p, x, n) & c.vm;
+        }
+    }
+    __syncthreads();
+    for (int r = c.ra; r < c.rb; ++r) {
+        uint32_t acc = 0;
+        if (r - R >= c.r_lo && r + R < c.r_hi) {
+            const uint32_t* q = B + (r - R) * c.wpr + c.j;
+#pragma unroll
+            for (int d = 0; d < K; ++d) acc |= q[d * c.wpr];
+        } else {
+            const int a0 = max(r - R, c.r_lo), a1 = min(r + R, c.r_hi - 1);
+            for (int rr = a0; rr <= a1; ++rr) acc |= B[rr * c.wpr + c.j];
+        }
+        A[r * c.wpr + c.j] = (acc ^ flip) & c.vm;
+    }
+    __syncthreads();
+}
+
+// 3x3-bounded element with compile-time row flags (bit0 centre, bit1 dx=-1, bit2 dx=+1): A -> B.
+// out[r] = V_up(r-1) | V_mid(r) | V_dn(r+1); every input row streams once through registers.
+template <int FU, int FM, int FD>
+DEVI void small_pass(const uint32_t* A, uint32_t* B, const BandCtx& c, uint32_t flip) {
+    constexpr bool NEED_L = ((FU | FM | FD) & 2) != 0, NEED_R = ((FU | FM | FD) & 4) != 0;
+    uint32_t pend = 0, up_prev = 0;            // pend = V_up(x-2) | V_mid(x-1);  up_prev = V_up(x-1)
+    const uint32_t* row = A + (c.ra - 1) * c.wpr;
+    uint32_t* out = B + (c.ra - 1) * c.wpr + c.j;
+    if (c.ra < c.rb)
+        for (int x = c.ra - 1; x <= c.rb; ++x, row += c.wpr, out += c.wpr) {
+            uint32_t v_up = 0, v_mid = 0, v_dn = 0;
+            if (x >= c.r_lo && x < c.r_hi) {
+                const uint32_t m = (row[c.j] ^ flip) & c.vm;
+                const uint32_t cl = NEED_L ? __funnelshift_l((row[c.jp] ^ flip) & c.pm, m, 1) : 0u;
+                const uint32_t cr = NEED_R ? __funnelshift_r(m, (row[c.jn] ^ flip) & c.nm, 1) : 0u;
+                v_up = ((FU & 1) ? m : 0u) | ((FU & 2) ? cl : 0u) | ((FU & 4) ? cr : 0u);
+                v_mid = ((FM & 1) ? m : 0u) | ((FM & 2) ? cl : 0u) | ((FM & 4) ? cr : 0u);
+                v_dn = ((FD & 1) ? m : 0u) | ((FD & 2) ? cl : 0u) | ((FD & 4) ? cr : 0u);
+            }
+            if (x > c.ra) out[-c.wpr] = ((pend | v_dn) ^ flip) & c.vm;        // row x-1 in [ra, rb)
+            pend = up_prev | v_mid;
+            up_prev = v_up;
+        }
+    __syncthreads();
+}
 
 // grid: (bands, n_images); dynamic smem: 2 planes of ext_rows x wpr words + one mbarrier.
 // Thread (g, j) owns word column j of a contiguous run of rows (row group g), so consecutive outputs of a
@@ -262,9 +346,31 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
     }
     __syncthreads();
 
+    BandCtx cx;
+    cx.wpr = wpr; cx.j = j; cx.jp = jp; cx.jn = jn; cx.ra = ra; cx.rb = rb; cx.r_lo = r_lo; cx.r_hi = r_hi;
+    cx.vm = vm; cx.pm = pm; cx.nm = nm;
+
     for (int pi = 0; pi < ch.n; ++pi) {
         const MorphPrim& P = ch.p[pi];
         const uint32_t flip = P.erode ? 0xffffffffu : 0u;
+        // compile-time specialisations of the common elements
+        if (P.kind != 0) {
+            bool swap = true;
+            switch (P.kind) {
+                case 103: rect_pass<3>(A, B, cx, flip); swap = false; break;
+                case 105: rect_pass<5>(A, B, cx, flip); swap = false; break;
+                case 107: rect_pass<7>(A, B, cx, flip); swap = false; break;
+                case 109: rect_pass<9>(A, B, cx, flip); swap = false; break;
+                case 111: rect_pass<11>(A, B, cx, flip); swap = false; break;
+                case 113: rect_pass<13>(A, B, cx, flip); swap = false; break;
+                case 115: rect_pass<15>(A, B, cx, flip); swap = false; break;
+                case 1: small_pass<1, 3, 0>(A, B, cx, flip); break;     // MORPH_ELLIPSE 2x2
+                case 2: small_pass<1, 7, 1>(A, B, cx, flip); break;     // MORPH_ELLIPSE 3x3 (a cross)
+                default: break;
+            }
+            if (swap) { uint32_t* t = A; A = B; B = t; }
+            continue;
+        }
         if (P.separable) {
             const HRun hr = make_hrun(P.lo[0], P.hi[0]);
             {                                                                   // horizontal: A -> B

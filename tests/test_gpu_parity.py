@@ -68,8 +68,8 @@ def test_gray_absdiff_thresh(P, shape, blur5):
 
 
 @pytest.mark.parametrize("shape", [(1, 1), (3, 5), (17, 33), (48, 70), (101, 130), (64, 300)])
-@pytest.mark.parametrize("kind,k", [("rect", 1), ("rect", 2), ("rect", 3), ("rect", 7), ("rect", 10), ("rect", 15),
-                                    ("rect", 33), ("ellipse", 2), ("ellipse", 3), ("ellipse", 5), ("ellipse", 9)])
+@pytest.mark.parametrize("kind,k", [("rect", 1), ("rect", 2), ("rect", 3), ("rect", 5), ("rect", 7), ("rect", 9), ("rect", 10), ("rect", 11),
+                                    ("rect", 13), ("rect", 15), ("rect", 33), ("ellipse", 2), ("ellipse", 3), ("ellipse", 5), ("ellipse", 9)])
 def test_morphology(P, shape, kind, k):
     r = rng(5)
     kernel = so.structuring_rect(k) if kind == "rect" else so.structuring_ellipse(k)
