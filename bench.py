@@ -37,12 +37,12 @@ ACTUAL_LOOP_BYTES_PER_PX = 3 + 1.0 / 8 + K4_ALG_BYTES_PER_PX + 4 * (1.0 / 8)   #
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--frames", type=int, default=1800)
     p.add_argument("--resolution", default="1080p")
-    p.add_argument("--max-batch", type=int, default=int(os.environ.get("DVC_BENCH_BATCH", "64")))
+    p.add_argument("--max-batch", type=int, default=int(os.environ.get("DVC_BENCH_BATCH", "128")))
     p.add_argument("--e2e-frames", type=int, default=256)
     p.add_argument("--mode", default="window", choices=["window", "fd"])
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -70,7 +70,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -86,6 +86,7 @@ class ClockSampler:
             self.proc.kill()
             out = ""
         sm, mx, reasons = [], [], set()
+        self.power_max = None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
@@ -93,13 +94,15 @@ class ClockSampler:
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
+                self.power_max = max(self.power_max or 0.0, float(f[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sm_mhz_min": min(sm) if sm else None,
+                "power_w_max": self.power_max}
 
 
 # ---------------------------------------------------------------------------------------------------

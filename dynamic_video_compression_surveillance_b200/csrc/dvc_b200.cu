@@ -249,7 +249,9 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         qc.tie_lo = 0.5f - band;
         qc.fast = band <= 0.01f && q <= 1.0e6f;
         dim3 grid(cdiv((size_t)(W / 8) * (H / 4), 256), n);
-        k_degrade4<<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
+        static const bool luma_dp4a = [] { const char* e = getenv("DVC_LUMA_DP4A"); return e ? atoi(e) != 0 : true; }();
+        if (luma_dp4a) k_degrade4<true><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
+        else k_degrade4<false><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
     } else {
         int rc = ensure_dct8(ERRBUF);
         if (rc) return rc;

@@ -203,13 +203,14 @@ DEVI float luma_from_sum(uint32_t hi, uint32_t lo) {
     const uint32_t y = ((hi << 8) + lo) >> 14;
     return __fsub_rn(__uint_as_float(0x4B000000u | y), 8388736.0f);      // 2^23 + 128
 }
+template <bool DP4A>
 DEVI void luma_row4(uint32_t w0, uint32_t w1, uint32_t w2, float (&v)[4]) {
-#ifdef DVC_LUMA_NO_DP4A
+  if (!DP4A) {
     v[0] = luma_m128_f(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
     v[1] = luma_m128_f(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
     v[2] = luma_m128_f((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
     v[3] = luma_m128_f((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
-#else
+  } else {
     // 1868 = 7*256+76, 9617 = 37*256+145, 4899 = 19*256+35
     const uint32_t L0 = 76u | (145u << 8) | (35u << 16), H0 = 7u | (37u << 8) | (19u << 16);            // B G R .
     const uint32_t L1a = 76u << 24, H1a = 7u << 24, L1b = 145u | (35u << 8), H1b = 37u | (19u << 8);     // ...B | G R
@@ -219,7 +220,7 @@ DEVI void luma_row4(uint32_t w0, uint32_t w1, uint32_t w2, float (&v)[4]) {
     v[1] = luma_from_sum(__dp4a(w1, H1b, __dp4a(w0, H1a, 0u)), __dp4a(w1, L1b, __dp4a(w0, L1a, 8192u)));
     v[2] = luma_from_sum(__dp4a(w2, H2b, __dp4a(w1, H2a, 0u)), __dp4a(w2, L2b, __dp4a(w1, L2a, 8192u)));
     v[3] = luma_from_sum(__dp4a(w2, H3, 0u), __dp4a(w2, L3, 8192u));
-#endif
+  }
 }
 // np.clip(v + 128, 0, 255) stored to uint8 (truncation): one saturating round-toward-zero conversion
 DEVI uint32_t out_byte_bits(float v) {
@@ -228,6 +229,7 @@ DEVI uint32_t out_byte_bits(float v) {
     return r;
 }
 
+template <bool DP4A>
 __global__ void __launch_bounds__(256, 4)
 k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127,
            const uint32_t* __restrict__ nonzero, uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay,
@@ -294,12 +296,12 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
             if (is_static) {
                 float v[4][4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) luma_row4(w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2], v[r]);
+                for (int r = 0; r < 4; ++r) luma_row4<DP4A>(w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2], v[r]);
                 fwd_dct_block(v);
                 const float tie = quantise_block_fast(v, qc);
                 if (!qc.fast || tie > qc.tie_lo) {       // rare (~1e-4 of blocks): near-tie on an irrational coefficient
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) luma_row4(w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2], v[r]);
+                    for (int r = 0; r < 4; ++r) luma_row4<DP4A>(w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2], v[r]);
                     fwd_dct_block(v);
                     quantise_block_exact(v, qc);
                 }
