@@ -62,7 +62,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
@@ -74,6 +74,11 @@ class ClockSampler:
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Start of the timed region: samples before this wall-clock instant are ignored."""
+        import datetime
+        self.t_mark = datetime.datetime.now()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -93,6 +98,10 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
+                import datetime
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                if getattr(self, "t_mark", None) and ts < self.t_mark:
+                    continue
                 sm.append(float(f[1])); mx.append(float(f[2]))
                 self.power_max = max(self.power_max or 0.0, float(f[3]))
             except ValueError:
@@ -234,17 +243,18 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # started early: nvidia-smi's own start-up must not fall into the timed region
     for _ in range(max(3, args.warmup)):
         one_pass()
     barrier()
-    sampler = ClockSampler(local_rank)
     launches0 = pipe.launch_count()
     pipe.profile(True)
     pipe.profile_read()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if rank == 0:
-        sampler.start()
     barrier()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         one_pass()

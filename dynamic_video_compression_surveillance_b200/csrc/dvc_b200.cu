@@ -187,11 +187,12 @@ static int launch_contour_filter(char* ERRBUF, const uint32_t* raw, uint32_t* ou
         const int m = std::min(sc.frames, n - i0);
         dim3 grid(cdiv(pw, 256), m);
         const uint32_t* r = raw + (size_t)i0 * pw;
-        k_ccl_init<true><<<grid, 256, 0, st>>>(r, sc.parents_a, nullptr, H, W, wpr);
-        k_ccl_union<true, 4, true><<<grid, 256, 0, st>>>(r, sc.parents_a, H, W, wpr);
+        dim3 grow((H + 7) / 8, m);
+        k_ccl_rowlink<true, true><<<grow, 256, 0, st>>>(r, sc.parents_a, nullptr, H, W, wpr);
+        k_ccl_union<true, 4><<<grid, 256, 0, st>>>(r, sc.parents_a, H, W, wpr);
         k_ccl_fill<<<grid, 256, 0, st>>>(r, sc.parents_a, sc.filled, H, W, wpr);
-        k_ccl_init<false><<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, H, W, wpr);
-        k_ccl_union<false, 8, false><<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, H, W, wpr);
+        k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, H, W, wpr);
+        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, H, W, wpr);
         k_ccl_area<<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, H, W, wpr);
         k_ccl_select<<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, out + (size_t)i0 * pw, H, W, wpr, thr);
         CHECK_LAUNCH();
@@ -382,7 +383,7 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
         CU(cudaMalloc(&h->acc, h->plane_bytes));
         CU(cudaMemset(h->acc, 0, h->plane_bytes));
         CU(cudaMalloc(&h->blurred, h->plane_bytes * T));
-        int rc = ccl_scratch_alloc(h->err, h->ccl, std::min(T, 16), h->H, h->W);
+        int rc = ccl_scratch_alloc(h->err, h->ccl, std::min(T, 64), h->H, h->W);
         if (rc) return rc;
         if (cfg->kernel_size > 0 && !chain_push(h->chain, DVC_MORPH_DILATE, DVC_SHAPE_RECT, cfg->kernel_size))
             return set_err(h->err, DVC_ERR_UNSUPPORTED, "kernel_size %d: supported range is 1..%d", cfg->kernel_size, MORPH_MAX_K);

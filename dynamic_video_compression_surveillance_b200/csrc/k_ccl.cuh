@@ -58,50 +58,86 @@ DEVI uint32_t plane_word(const uint32_t* plane, int y, int j, int H, int W, int 
     return INVERT ? (~w & valid_mask(j, W)) : w;
 }
 
-// ---- init: every run becomes its own set -------------------------------------------------------
-template <bool INVERT>
+// ---- init + horizontal linking: one warp per image row ------------------------------------------------
+// Every run inside a word becomes a node; a run that continues from the previous word (bit 31 of word j-1
+// and bit 0 of word j both set) is pointed straight at the head of the whole horizontal run, found with
+// warp ballots over "word is all ones and linked" -- no atomics, depth 1.  With BORDER (phase A) runs that
+// touch the image border are rooted at node 0 ("outside") directly, so an empty mask needs no union at all.
+template <bool INVERT, bool BORDER>
 __global__ void __launch_bounds__(256)
-k_ccl_init(const uint32_t* __restrict__ planes, int* __restrict__ parents, int* __restrict__ areas, int H, int W,
-           int wpr) {
+k_ccl_rowlink(const uint32_t* __restrict__ planes, int* __restrict__ parents, int* __restrict__ areas, int H, int W,
+              int wpr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * 8 + warp;
+    if (y >= H) return;
     const size_t plane_words = (size_t)H * wpr;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= plane_words) return;
-    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
     const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
     int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
     int* A = areas ? areas + (size_t)blockIdx.y * (plane_words * 32 + 1) : nullptr;
-    uint32_t m = plane_word<INVERT>(plane, y, j, H, W, wpr);
-    if (INVERT && idx == 0) P[0] = 0;
-    const int base = (int)idx * 32 + 1;
-    while (m) {
-        int lo;
-        const uint32_t run = lowest_run(m, lo);
-        P[base + lo] = base + lo;
-        if (A) A[base + lo] = 0;
-        m &= ~run;
+    if (BORDER && y == 0 && lane == 0) P[0] = 0;
+    const bool edge_row = BORDER && (y == 0 || y == H - 1);
+    const int last_word = (W - 1) >> 5, last_bit = (W - 1) & 31;
+    int carry_root = -1;                      // root of the run leaving the previous chunk through bit 31 (-1: none)
+    for (int j0 = 0; j0 < wpr; j0 += 32) {
+        const int j = j0 + lane;
+        const uint32_t w = j < wpr ? plane_word<INVERT>(plane, y, j, H, W, wpr) : 0u;
+        const int base = (y * wpr + j) * 32 + 1;
+        const bool full = w == 0xffffffffu;
+        const uint32_t w_prev = __shfl_up_sync(0xffffffffu, w, 1);
+        const bool prev_msb = lane == 0 ? carry_root >= 0 : (w_prev >> 31) != 0;
+        const bool link = (w & 1u) && prev_msb;
+        const uint32_t T = __ballot_sync(0xffffffffu, full && link);
+        const int ls = (w >> 31) ? run_start(w, 31) : 0;
+        // root of a run that starts inside this word and leaves it through bit 31 (valid when !(full && link))
+        int own_out = full ? ((BORDER && j == 0) ? 0 : base) : base + ls;
+        if (edge_row) own_out = 0;
+        const uint32_t z = ~T & ((1u << lane) - 1u);
+        const int h = z ? 31 - __clz(z) : 0;
+        const int src = __shfl_sync(0xffffffffu, own_out, h);
+        int root_first;                        // root of the run containing bit 0 (when set)
+        if (link) root_first = z ? src : carry_root;
+        else root_first = (BORDER && j == 0) ? 0 : base;
+        if (edge_row) root_first = 0;
+        // write the nodes of this word
+        uint32_t m = w;
+        while (m) {
+            int lo;
+            const uint32_t run = lowest_run(m, lo);
+            m &= ~run;
+            P[base + lo] = edge_row ? 0 : (lo == 0 ? root_first : base + lo);
+            if (A) A[base + lo] = 0;
+        }
+        const int out_root = (w >> 31) ? ((full || ls == 0) ? root_first : base + ls) : -1;
+        __syncwarp();
+        if (BORDER && !edge_row && j == last_word && ((w >> last_bit) & 1u)) {
+            // the run holding the image's last column is outside: root its head at 0
+            const int s0 = run_start(w, last_bit);
+            const int head = s0 == 0 ? root_first : base + s0;
+            if (head != 0) P[head] = 0;
+        }
+        carry_root = __shfl_sync(0xffffffffu, out_root, 31);
     }
 }
 
-// ---- unions: left neighbour word, row above (4- or 8-connected), image border (phase A) ----------
-template <bool INVERT, int CONN, bool BORDER>
+// ---- unions with the row above (4- or 8-connected); horizontal links already exist ----------------------
+template <bool INVERT, int CONN>
 __global__ void __launch_bounds__(256)
 k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ parents, int H, int W, int wpr) {
     const size_t plane_words = (size_t)H * wpr;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= plane_words) return;
     const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    if (y == 0) return;
     const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
     int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
     const uint32_t cur = plane_word<INVERT>(plane, y, j, H, W, wpr);
     if (!cur) return;
     const int base = (int)idx * 32 + 1;
-    const uint32_t left = plane_word<INVERT>(plane, y, j - 1, H, W, wpr);
-    if ((cur & 1u) && (left >> 31)) uf_union(P, base, base - 32 + run_start(left, 31));
     const uint32_t up = plane_word<INVERT>(plane, y - 1, j, H, W, wpr);
     const uint32_t upl = CONN == 8 ? plane_word<INVERT>(plane, y - 1, j - 1, H, W, wpr) : 0u;
     const uint32_t upr = CONN == 8 ? plane_word<INVERT>(plane, y - 1, j + 1, H, W, wpr) : 0u;
+    if (!(up | (upl >> 31) | (upr & 1u))) return;
     const int base_up = base - wpr * 32;
-    const int last_x = W - 1 - j * 32;                 // bit index of the image's last column in this word
     uint32_t m = cur;
     while (m) {
         int lo;
@@ -109,22 +145,24 @@ k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ parents, int 
         m &= ~run;
         const int id = base + lo;
         const int hi = 31 - __clz(run);
-        if (BORDER) {
-            if (y == 0 || y == H - 1 || (j == 0 && lo == 0) || hi == last_x) uf_union(P, id, 0);
+        const int pa = __ldcg(P + id);                       // quick test: same parent already (e.g. both outside)
+        uint32_t nm = run;
+        if (CONN == 8) nm |= (run << 1) | (run >> 1);
+        uint32_t n = up & nm;
+        while (n) {
+            const int p = __ffs(n) - 1;
+            const int s = run_start(up, p);
+            if (__ldcg(P + base_up + s) != pa) uf_union(P, id, base_up + s);
+            n &= ~run_mask_from(up, s);
         }
-        if (y > 0) {
-            uint32_t nm = run;
-            if (CONN == 8) nm |= (run << 1) | (run >> 1);
-            uint32_t n = up & nm;
-            while (n) {
-                const int p = __ffs(n) - 1;
-                const int s = run_start(up, p);
-                uf_union(P, id, base_up + s);
-                n &= ~run_mask_from(up, s);
+        if (CONN == 8) {
+            if (lo == 0 && (upl >> 31)) {
+                const int o = base_up - 32 + run_start(upl, 31);
+                if (__ldcg(P + o) != pa) uf_union(P, id, o);
             }
-            if (CONN == 8) {
-                if (lo == 0 && (upl >> 31)) uf_union(P, id, base_up - 32 + run_start(upl, 31));
-                if (hi == 31 && (upr & 1u)) uf_union(P, id, base_up + 32);
+            if (hi == 31 && (upr & 1u)) {
+                const int o = base_up + 32;
+                if (__ldcg(P + o) != pa) uf_union(P, id, o);
             }
         }
     }
