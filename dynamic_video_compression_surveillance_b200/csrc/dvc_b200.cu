@@ -170,9 +170,9 @@ static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, 
 }
 
 struct CclScratch {
-    int* parents_a = nullptr;   // [frames][plane_words*32+1]
-    int* parents_b = nullptr;
-    int* areas = nullptr;
+    // union-find storage per frame (k_ccl.cuh): dense slot-0 arrays [plane_words + 1] and overflow arrays
+    // [plane_words * 15], for the phase A parents, the phase B parents and the phase B areas
+    int *pa0 = nullptr, *paov = nullptr, *pb0 = nullptr, *pbov = nullptr, *ar0 = nullptr, *arov = nullptr;
     uint32_t* filled = nullptr;  // [frames] planes
     int frames = 0;
 };
@@ -186,32 +186,36 @@ static int launch_contour_filter(char* ERRBUF, const uint32_t* raw, uint32_t* ou
     for (int i0 = 0; i0 < n; i0 += sc.frames) {
         const int m = std::min(sc.frames, n - i0);
         dim3 grid(cdiv(pw, 256), m);
-        const uint32_t* r = raw + (size_t)i0 * pw;
         dim3 grow((H + 7) / 8, m);
-        k_ccl_rowlink<true, true><<<grow, 256, 0, st>>>(r, sc.parents_a, nullptr, H, W, wpr);
-        k_ccl_union<true, 4><<<grid, 256, 0, st>>>(r, sc.parents_a, H, W, wpr);
-        k_ccl_fill<<<grid, 256, 0, st>>>(r, sc.parents_a, sc.filled, H, W, wpr);
-        k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, H, W, wpr);
-        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, H, W, wpr);
-        k_ccl_area<<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, H, W, wpr);
-        k_ccl_select<<<grid, 256, 0, st>>>(sc.filled, sc.parents_b, sc.areas, out + (size_t)i0 * pw, H, W, wpr, thr);
+        const uint32_t* r = raw + (size_t)i0 * pw;
+        k_ccl_rowlink<true, true><<<grow, 256, 0, st>>>(r, sc.pa0, sc.paov, nullptr, nullptr, H, W, wpr);
+        k_ccl_union<true, 4><<<grid, 256, 0, st>>>(r, sc.pa0, sc.paov, H, W, wpr);
+        k_ccl_fill<<<grid, 256, 0, st>>>(r, sc.pa0, sc.paov, sc.filled, H, W, wpr);
+        k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, H, W, wpr);
+        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, H, W, wpr);
+        k_ccl_area<<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, H, W, wpr);
+        k_ccl_select<<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, out + (size_t)i0 * pw, H, W, wpr, thr);
         CHECK_LAUNCH();
     }
     return DVC_OK;
 }
 
+static size_t ccl_dense_ints(int H, int W) { return (size_t)H * words_per_row(W) + 1; }
+static size_t ccl_overflow_ints(int H, int W) { return (size_t)H * words_per_row(W) * 15; }
+
 static int ccl_scratch_alloc(char* ERRBUF, CclScratch& sc, int frames, int H, int W) {
     const size_t pw = (size_t)H * words_per_row(W);
-    const size_t nodes = pw * 32 + 1;
+    const size_t d = ccl_dense_ints(H, W) * sizeof(int) * frames, o = ccl_overflow_ints(H, W) * sizeof(int) * frames;
     sc.frames = frames;
-    CU(cudaMalloc(&sc.parents_a, nodes * sizeof(int) * frames));
-    CU(cudaMalloc(&sc.parents_b, nodes * sizeof(int) * frames));
-    CU(cudaMalloc(&sc.areas, nodes * sizeof(int) * frames));
+    CU(cudaMalloc(&sc.pa0, d)); CU(cudaMalloc(&sc.paov, o));
+    CU(cudaMalloc(&sc.pb0, d)); CU(cudaMalloc(&sc.pbov, o));
+    CU(cudaMalloc(&sc.ar0, d)); CU(cudaMalloc(&sc.arov, o));
     CU(cudaMalloc(&sc.filled, pw * 4 * frames));
     return DVC_OK;
 }
 static void ccl_scratch_free(CclScratch& sc) {
-    cudaFree(sc.parents_a); cudaFree(sc.parents_b); cudaFree(sc.areas); cudaFree(sc.filled);
+    cudaFree(sc.pa0); cudaFree(sc.paov); cudaFree(sc.pb0); cudaFree(sc.pbov); cudaFree(sc.ar0); cudaFree(sc.arov);
+    cudaFree(sc.filled);
     sc = CclScratch();
 }
 
@@ -893,17 +897,16 @@ extern "C" int dvc_contour_filter_u8(const uint8_t* src, uint8_t* dst, int32_t n
     if (!src || !dst) return set_err(nullptr, DVC_ERR_INVALID, "dvc_contour_filter_u8: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t pw = (size_t)H * words_per_row(W);
-    const size_t nodes = pw * 32 + 1;
     const int fr = std::min(n, 8);
-    ScopedAsyncBuf a(st), b(st), pa(st), pb(st), ar(st), fl(st);
+    const size_t d = ccl_dense_ints(H, W) * sizeof(int) * fr, o = ccl_overflow_ints(H, W) * sizeof(int) * fr;
+    ScopedAsyncBuf a(st), b(st), pa0(st), paov(st), pb0(st), pbov(st), ar0(st), arov(st), fl(st);
     CU(a.alloc(pw * 4 * n));
     CU(b.alloc(pw * 4 * n));
-    CU(pa.alloc(nodes * 4 * fr));
-    CU(pb.alloc(nodes * 4 * fr));
-    CU(ar.alloc(nodes * 4 * fr));
+    CU(pa0.alloc(d)); CU(paov.alloc(o)); CU(pb0.alloc(d)); CU(pbov.alloc(o)); CU(ar0.alloc(d)); CU(arov.alloc(o));
     CU(fl.alloc(pw * 4 * fr));
     CclScratch sc;
-    sc.parents_a = (int*)pa.p; sc.parents_b = (int*)pb.p; sc.areas = (int*)ar.p; sc.filled = (uint32_t*)fl.p; sc.frames = fr;
+    sc.pa0 = (int*)pa0.p; sc.paov = (int*)paov.p; sc.pb0 = (int*)pb0.p; sc.pbov = (int*)pbov.p;
+    sc.ar0 = (int*)ar0.p; sc.arov = (int*)arov.p; sc.filled = (uint32_t*)fl.p; sc.frames = fr;
     rc = pack_to_bits(src, (uint32_t*)a.p, n, H, W, st);
     if (rc) return rc;
     rc = launch_contour_filter(nullptr, (const uint32_t*)a.p, (uint32_t*)b.p, n, H, W, min_area, sc, st);

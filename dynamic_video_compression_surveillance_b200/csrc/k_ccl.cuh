@@ -8,31 +8,51 @@
 //            of 2x2 windows holding 4 / 3 of its pixels;  keep labels with 2*area > 2*min_area.
 //
 // Both phases are a union-find over *bit runs*: the graph nodes are the maximal runs of set bits inside
-// each 32-bit word of the bit-plane (node id = 1 + pixel index of the run's first bit; id 0 is the
-// "outside" node in phase A), so an empty 1080p mask is 65 k nodes instead of 2 M pixels and a thread
-// owns one word.  Unions are lock-free (atomicMin on the larger root), finds use path halving.
+// each 32-bit word of the bit-plane, so an empty 1080p mask is 65 k nodes instead of 2 M pixels and a thread
+// owns one word.  Node id = ((word index + 1) << 4) | slot, slot = ordinal of the run inside its word
+// (a word holds at most 16 runs); id 0 is the "outside" node of phase A.  Slot-0 parents live in a dense
+// array indexed by word (coalesced, L2 resident: 259 KB per 1080p frame); the rarely used slots 1..15 live in
+// an overflow array.  Horizontal runs are linked by a warp-per-row kernel without atomics; vertical links are
+// lock-free unions (atomicMin on the larger root) with path halving.
 #pragma once
 #include "common.cuh"
 
 namespace dvc {
 
-DEVI int uf_find(int* P, int x) {
+struct UF {
+    int* p0;     // [1 + plane_words]: p0[0] = outside, p0[1 + w] = slot 0 of word w
+    int* pov;    // [plane_words * 15]: slots 1..15
+};
+
+DEVI int node_id(int word, int slot) { return ((word + 1) << 4) | slot; }
+DEVI int* uf_addr(const UF& u, int id) {
+    const int s = id & 15, w = id >> 4;
+    return s == 0 ? u.p0 + w : u.pov + (size_t)(w - 1) * 15 + (s - 1);
+}
+DEVI UF uf_of_frame(int* p0, int* pov, size_t plane_words, int frame) {
+    UF u;
+    u.p0 = p0 + (size_t)frame * (plane_words + 1);
+    u.pov = pov + (size_t)frame * plane_words * 15;
+    return u;
+}
+
+DEVI int uf_find(const UF& u, int x) {
     while (true) {
-        const int p = __ldcg(P + x);       // L2 reads: other SMs link roots with atomics at L2
+        const int p = __ldcg(uf_addr(u, x));       // L2 reads: other SMs link roots with atomics at L2
         if (p == x) return x;
-        const int gp = __ldcg(P + p);
+        const int gp = __ldcg(uf_addr(u, p));
         if (gp == p) return p;
-        __stcg(P + x, gp);   // path halving; parents only ever move to smaller ancestors of the same set
+        __stcg(uf_addr(u, x), gp);                 // path halving; parents only move to smaller ancestors of the set
         x = gp;
     }
 }
-DEVI void uf_union(int* P, int a, int b) {
+DEVI void uf_union(const UF& u, int a, int b) {
     while (true) {
-        a = uf_find(P, a);
-        b = uf_find(P, b);
+        a = uf_find(u, a);
+        b = uf_find(u, b);
         if (a == b) return;
         if (a < b) { const int t = a; a = b; b = t; }
-        const int old = atomicMin(&P[a], b);
+        const int old = atomicMin(uf_addr(u, a), b);
         if (old == a) return;
         a = old;
     }
@@ -50,6 +70,9 @@ DEVI int run_start(uint32_t u, int p) {
     return z ? 32 - __clz(z) : 0;
 }
 DEVI uint32_t run_mask_from(uint32_t u, int start) { return u & ~(u + (1u << start)); }
+DEVI uint32_t run_starts(uint32_t u) { return u & ~(u << 1); }
+// ordinal of the run of u that contains bit p (bit p must be set)
+DEVI int run_slot(uint32_t u, int p) { return __popc(run_starts(u) & (0xffffffffu >> (31 - p))) - 1; }
 
 template <bool INVERT>
 DEVI uint32_t plane_word(const uint32_t* plane, int y, int j, int H, int W, int wpr) {
@@ -65,55 +88,60 @@ DEVI uint32_t plane_word(const uint32_t* plane, int y, int j, int H, int W, int 
 // touch the image border are rooted at node 0 ("outside") directly, so an empty mask needs no union at all.
 template <bool INVERT, bool BORDER>
 __global__ void __launch_bounds__(256)
-k_ccl_rowlink(const uint32_t* __restrict__ planes, int* __restrict__ parents, int* __restrict__ areas, int H, int W,
-              int wpr) {
+k_ccl_rowlink(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov,
+              int* __restrict__ a0, int* __restrict__ aov, int H, int W, int wpr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * 8 + warp;
     if (y >= H) return;
     const size_t plane_words = (size_t)H * wpr;
     const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
-    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
-    int* A = areas ? areas + (size_t)blockIdx.y * (plane_words * 32 + 1) : nullptr;
-    if (BORDER && y == 0 && lane == 0) P[0] = 0;
+    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
+    const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
+    if (BORDER && y == 0 && lane == 0) P.p0[0] = 0;
     const bool edge_row = BORDER && (y == 0 || y == H - 1);
     const int last_word = (W - 1) >> 5, last_bit = (W - 1) & 31;
     int carry_root = -1;                      // root of the run leaving the previous chunk through bit 31 (-1: none)
     for (int j0 = 0; j0 < wpr; j0 += 32) {
         const int j = j0 + lane;
         const uint32_t w = j < wpr ? plane_word<INVERT>(plane, y, j, H, W, wpr) : 0u;
-        const int base = (y * wpr + j) * 32 + 1;
+        const int word = y * wpr + j;
+        const int nruns = __popc(run_starts(w));
         const bool full = w == 0xffffffffu;
         const uint32_t w_prev = __shfl_up_sync(0xffffffffu, w, 1);
         const bool prev_msb = lane == 0 ? carry_root >= 0 : (w_prev >> 31) != 0;
         const bool link = (w & 1u) && prev_msb;
         const uint32_t T = __ballot_sync(0xffffffffu, full && link);
-        const int ls = (w >> 31) ? run_start(w, 31) : 0;
-        // root of a run that starts inside this word and leaves it through bit 31 (valid when !(full && link))
-        int own_out = full ? ((BORDER && j == 0) ? 0 : base) : base + ls;
+        // root of a run that starts inside this word and leaves it through bit 31 (used when !(full && link))
+        int own_out = full ? ((BORDER && j == 0) ? 0 : node_id(word, 0)) : node_id(word, nruns - 1);
         if (edge_row) own_out = 0;
         const uint32_t z = ~T & ((1u << lane) - 1u);
         const int h = z ? 31 - __clz(z) : 0;
         const int src = __shfl_sync(0xffffffffu, own_out, h);
         int root_first;                        // root of the run containing bit 0 (when set)
         if (link) root_first = z ? src : carry_root;
-        else root_first = (BORDER && j == 0) ? 0 : base;
+        else root_first = (BORDER && j == 0) ? 0 : node_id(word, 0);
         if (edge_row) root_first = 0;
         // write the nodes of this word
         uint32_t m = w;
+        int slot = 0;
         while (m) {
             int lo;
             const uint32_t run = lowest_run(m, lo);
             m &= ~run;
-            P[base + lo] = edge_row ? 0 : (lo == 0 ? root_first : base + lo);
-            if (A) A[base + lo] = 0;
+            const int id = node_id(word, slot);
+            *uf_addr(P, id) = edge_row ? 0 : (lo == 0 ? root_first : id);
+            if (a0) *uf_addr(A, id) = 0;
+            ++slot;
         }
-        const int out_root = (w >> 31) ? ((full || ls == 0) ? root_first : base + ls) : -1;
+        const bool last_is_first = nruns == 1 && (w & 1u);     // the run through bit 31 is also the run through bit 0
+        int out_root = -1;
+        if (w >> 31) out_root = edge_row ? 0 : (last_is_first ? root_first : node_id(word, nruns - 1));
         __syncwarp();
         if (BORDER && !edge_row && j == last_word && ((w >> last_bit) & 1u)) {
             // the run holding the image's last column is outside: root its head at 0
-            const int s0 = run_start(w, last_bit);
-            const int head = s0 == 0 ? root_first : base + s0;
-            if (head != 0) P[head] = 0;
+            const int s = run_slot(w, last_bit);
+            const int head = (s == 0 && (w & 1u)) ? root_first : node_id(word, s);
+            if (head != 0) *uf_addr(P, head) = 0;
         }
         carry_root = __shfl_sync(0xffffffffu, out_root, 31);
     }
@@ -122,47 +150,47 @@ k_ccl_rowlink(const uint32_t* __restrict__ planes, int* __restrict__ parents, in
 // ---- unions with the row above (4- or 8-connected); horizontal links already exist ----------------------
 template <bool INVERT, int CONN>
 __global__ void __launch_bounds__(256)
-k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ parents, int H, int W, int wpr) {
+k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov, int H, int W, int wpr) {
     const size_t plane_words = (size_t)H * wpr;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= plane_words) return;
     const int y = (int)(idx / wpr), j = (int)(idx % wpr);
     if (y == 0) return;
     const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
-    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     const uint32_t cur = plane_word<INVERT>(plane, y, j, H, W, wpr);
     if (!cur) return;
-    const int base = (int)idx * 32 + 1;
     const uint32_t up = plane_word<INVERT>(plane, y - 1, j, H, W, wpr);
     const uint32_t upl = CONN == 8 ? plane_word<INVERT>(plane, y - 1, j - 1, H, W, wpr) : 0u;
     const uint32_t upr = CONN == 8 ? plane_word<INVERT>(plane, y - 1, j + 1, H, W, wpr) : 0u;
     if (!(up | (upl >> 31) | (upr & 1u))) return;
-    const int base_up = base - wpr * 32;
+    const int word = (int)idx, word_up = word - wpr;
     uint32_t m = cur;
+    int slot = 0;
     while (m) {
         int lo;
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
-        const int id = base + lo;
+        const int id = node_id(word, slot++);
         const int hi = 31 - __clz(run);
-        const int pa = __ldcg(P + id);                       // quick test: same parent already (e.g. both outside)
+        const int pa = __ldcg(uf_addr(P, id));               // quick test: same parent already (e.g. both outside)
         uint32_t nm = run;
         if (CONN == 8) nm |= (run << 1) | (run >> 1);
         uint32_t n = up & nm;
         while (n) {
             const int p = __ffs(n) - 1;
-            const int s = run_start(up, p);
-            if (__ldcg(P + base_up + s) != pa) uf_union(P, id, base_up + s);
-            n &= ~run_mask_from(up, s);
+            const int o = node_id(word_up, run_slot(up, p));
+            if (__ldcg(uf_addr(P, o)) != pa) uf_union(P, id, o);
+            n &= ~run_mask_from(up, run_start(up, p));
         }
         if (CONN == 8) {
             if (lo == 0 && (upl >> 31)) {
-                const int o = base_up - 32 + run_start(upl, 31);
-                if (__ldcg(P + o) != pa) uf_union(P, id, o);
+                const int o = node_id(word_up - 1, __popc(run_starts(upl)) - 1);
+                if (__ldcg(uf_addr(P, o)) != pa) uf_union(P, id, o);
             }
             if (hi == 31 && (upr & 1u)) {
-                const int o = base_up + 32;
-                if (__ldcg(P + o) != pa) uf_union(P, id, o);
+                const int o = node_id(word_up + 1, 0);
+                if (__ldcg(uf_addr(P, o)) != pa) uf_union(P, id, o);
             }
         }
     }
@@ -170,36 +198,36 @@ k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ parents, int 
 
 // ---- phase A result: F = complement of the background reachable from outside ---------------------
 __global__ void __launch_bounds__(256)
-k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ parents, uint32_t* __restrict__ filled, int H,
-           int W, int wpr) {
+k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov,
+           uint32_t* __restrict__ filled, int H, int W, int wpr) {
     const size_t plane_words = (size_t)H * wpr;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= plane_words) return;
     const int y = (int)(idx / wpr), j = (int)(idx % wpr);
-    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     uint32_t m = plane_word<true>(planes + (size_t)blockIdx.y * plane_words, y, j, H, W, wpr);
-    const int base = (int)idx * 32 + 1;
     uint32_t outside = 0;
+    int slot = 0;
     while (m) {
         int lo;
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
-        if (uf_find(P, base + lo) == 0) outside |= run;
+        if (uf_find(P, node_id((int)idx, slot++)) == 0) outside |= run;
     }
     filled[(size_t)blockIdx.y * plane_words + idx] = ~outside & valid_mask(j, W);
 }
 
 // ---- phase B: 2*area = 2*Q4 + Q3 per label --------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ parents, int* __restrict__ areas, int H, int W,
-           int wpr) {
+k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __restrict__ pov, int* __restrict__ a0,
+           int* __restrict__ aov, int H, int W, int wpr) {
     const size_t plane_words = (size_t)H * wpr;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= plane_words) return;
     const int y = (int)(idx / wpr), j = (int)(idx % wpr);
     const uint32_t* F = filled + (size_t)blockIdx.y * plane_words;
-    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
-    int* A = areas + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
+    const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
     const uint32_t a = plane_word<false>(F, y, j, H, W, wpr), b = plane_word<false>(F, y + 1, j, H, W, wpr);
     if (!(a | b)) return;
     const uint32_t an = plane_word<false>(F, y, j + 1, H, W, wpr), bn = plane_word<false>(F, y + 1, j + 1, H, W, wpr);
@@ -207,42 +235,45 @@ k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ parents, int* 
     const uint32_t q4 = a & a1 & b & b1;
     const uint32_t q3a = a & ((a1 & b & ~b1) | (a1 & ~b & b1) | (~a1 & b & b1));   // top-left pixel in F
     const uint32_t q3b = ~a & a1 & b & b1;                                         // top-left pixel not in F
-    const int base = (int)idx * 32 + 1;
+    if (!(q4 | q3a | q3b)) return;
     uint32_t m = a;
+    int slot = 0;
     while (m) {
         int lo;
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
         const int c = 2 * __popc(q4 & run) + __popc(q3a & run);
-        if (c) atomicAdd(&A[uf_find(P, base + lo)], c);
+        if (c) atomicAdd(uf_addr(A, uf_find(P, node_id((int)idx, slot))), c);
+        ++slot;
     }
     m = q3b ? b : 0u;
-    const int base_dn = base + wpr * 32;
+    slot = 0;
     while (m) {
         int lo;
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
         const int c = __popc(q3b & run);
-        if (c) atomicAdd(&A[uf_find(P, base_dn + lo)], c);
+        if (c) atomicAdd(uf_addr(A, uf_find(P, node_id((int)idx + wpr, slot))), c);
+        ++slot;
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_ccl_select(const uint32_t* __restrict__ filled, int* __restrict__ parents, const int* __restrict__ areas,
-             uint32_t* __restrict__ out, int H, int W, int wpr, int twice_min_area_floor) {
+k_ccl_select(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __restrict__ pov, int* __restrict__ a0,
+             int* __restrict__ aov, uint32_t* __restrict__ out, int H, int W, int wpr, int twice_min_area_floor) {
     const size_t plane_words = (size_t)H * wpr;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= plane_words) return;
-    int* P = parents + (size_t)blockIdx.y * (plane_words * 32 + 1);
-    const int* A = areas + (size_t)blockIdx.y * (plane_words * 32 + 1);
+    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
+    const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
     uint32_t m = filled[(size_t)blockIdx.y * plane_words + idx];
-    const int base = (int)idx * 32 + 1;
     uint32_t keep = 0;
+    int slot = 0;
     while (m) {
         int lo;
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
-        if (A[uf_find(P, base + lo)] > twice_min_area_floor) keep |= run;
+        if (__ldcg(uf_addr(A, uf_find(P, node_id((int)idx, slot++)))) > twice_min_area_floor) keep |= run;
     }
     out[(size_t)blockIdx.y * plane_words + idx] = keep;
 }
