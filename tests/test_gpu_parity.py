@@ -407,3 +407,102 @@ def test_full_size_properties_1080p(P):
         assert np.array_equal(mk[t], ref["mask"][t])
         _check_degraded(cp[t], ref["compressed"][t], frames[t + 1], ref["mask"][t], 4, 100, exact)
     pipe.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations as parity cases
+# ---------------------------------------------------------------------------------------------------
+def test_config3_4k_large_morphology(P):
+    """configs[2]: 4K stream, 15x15 morphology (close + open + dilate all 15x15 rect), K=5 window."""
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n = 2160, 3840, 7
+    frames = make_clip("4k", n, seed=2).frames()
+    cfg = dict(window_size=5, alpha_fraction=0.2, morph_kernel=15, morph_shape="rect", kernel_size=15)
+    ref = loops.window_loop(list(frames), degrade=False, **cfg)
+    pipe = P.FramePipeline(w, h, "window", max_batch=8, **cfg)
+    pipe.begin_stream(so.bgr2gray(frames[0]))
+    d = dev(frames[1:])
+    ov = torch.empty_like(d); cp = torch.empty_like(d)
+    mk = torch.empty(d.shape[:3], dtype=torch.uint8, device="cuda")
+    pipe.process_device(d, ov, cp, mk)
+    torch.cuda.synchronize()
+    mk, ov, cp = host(mk), host(ov), host(cp)
+    for t in range(n - 1):
+        assert np.array_equal(mk[t], ref["mask"][t]), t
+        assert np.array_equal(ov[t], ref["overlay"][t]), t
+    exact = so.cv2_dct4_matches_closed_form()
+    t = n - 2
+    _check_degraded(cp[t], so.degrade_fd(frames[t + 1], ref["mask"][t], 4, 100), frames[t + 1], ref["mask"][t], 4, 100, exact)
+    pipe.close()
+
+
+def test_config4_concurrent_streams_are_independent(P):
+    """configs[3]: many camera streams on one GPU, batches interleaved: every stream must equal its solo run."""
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n, S = 96, 160, 25, 6
+    clips = [make_clip((h, w), n, seed=s).frames() for s in range(S)]
+    cfg = dict(window_size=5, alpha_fraction=0.2, morph_kernel=2, kernel_size=7)
+    solo = []
+    for s in range(S):
+        ref = loops.window_loop(list(clips[s]), **cfg)
+        solo.append((np.stack(ref["mask"]), np.stack(ref["compressed"])))
+    pipes = [P.FramePipeline(w, h, "window", max_batch=8, **cfg) for _ in range(S)]
+    outs = []
+    for s in range(S):
+        pipes[s].begin_stream(so.bgr2gray(clips[s][0]))
+        d = dev(clips[s][1:])
+        outs.append((d, torch.empty_like(d), torch.empty(d.shape[:3], dtype=torch.uint8, device="cuda")))
+    streams = [torch.cuda.Stream() for _ in range(S)]
+    for i in range(0, n - 1, 8):                       # interleave the streams batch by batch
+        for s in range(S):
+            d, cp, mk = outs[s]
+            with torch.cuda.stream(streams[s]):
+                pipes[s].process_device(d[i:i + 8], None, cp[i:i + 8], mk[i:i + 8])
+    torch.cuda.synchronize()
+    exact = so.cv2_dct4_matches_closed_form()
+    for s in range(S):
+        assert np.array_equal(host(outs[s][2]), solo[s][0]), s
+        if exact:
+            assert np.array_equal(host(outs[s][1]), solo[s][1]), s
+        pipes[s].close()
+
+
+def test_config5_farneback_masks_to_mco_degrade_1080p(P):
+    """configs[4]: masks from the reference's Farneback + window vote + rectangles arithmetic
+    (motion_compression_opt.py:72-97, on the CPU) fed to the shared degrade kernel in MCO flavour at 1080p."""
+    from collections import deque
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n = 1080, 1920, 4
+    clip = make_clip("1080p", n, seed=1)
+    yy, xx = np.mgrid[0:h, 0:w]
+    clip.background = np.stack([(xx * 255 // w), (yy * 255 // h), ((xx + yy) * 255 // (w + h))], -1).astype(np.uint8)
+    frames = clip.frames()
+    prev = cv2.cvtColor(frames[0], cv2.COLOR_BGR2GRAY)
+    q = deque(maxlen=30)
+    kernel = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2, 2))
+    masks = []
+    for f in frames[1:]:
+        gray = cv2.cvtColor(f, cv2.COLOR_BGR2GRAY)
+        flow = cv2.calcOpticalFlowFarneback(prev, gray, None, 0.3, 2, 9, 2, 5, 1.1, 0)
+        mag, _ = cv2.cartToPolar(flow[..., 0], flow[..., 1])
+        q.append((mag > 0.5).astype(np.uint8) * 255)
+        sm = (np.sum(np.array(q), axis=0) >= 0.2 * len(q) * 255).astype(np.uint8) * 255
+        sm = cv2.morphologyEx(cv2.morphologyEx(sm, cv2.MORPH_CLOSE, kernel), cv2.MORPH_OPEN, kernel)
+        rect = np.zeros((h, w), np.uint8)
+        for c in cv2.findContours(sm, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]:
+            x, y, ww, hh = cv2.boundingRect(c)
+            cv2.rectangle(rect, (x, y), (x + ww, y + hh), 255, -1)
+        masks.append(rect)
+        prev = gray
+    masks = np.stack(masks)
+    comp, _ = P.degrade_blend(dev(frames[1:]), dev(masks), 8, 100, "mco", False)
+    comp = host(comp)
+    for i in (0, n - 2):
+        ref = so.degrade_mco(frames[i + 1], masks[i])
+        static = so.block_all_zero(masks[i], 8, full_blocks_only=True)
+        st_px = np.repeat(np.repeat(static, 8, 0), 8, 1)
+        assert np.array_equal(comp[i][~st_px], ref[~st_px])
+        d = np.abs(comp[i].astype(int) - ref.astype(int))[st_px]
+        assert np.mean(d <= 2) > 0.97 and d.max() <= 110       # a flipped tie moves a block by one quantiser step
+        psnr = 10 * np.log10(255.0 ** 2 / max(1e-9, np.mean((comp[i].astype(float) - ref.astype(float)) ** 2)))
+        assert psnr > 40, psnr
