@@ -54,6 +54,8 @@ SYMBOLS = {
     "dvc_get_counters": (C.c_int, [_P, C.POINTER(DvcCounters)]),
     "dvc_reset_counters": (C.c_int, [_P]),
     "dvc_process_batch": (C.c_int, [_P, _P, _I, _P, _P, _P, _P]),
+    "dvc_set_overlap": (C.c_int, [_P, _I]),
+    "dvc_flush": (C.c_int, [_P, _P]),
     "dvc_process_host": (C.c_int, [_P, _P, _L, _P, _P, _P]),
     "dvc_profile_enable": (C.c_int, [_P, _I]),
     "dvc_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _I]),

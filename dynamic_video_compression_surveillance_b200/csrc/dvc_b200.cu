@@ -299,15 +299,21 @@ struct dvc_handle {
     int ring_cap;
     MinCounts min_counts;
     // scratch (max_batch planes each)
-    uint32_t *bits_a, *bits_b, *bits_c;
+    uint32_t* bits[2][3];         // two sets (software pipelining across batches) of three bit-plane arrays
     uint8_t* blurred;             // FD: [max_batch] gray planes
     CclScratch ccl;
     MorphChain chain;
     Counters* counters_dev;
     dvc_counters counters_host;   // frames / pixels / blocks are counted on the host
+    // two-stream software pipeline: mask kernels of batch c+1 overlap the degrade kernel of batch c
+    bool overlap;                 // dvc_set_overlap: applies to dvc_process_batch (dvc_process_host always pipelines)
+    int pp;                       // scratch set / event parity of the next batch
+    cudaStream_t s_mask, s_k4;
+    cudaEvent_t ev_in, ev_mask[2], ev_k4[2];
+    bool ev_used[2];
     // host pipeline
-    cudaStream_t s_h2d, s_comp, s_d2h;
-    cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
+    cudaStream_t s_h2d, s_d2h;
+    cudaEvent_t ev_h2d[2], ev_d2h[2];
     uint8_t *st_in[2], *st_ov[2], *st_cp[2], *st_mask[2];
     bool staging;
     // profiling: CUDA events around each kernel group, on the launching stream
@@ -327,11 +333,9 @@ static int alloc_staging(dvc_handle* h) {
         CU(cudaMalloc(&h->st_cp[b], fb));
         CU(cudaMalloc(&h->st_mask[b], h->plane_bytes * h->cfg.max_batch));
         CU(cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
     }
     CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
     h->staging = true;
     return DVC_OK;
@@ -374,12 +378,18 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     h->gray_dp4a = gd && atoi(gd) != 0;
     CU(cudaSetDevice(cfg->device));
     for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&h->prev_gray[i], h->plane_bytes)); CU(cudaMemset(h->prev_gray[i], 0, h->plane_bytes)); }
-    CU(cudaMalloc(&h->bits_a, h->plane_words * 4 * T));
-    CU(cudaMalloc(&h->bits_b, h->plane_words * 4 * T));
-    CU(cudaMalloc(&h->bits_c, h->plane_words * 4 * T));
-    CU(cudaMemset(h->bits_a, 0, h->plane_words * 4 * T));
-    CU(cudaMemset(h->bits_b, 0, h->plane_words * 4 * T));
-    CU(cudaMemset(h->bits_c, 0, h->plane_words * 4 * T));
+    for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < 3; ++k) {
+            CU(cudaMalloc(&h->bits[s][k], h->plane_words * 4 * T));
+            CU(cudaMemset(h->bits[s][k], 0, h->plane_words * 4 * T));
+        }
+    CU(cudaStreamCreateWithFlags(&h->s_mask, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_k4, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    for (int s = 0; s < 2; ++s) {
+        CU(cudaEventCreateWithFlags(&h->ev_mask[s], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_k4[s], cudaEventDisableTiming));
+    }
     CU(cudaMalloc(&h->counters_dev, sizeof(Counters)));
     CU(cudaMemset(h->counters_dev, 0, sizeof(Counters)));
     h->chain.n = 0; h->chain.halo_top = h->chain.halo_bot = 0;
@@ -414,14 +424,19 @@ extern "C" int dvc_destroy(dvc_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(h->prev_gray[0]); cudaFree(h->prev_gray[1]); cudaFree(h->acc); cudaFree(h->ring);
-    cudaFree(h->bits_a); cudaFree(h->bits_b); cudaFree(h->bits_c); cudaFree(h->blurred); cudaFree(h->counters_dev);
+    for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(h->bits[s][k]);
+    cudaFree(h->blurred); cudaFree(h->counters_dev);
+    if (h->s_mask) cudaStreamDestroy(h->s_mask);
+    if (h->s_k4) cudaStreamDestroy(h->s_k4);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    for (int s = 0; s < 2; ++s) { if (h->ev_mask[s]) cudaEventDestroy(h->ev_mask[s]); if (h->ev_k4[s]) cudaEventDestroy(h->ev_k4[s]); }
     ccl_scratch_free(h->ccl);
     if (h->staging) {
         for (int b = 0; b < 2; ++b) {
             cudaFree(h->st_in[b]); cudaFree(h->st_ov[b]); cudaFree(h->st_cp[b]); cudaFree(h->st_mask[b]);
-            cudaEventDestroy(h->ev_h2d[b]); cudaEventDestroy(h->ev_comp[b]); cudaEventDestroy(h->ev_d2h[b]);
+            cudaEventDestroy(h->ev_h2d[b]); cudaEventDestroy(h->ev_d2h[b]);
         }
-        cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_comp); cudaStreamDestroy(h->s_d2h);
+        cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h);
     }
     if (h->prof_recs) { for (ProfRec& r : *h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } delete h->prof_recs; }
     delete h;
@@ -595,9 +610,14 @@ extern "C" int64_t dvc_launch_count(const dvc_handle* h) { return h ? h->launche
 // ------------------------------------------------------------------------------------------------
 // the loop body for one device-resident batch
 // ------------------------------------------------------------------------------------------------
+// Mask kernels run on `st`, the degrade kernel on `st_k4` (the same stream, or a second one so that it overlaps
+// the mask kernels of the next batch); `set` selects the scratch bit-planes.
 static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8_t* overlay, uint8_t* compressed,
-                              uint8_t* mask_out, cudaStream_t st) {
+                              uint8_t* mask_out, cudaStream_t st, cudaStream_t st_k4, int set) {
     char* ERRBUF = h->err;
+    uint32_t* const bits_a = h->bits[set][0];
+    uint32_t* const bits_b = h->bits[set][1];
+    uint32_t* const bits_c = h->bits[set][2];
     const int H = h->H, W = h->W, wpr = h->wpr;
     const uint32_t thr = (uint32_t)std::max(0.0f, std::floor(h->cfg.motion_threshold));
     const uint32_t* over127 = nullptr;
@@ -620,15 +640,15 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         h->cur ^= 1;
         dim3 g2(cdiv(h->plane_words, 256), nseg);
         { ProfScope ps(h, DVC_PROF_VOTE, 1, st);
-        k_window_vote<<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, (int)(h->n_masks % h->ring_cap), T, h->cfg.window_size, h->min_counts, h->bits_a, h->seg_len);
+        k_window_vote<<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, (int)(h->n_masks % h->ring_cap), T, h->cfg.window_size, h->min_counts, bits_a, h->seg_len);
         }
         CHECK_LAUNCH();
-        const uint32_t* fin = h->bits_a;
+        const uint32_t* fin = bits_a;
         if (h->chain.n) {
             ProfScope ps(h, DVC_PROF_MORPH, 1, st);
-            int rc = launch_morph_chain(h->err, h->bits_a, h->bits_b, T, H, W, h->chain, st);
+            int rc = launch_morph_chain(h->err, bits_a, bits_b, T, H, W, h->chain, st);
             if (rc) return rc;
-            fin = h->bits_b;
+            fin = bits_b;
         }
         over127 = nonzero = fin;
         if (mask_out) {
@@ -646,35 +666,43 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         CHECK_LAUNCH();
         dim3 gd(g16, T);
         { ProfScope ps(h, DVC_PROF_DIFF, 1, st);
-        if (h->aligned) k_diff_thresh_planes<true><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, h->bits_a, wpr, thr);
-        else k_diff_thresh_planes<false><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, h->bits_a, wpr, thr);
+        if (h->aligned) k_diff_thresh_planes<true><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, bits_a, wpr, thr);
+        else k_diff_thresh_planes<false><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, bits_a, wpr, thr);
         }
         CHECK_LAUNCH();
         CU(cudaMemcpyAsync(h->prev_gray[h->cur ^ 1], h->blurred + (size_t)(T - 1) * h->plane_bytes, h->plane_bytes, cudaMemcpyDeviceToDevice, st));
         h->cur ^= 1;
         int rc;
         { ProfScope ps(h, DVC_PROF_CCL, 7 * ((T + h->ccl.frames - 1) / h->ccl.frames), st);
-        rc = launch_contour_filter(h->err, h->bits_a, h->bits_b, T, H, W, h->cfg.min_area, h->ccl, st);
+        rc = launch_contour_filter(h->err, bits_a, bits_b, T, H, W, h->cfg.min_area, h->ccl, st);
         }
         if (rc) return rc;
         { ProfScope ps(h, DVC_PROF_MORPH, 1, st);
-        rc = launch_morph_chain(h->err, h->bits_b, h->bits_a, T, H, W, h->chain, st);      // dilate -> bits_a
+        rc = launch_morph_chain(h->err, bits_b, bits_a, T, H, W, h->chain, st);      // dilate -> bits_a
         }
         if (rc) return rc;
         const float alpha = (float)h->cfg.release_factor, beta = (float)(1.0 - h->cfg.release_factor);
         { ProfScope ps(h, DVC_PROF_EMA, 1, st);
-        if (h->aligned) k_ema<true><<<g16, 256, 0, st>>>(h->acc, h->bits_a, h->bits_b, h->bits_c, mask_out, T, H, W, wpr, alpha, beta);
-        else k_ema<false><<<g16, 256, 0, st>>>(h->acc, h->bits_a, h->bits_b, h->bits_c, mask_out, T, H, W, wpr, alpha, beta);
+        if (h->aligned) k_ema<true><<<g16, 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
+        else k_ema<false><<<g16, 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
         }
         CHECK_LAUNCH();
-        over127 = h->bits_b;
-        nonzero = h->bits_c;
+        over127 = bits_b;
+        nonzero = bits_c;
+    }
+    if (st_k4 != st) {
+        CU(cudaEventRecord(h->ev_mask[set], st));
+        CU(cudaStreamWaitEvent(st_k4, h->ev_mask[set], 0));
     }
     if (overlay || compressed) {
-        ProfScope ps(h, DVC_PROF_DEGRADE, 1, st);
+        ProfScope ps(h, DVC_PROF_DEGRADE, 1, st_k4);
         int rc = launch_degrade(h->err, frames, over127, nonzero, compressed, overlay, T, H, W, h->cfg.block_size,
-                                h->cfg.quantization_level, DVC_DEGRADE_FD, h->counters_dev, st);
+                                h->cfg.quantization_level, DVC_DEGRADE_FD, h->counters_dev, st_k4);
         if (rc) return rc;
+    }
+    if (st_k4 != st) {
+        CU(cudaEventRecord(h->ev_k4[set], st_k4));
+        h->ev_used[set] = true;
     }
     h->n_masks += T;
     h->counters_host.frames += T;
@@ -691,7 +719,36 @@ extern "C" int dvc_process_batch(dvc_handle* h, const uint8_t* frames_dev, int32
     if (n_frames == 0) return DVC_OK;
     if (!frames_dev) return set_err(h->err, DVC_ERR_INVALID, "dvc_process_batch: null frames");
     CU(cudaSetDevice(h->cfg.device));
-    return process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->overlap) return process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, st, st, 0);
+    // pipelined: the batch is ordered after the work already in `stream`, but `stream` is only re-joined by dvc_flush
+    const int set = h->pp;
+    h->pp ^= 1;
+    CU(cudaEventRecord(h->ev_in, st));
+    CU(cudaStreamWaitEvent(h->s_mask, h->ev_in, 0));
+    if (h->ev_used[set]) CU(cudaStreamWaitEvent(h->s_mask, h->ev_k4[set], 0));      // scratch set free again
+    return process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, h->s_mask, h->s_k4, set);
+}
+
+extern "C" int dvc_set_overlap(dvc_handle* h, int32_t on) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h) return set_err(nullptr, DVC_ERR_INVALID, "dvc_set_overlap: null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    h->overlap = on != 0;
+    return DVC_OK;
+}
+
+extern "C" int dvc_flush(dvc_handle* h, void* stream) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h) return set_err(nullptr, DVC_ERR_INVALID, "dvc_flush: null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    for (int s = 0; s < 2; ++s)
+        if (h->ev_used[s]) {
+            CU(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_mask[s], 0));
+            CU(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_k4[s], 0));
+        }
+    return DVC_OK;
 }
 
 extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64_t n_frames, uint8_t* overlay_host,
@@ -706,29 +763,35 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
     if (rc) return rc;
     const int Tc = h->cfg.max_batch;
     const int64_t nchunks = (n_frames + Tc - 1) / Tc;
+    CU(cudaDeviceSynchronize());          // join whatever dvc_process_batch left in flight
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int b = (int)(c & 1);
+        const int b = (int)(c & 1);       // staging buffers, scratch set and events all alternate with the chunk
         const int64_t f0 = c * Tc;
         const int T = (int)std::min<int64_t>(Tc, n_frames - f0);
-        // the input buffer is free once the compute that read it (chunk c-2) is done
-        if (c >= 2) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));
+        // the input buffer is free once the degrade kernel that read it (chunk c-2) is done
+        if (c >= 2) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_k4[b], 0));
         CU(cudaMemcpyAsync(h->st_in[b], frames_host + (size_t)f0 * h->frame_bytes, (size_t)T * h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
         CU(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
-        CU(cudaStreamWaitEvent(h->s_comp, h->ev_h2d[b], 0));
-        // the output buffers are free once their download (chunk c-2) is done
-        if (c >= 2) CU(cudaStreamWaitEvent(h->s_comp, h->ev_d2h[b], 0));
+        CU(cudaStreamWaitEvent(h->s_mask, h->ev_h2d[b], 0));
+        if (c >= 2) {
+            CU(cudaStreamWaitEvent(h->s_mask, h->ev_k4[b], 0));      // scratch set b free
+            CU(cudaStreamWaitEvent(h->s_mask, h->ev_d2h[b], 0));     // output staging of chunk c-2 downloaded
+            CU(cudaStreamWaitEvent(h->s_k4, h->ev_d2h[b], 0));
+        }
         rc = process_batch_impl(h, h->st_in[b], T, overlay_host ? h->st_ov[b] : nullptr, compressed_host ? h->st_cp[b] : nullptr,
-                                mask_host ? h->st_mask[b] : nullptr, h->s_comp);
+                                mask_host ? h->st_mask[b] : nullptr, h->s_mask, h->s_k4, b);
         if (rc) { cudaDeviceSynchronize(); return rc; }
-        CU(cudaEventRecord(h->ev_comp[b], h->s_comp));
-        CU(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
+        CU(cudaStreamWaitEvent(h->s_d2h, h->ev_k4[b], 0));
         if (overlay_host) CU(cudaMemcpyAsync(overlay_host + (size_t)f0 * h->frame_bytes, h->st_ov[b], (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
         if (compressed_host) CU(cudaMemcpyAsync(compressed_host + (size_t)f0 * h->frame_bytes, h->st_cp[b], (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
         if (mask_host) CU(cudaMemcpyAsync(mask_host + (size_t)f0 * h->plane_bytes, h->st_mask[b], (size_t)T * h->plane_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
         CU(cudaEventRecord(h->ev_d2h[b], h->s_d2h));
     }
     CU(cudaStreamSynchronize(h->s_d2h));
-    CU(cudaStreamSynchronize(h->s_comp));
+    CU(cudaStreamSynchronize(h->s_k4));
+    CU(cudaStreamSynchronize(h->s_mask));
+    h->ev_used[0] = h->ev_used[1] = false;
+    h->pp = 0;
     return DVC_OK;
 }
 

@@ -151,6 +151,15 @@ class FramePipeline:
         self._check(self._lib.dvc_process_batch(self._h, frames.data_ptr(), T, ptr(overlay), ptr(compressed), ptr(mask),
                                                 _stream_ptr(stream)))
 
+    def set_overlap(self, on: bool):
+        """Pipeline consecutive process_device batches on two internal streams (mask kernels of batch c+1 overlap
+        the degrade kernel of batch c).  Buffers must stay untouched until ``flush``."""
+        self._check(self._lib.dvc_set_overlap(self._h, int(bool(on))))
+
+    def flush(self, stream=None):
+        """Make the current (or given) torch stream wait for every batch issued so far."""
+        self._check(self._lib.dvc_flush(self._h, _stream_ptr(stream)))
+
     def process_host(self, frames, overlay=None, compressed=None, mask=None):
         """frames [N,H,W,3] uint8 HOST array (numpy or CPU torch tensor, pinned for full speed); outputs are host
         arrays of matching shape or None.  Upload, loop and download are pipelined in chunks of max_batch inside

@@ -116,6 +116,12 @@ int dvc_reset_counters(dvc_handle* h);
  * n_frames <= cfg.max_batch. */
 int dvc_process_batch(dvc_handle* h, const uint8_t* frames_dev, int32_t n_frames, uint8_t* overlay_dev,
                       uint8_t* compressed_dev, uint8_t* mask_dev, void* stream);
+/* Software pipelining across batches (off by default).  When on, dvc_process_batch runs the mask kernels and the
+ * degrade kernel on two internal streams so that the mask kernels of batch c+1 overlap the degrade kernel of
+ * batch c.  Each batch is still ordered after the work already queued in `stream`, but `stream` is re-joined
+ * only by dvc_flush(): input and output buffers must stay untouched until then. */
+int dvc_set_overlap(dvc_handle* h, int32_t on);
+int dvc_flush(dvc_handle* h, void* stream);     /* make `stream` wait for every batch issued so far */
 /* Same loop with HOST buffers (pinned for full speed): frames are uploaded, processed and the results
  * downloaded in chunks of cfg.max_batch, double-buffered on the handle's own copy/compute streams.
  * Returns after everything has landed in the host buffers.  Any n_frames >= 0. */

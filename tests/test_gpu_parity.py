@@ -351,6 +351,34 @@ def test_window_front_end_dp4a_variant(P, monkeypatch):
         pipe.close()
 
 
+def test_two_stream_overlap_matches_strict_order(P):
+    """dvc_set_overlap: mask kernels of batch c+1 overlap the degrade kernel of batch c; results must not change."""
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n = 120, 176, 70
+    frames = make_clip((h, w), n, seed=9).frames()
+    for mode, kw, seed in (("window", dict(window_size=5, alpha_fraction=0.2, morph_kernel=2, kernel_size=7), so.bgr2gray(frames[0])),
+                           ("fd", {}, loops.first_frame_gray_fd(frames[0]))):
+        res = []
+        for overlap in (False, True):
+            pipe = P.FramePipeline(w, h, mode, max_batch=4, **kw)
+            pipe.begin_stream(seed)
+            pipe.set_overlap(overlap)
+            d = dev(frames[1:])
+            ov = torch.empty_like(d); cp = torch.empty_like(d)
+            mk = torch.empty(d.shape[:3], dtype=torch.uint8, device="cuda")
+            for i in range(0, n - 1, 4):
+                pipe.process_device(d[i:i + 4], ov[i:i + 4], cp[i:i + 4], mk[i:i + 4])
+            pipe.flush()
+            torch.cuda.synchronize()
+            res.append((host(ov), host(cp), host(mk), pipe.counters()))
+            pipe.close()
+        for a, b in zip(res[0][:3], res[1][:3]):
+            assert np.array_equal(a, b), mode
+        assert res[0][3] == res[1][3]
+        ref = loops.window_loop(list(frames), **kw) if mode == "window" else loops.fd_loop(list(frames))
+        assert np.array_equal(res[1][2], np.stack(ref["mask" if mode == "window" else "acc"])), mode
+
+
 def test_state_handoff_between_handles(P):
     """Frame-chunk sharding: a second handle continues a stream from a state blob."""
     from dynamic_video_compression_surveillance_b200.synth import make_clip
