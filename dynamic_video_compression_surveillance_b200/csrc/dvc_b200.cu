@@ -253,10 +253,21 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         const float band = std::max(1.0e-5f, 4.0f * 1.8e-7f * (512.0f / q));
         qc.tie_lo = 0.5f - band;
         qc.fast = band <= 0.01f && q <= 1.0e6f;
-        dim3 grid(cdiv((size_t)(W / 8) * (H / 4), 256), n);
+        dim3 grid((unsigned)((H / 4) * ((W / 8 + 255) / 256)), n);
         static const bool luma_dp4a = [] { const char* e = getenv("DVC_LUMA_DP4A"); return e ? atoi(e) != 0 : true; }();
-        if (luma_dp4a) k_degrade4<true><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
-        else k_degrade4<false><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
+        static const bool tma_env = [] { const char* e = getenv("DVC_K4_TMA_STORE"); return e ? atoi(e) != 0 : true; }();
+        const bool tma = tma_env && W % 16 == 0;
+        const size_t smem = tma ? 8 * (size_t)K4_WARP_STAGE_BYTES : 0;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU(cudaFuncSetAttribute(k_degrade4<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CU(cudaFuncSetAttribute(k_degrade4<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            attr_set = true;
+        }
+        if (luma_dp4a && tma) k_degrade4<true, true><<<grid, 256, smem, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
+        else if (luma_dp4a) k_degrade4<true, false><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
+        else if (tma) k_degrade4<false, true><<<grid, 256, smem, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
+        else k_degrade4<false, false><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
     } else {
         int rc = ensure_dct8(ERRBUF);
         if (rc) return rc;

@@ -229,16 +229,26 @@ DEVI uint32_t out_byte_bits(float v) {
     return r;
 }
 
-template <bool DP4A>
+// TMA_STORE: results are staged per warp in shared memory (each warp owns 32 adjacent pixel groups = 768 contiguous
+// bytes per row) and written with cp.async.bulk (one TMA store per row and output, issued by one lane), so HBM sees
+// whole lines instead of 8-byte pieces at a 24-byte lane stride.  Needs W % 16 == 0 (16-byte aligned row segments).
+// grid: (H/4 * ceil(W/8 / 256), n_frames): a CTA never straddles two block rows.
+constexpr int K4_WARP_STAGE_BYTES = 2 * 4 * 768;     // two outputs x four rows x 32 groups x 24 bytes
+
+template <bool DP4A, bool TMA_STORE>
 __global__ void __launch_bounds__(256, 4)
 k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127,
            const uint32_t* __restrict__ nonzero, uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay,
            int H, int W, int wpr, QuantConsts qc, Counters* __restrict__ counters) {
-    const int gpr = W >> 3, nbr = H >> 2;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(128) uint8_t k4_stage[];
+    const int gpr = W >> 3;
+    const int segs = (gpr + 255) >> 8;
+    const int br = blockIdx.x / segs, gx = (blockIdx.x - br * segs) * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint8_t* const wbuf = k4_stage + (threadIdx.x >> 5) * K4_WARP_STAGE_BYTES;      // this warp's staging area
+    const int warp_groups = min(32, gpr - (gx - lane));                              // valid groups in this warp (<= 0: none)
     unsigned n_motion = 0, n_static = 0;
-    if (gid < gpr * nbr) {
-        const int br = gid / gpr, gx = gid - br * gpr;
+    if (gx < gpr) {
         const size_t frame_off = (size_t)blockIdx.y * H * W * 3;
         const size_t plane_off = (size_t)blockIdx.y * H * wpr;
         const size_t base = frame_off + ((size_t)(br * 4) * W + (size_t)gx * 8) * 3;
@@ -264,8 +274,10 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
             for (int r = 0; r < 4; ++r) {
                 if (hi[r] == 0u) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i)
-                        __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
+                    for (int i = 0; i < 3; ++i) {
+                        if (TMA_STORE) *reinterpret_cast<uint2*>(wbuf + r * 768 + lane * 24 + 8 * i) = make_uint2(w[r][2 * i], w[r][2 * i + 1]);
+                        else __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
+                    }
                     continue;
                 }
                 uint32_t o[6];
@@ -282,8 +294,10 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(o[2 * i], o[2 * i + 1]));
+                for (int i = 0; i < 3; ++i) {
+                    if (TMA_STORE) *reinterpret_cast<uint2*>(wbuf + r * 768 + lane * 24 + 8 * i) = make_uint2(o[2 * i], o[2 * i + 1]);
+                    else __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(o[2 * i], o[2 * i + 1]));
+                }
             }
         }
         n_motion = __popc(hi[0]) + __popc(hi[1]) + __popc(hi[2]) + __popc(hi[3]);
@@ -336,8 +350,31 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    __stcs(reinterpret_cast<uint2*>(compressed + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
+                for (int i = 0; i < 3; ++i) {
+                    if (TMA_STORE) *reinterpret_cast<uint2*>(wbuf + (4 + r) * 768 + lane * 24 + 8 * i) = make_uint2(w[r][2 * i], w[r][2 * i + 1]);
+                    else __stcs(reinterpret_cast<uint2*>(compressed + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
+                }
+        }
+    }
+    if (TMA_STORE && warp_groups > 0) {
+        // generic-proxy writes to shared memory -> visible to the async proxy, then one lane issues the bulk stores
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)warp_groups * 24u;
+            const size_t seg = (size_t)blockIdx.y * H * W * 3 + ((size_t)(br * 4) * W + (size_t)(gx) * 8) * 3;   // lane 0's group
+            const size_t pitch = (size_t)W * 3;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (overlay)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(overlay + seg + r * pitch), "r"((uint32_t)__cvta_generic_to_shared(wbuf + r * 768)), "r"(bytes) : "memory");
+                if (compressed)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(compressed + seg + r * pitch), "r"((uint32_t)__cvta_generic_to_shared(wbuf + (4 + r) * 768)), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
         }
     }
     // ---- statistics: warp shuffle reduction, one atomic pair per warp ----
