@@ -253,11 +253,11 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         const float band = std::max(1.0e-5f, 4.0f * 1.8e-7f * (512.0f / q));
         qc.tie_lo = 0.5f - band;
         qc.fast = band <= 0.01f && q <= 1.0e6f;
-        dim3 grid((unsigned)((H / 4) * ((W / 8 + 255) / 256)), n);
+        dim3 grid(cdiv((size_t)(W / 8) * (H / 4), 256), n);
         static const bool luma_dp4a = [] { const char* e = getenv("DVC_LUMA_DP4A"); return e ? atoi(e) != 0 : true; }();
         static const bool tma_env = [] { const char* e = getenv("DVC_K4_TMA_STORE"); return e ? atoi(e) != 0 : true; }();
         const bool tma = tma_env && W % 16 == 0;
-        const size_t smem = tma ? 8 * (size_t)K4_WARP_STAGE_BYTES : 0;
+        const size_t smem = tma ? (size_t)K4_STAGE_BYTES : 0;
         static bool attr_set = false;
         if (!attr_set) {
             CU(cudaFuncSetAttribute(k_degrade4<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -229,11 +229,18 @@ DEVI uint32_t out_byte_bits(float v) {
     return r;
 }
 
-// TMA_STORE: results are staged per warp in shared memory (each warp owns 32 adjacent pixel groups = 768 contiguous
-// bytes per row) and written with cp.async.bulk (one TMA store per row and output, issued by one lane), so HBM sees
-// whole lines instead of 8-byte pieces at a 24-byte lane stride.  Needs W % 16 == 0 (16-byte aligned row segments).
-// grid: (H/4 * ceil(W/8 / 256), n_frames): a CTA never straddles two block rows.
-constexpr int K4_WARP_STAGE_BYTES = 2 * 4 * 768;     // two outputs x four rows x 32 groups x 24 bytes
+// TMA_STORE: results are staged per CTA in shared memory (256 adjacent pixel groups = 6 KB contiguous per row) and
+// written with cp.async.bulk (one TMA store per row and output, issued by one thread), so HBM sees whole lines
+// instead of 8-byte pieces at a 24-byte lane stride.  Needs W % 16 == 0 (16-byte aligned row segments).
+constexpr int K4_ROW_BYTES = 256 * 24;                 // one row of a CTA's 256 pixel groups
+constexpr int K4_STAGE_BYTES = 2 * 4 * K4_ROW_BYTES;   // two outputs x four rows
+
+DEVI void sts64(uint32_t saddr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+DEVI void bulk_store(const void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
 
 template <bool DP4A, bool TMA_STORE>
 __global__ void __launch_bounds__(256, 4)
@@ -241,14 +248,14 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
            const uint32_t* __restrict__ nonzero, uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay,
            int H, int W, int wpr, QuantConsts qc, Counters* __restrict__ counters) {
     extern __shared__ __align__(128) uint8_t k4_stage[];
-    const int gpr = W >> 3;
-    const int segs = (gpr + 255) >> 8;
-    const int br = blockIdx.x / segs, gx = (blockIdx.x - br * segs) * 256 + threadIdx.x;
+    const int gpr = W >> 3, nbr = H >> 2;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    uint8_t* const wbuf = k4_stage + (threadIdx.x >> 5) * K4_WARP_STAGE_BYTES;      // this warp's staging area
-    const int warp_groups = min(32, gpr - (gx - lane));                              // valid groups in this warp (<= 0: none)
+    // CTA staging area as a shared-window address: row r of output o sits at (o * 4 + r) * K4_ROW_BYTES, thread t at 24 t
+    const uint32_t wst = (uint32_t)__cvta_generic_to_shared(k4_stage) + threadIdx.x * 24;
     unsigned n_motion = 0, n_static = 0;
-    if (gx < gpr) {
+    if (gid < gpr * nbr) {
+        const int br = gid / gpr, gx = gid - br * gpr;
         const size_t frame_off = (size_t)blockIdx.y * H * W * 3;
         const size_t plane_off = (size_t)blockIdx.y * H * wpr;
         const size_t base = frame_off + ((size_t)(br * 4) * W + (size_t)gx * 8) * 3;
@@ -275,7 +282,7 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
                 if (hi[r] == 0u) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
-                        if (TMA_STORE) *reinterpret_cast<uint2*>(wbuf + r * 768 + lane * 24 + 8 * i) = make_uint2(w[r][2 * i], w[r][2 * i + 1]);
+                        if (TMA_STORE) sts64(wst + r * K4_ROW_BYTES + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
                         else __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
                     }
                     continue;
@@ -295,7 +302,7 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
                 }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    if (TMA_STORE) *reinterpret_cast<uint2*>(wbuf + r * 768 + lane * 24 + 8 * i) = make_uint2(o[2 * i], o[2 * i + 1]);
+                    if (TMA_STORE) sts64(wst + r * K4_ROW_BYTES + 8 * i, o[2 * i], o[2 * i + 1]);
                     else __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(o[2 * i], o[2 * i + 1]));
                 }
             }
@@ -351,27 +358,37 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    if (TMA_STORE) *reinterpret_cast<uint2*>(wbuf + (4 + r) * 768 + lane * 24 + 8 * i) = make_uint2(w[r][2 * i], w[r][2 * i + 1]);
+                    if (TMA_STORE) sts64(wst + (4 + r) * K4_ROW_BYTES + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
                     else __stcs(reinterpret_cast<uint2*>(compressed + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
                 }
         }
     }
-    if (TMA_STORE && warp_groups > 0) {
-        // generic-proxy writes to shared memory -> visible to the async proxy, then one lane issues the bulk stores
+    if (TMA_STORE) {
+        // generic-proxy writes to shared memory -> visible to the async proxy, then one thread issues the bulk stores:
+        // the CTA's 256 groups are contiguous in a row (6 KB per row and output); a CTA that crosses the end of a block
+        // row issues two parts.  Few large bulk operations keep the TMA unit's issue rate off the critical path.
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-            const uint32_t bytes = (uint32_t)warp_groups * 24u;
-            const size_t seg = (size_t)blockIdx.y * H * W * 3 + ((size_t)(br * 4) * W + (size_t)(gx) * 8) * 3;   // lane 0's group
+        __syncthreads();
+        const int g0 = blockIdx.x * blockDim.x;                 // first group of this CTA
+        if (threadIdx.x == 0) {
+            const int total = gpr * nbr;
+            const int br0 = g0 / gpr, gx0 = g0 - br0 * gpr;
+            const int n1 = min(min((int)blockDim.x, gpr - gx0), total - g0);   // groups in block row br0
+            const int n2 = min((int)blockDim.x - n1, total - g0 - n1);        // groups in block row br0 + 1
             const size_t pitch = (size_t)W * 3;
+            const size_t fo = (size_t)blockIdx.y * H * W * 3;
+            const size_t seg1 = fo + ((size_t)(br0 * 4) * W + (size_t)gx0 * 8) * 3;
+            const size_t seg2 = fo + (size_t)((br0 + 1) * 4) * W * 3;
+            const uint32_t sbase = wst;                          // thread 0: start of the staging area
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (overlay)
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 ::"l"(overlay + seg + r * pitch), "r"((uint32_t)__cvta_generic_to_shared(wbuf + r * 768)), "r"(bytes) : "memory");
-                if (compressed)
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 ::"l"(compressed + seg + r * pitch), "r"((uint32_t)__cvta_generic_to_shared(wbuf + (4 + r) * 768)), "r"(bytes) : "memory");
+            for (int o = 0; o < 2; ++o) {
+                uint8_t* dst = o == 0 ? overlay : compressed;
+                if (!dst) continue;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    bulk_store(dst + seg1 + r * pitch, sbase + (o * 4 + r) * K4_ROW_BYTES, (uint32_t)n1 * 24u);
+                    if (n2 > 0) bulk_store(dst + seg2 + r * pitch, sbase + (o * 4 + r) * K4_ROW_BYTES + (uint32_t)n1 * 24u, (uint32_t)n2 * 24u);
+                }
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
