@@ -372,23 +372,24 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
         const int g0 = blockIdx.x * blockDim.x;                 // first group of this CTA
         if (threadIdx.x == 0) {
             const int total = gpr * nbr;
-            const int br0 = g0 / gpr, gx0 = g0 - br0 * gpr;
-            const int n1 = min(min((int)blockDim.x, gpr - gx0), total - g0);   // groups in block row br0
-            const int n2 = min((int)blockDim.x - n1, total - g0 - n1);        // groups in block row br0 + 1
             const size_t pitch = (size_t)W * 3;
             const size_t fo = (size_t)blockIdx.y * H * W * 3;
-            const size_t seg1 = fo + ((size_t)(br0 * 4) * W + (size_t)gx0 * 8) * 3;
-            const size_t seg2 = fo + (size_t)((br0 + 1) * 4) * W * 3;
             const uint32_t sbase = wst;                          // thread 0: start of the staging area
+            const int g_end = min(g0 + (int)blockDim.x, total);
+            for (int g = g0; g < g_end;) {                       // one part per block row the CTA touches
+                const int brp = g / gpr, gxp = g - brp * gpr;
+                const int np = min(gpr - gxp, g_end - g);
+                const size_t seg = fo + ((size_t)(brp * 4) * W + (size_t)gxp * 8) * 3;
+                const uint32_t soff = (uint32_t)(g - g0) * 24u;
 #pragma unroll
-            for (int o = 0; o < 2; ++o) {
-                uint8_t* dst = o == 0 ? overlay : compressed;
-                if (!dst) continue;
+                for (int o = 0; o < 2; ++o) {
+                    uint8_t* dst = o == 0 ? overlay : compressed;
+                    if (!dst) continue;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    bulk_store(dst + seg1 + r * pitch, sbase + (o * 4 + r) * K4_ROW_BYTES, (uint32_t)n1 * 24u);
-                    if (n2 > 0) bulk_store(dst + seg2 + r * pitch, sbase + (o * 4 + r) * K4_ROW_BYTES + (uint32_t)n1 * 24u, (uint32_t)n2 * 24u);
+                    for (int r = 0; r < 4; ++r)
+                        bulk_store(dst + seg + r * pitch, sbase + (o * 4 + r) * K4_ROW_BYTES + soff, (uint32_t)np * 24u);
                 }
+                g += np;
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
