@@ -139,7 +139,7 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__(256)
 k_gray_blur5(const uint8_t* __restrict__ frames, uint8_t* __restrict__ blurred, int H, int W) {
     __shared__ __align__(16) uint8_t sg[(BL_TH + 4) * BL_GP];      // gray, column c <-> x = x0 - BL_PAD + c
-    __shared__ __align__(16) uint16_t sh[(BL_TH + 4) * BL_TW];     // horizontal pass
+    __shared__ __align__(16) uint2 sh[(BL_TH + 4) * (BL_TW / 4)];   // horizontal pass: (even, odd) 16-bit lane pairs per 4 px
     const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
     const uint8_t* fr = frames + (size_t)blockIdx.z * H * W * 3;
     uint8_t* out = blurred + (size_t)blockIdx.z * H * W;
@@ -179,33 +179,51 @@ k_gray_blur5(const uint8_t* __restrict__ frames, uint8_t* __restrict__ blurred, 
         sg[r * BL_GP + BL_PAD + dx] = v;
     }
     __syncthreads();
-    // phase 2: horizontal 5 taps, 4 pixels per task
+    // phase 2: horizontal 5 taps on 16-bit lanes (two pixels per 32-bit operation).  A task is one aligned group of
+    // four pixels: the shifted byte windows come from funnel shifts of (prev, cur, next), PRMT widens even / odd bytes
+    // to 16-bit lanes, and h = (a + e) + 4 (b + d) + 6 c <= 4080 per lane.  Result per group: (even lanes, odd lanes).
     for (int task = tid; task < (BL_TH + 4) * (BL_TW / 4); task += 256) {
-        const int r = task / (BL_TW / 4), c = (task % (BL_TW / 4)) * 4;
-        if (c >= tw) continue;
-        const uint8_t* g = &sg[r * BL_GP + BL_PAD + c];
-        uint32_t v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = g[i - 2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            sh[r * BL_TW + c + i] = (uint16_t)(v[i] + 4 * v[i + 1] + 6 * v[i + 2] + 4 * v[i + 3] + v[i + 4]);
+        const int r = task / (BL_TW / 4), cg = task % (BL_TW / 4);
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(&sg[r * BL_GP + BL_PAD]) + cg;
+        const uint32_t prev = g[-1], cur = g[0], next = g[1];
+        const uint32_t a = __funnelshift_r(prev, cur, 16), b = __funnelshift_r(prev, cur, 24);
+        const uint32_t d = __funnelshift_r(cur, next, 8), e = __funnelshift_r(cur, next, 16);
+        uint2 h;
+        {
+            const uint32_t ae = __byte_perm(a, 0u, 0x4240u) + __byte_perm(e, 0u, 0x4240u);
+            const uint32_t bd = __byte_perm(b, 0u, 0x4240u) + __byte_perm(d, 0u, 0x4240u);
+            h.x = ae + 4u * bd + 6u * __byte_perm(cur, 0u, 0x4240u);
+        }
+        {
+            const uint32_t ae = __byte_perm(a, 0u, 0x4341u) + __byte_perm(e, 0u, 0x4341u);
+            const uint32_t bd = __byte_perm(b, 0u, 0x4341u) + __byte_perm(d, 0u, 0x4341u);
+            h.y = ae + 4u * bd + 6u * __byte_perm(cur, 0u, 0x4341u);
+        }
+        sh[r * (BL_TW / 4) + cg] = h;
     }
     __syncthreads();
-    // phase 3: vertical 5 taps + rounding, 16 pixels per task -> one 16-byte store
-    for (int task = tid; task < BL_TH * (BL_TW / 16); task += 256) {
-        const int r = task / (BL_TW / 16), c = (task % (BL_TW / 16)) * 16;
-        const int y = y0 + r;
-        if (y >= H || c >= tw) continue;
-        uint32_t o[4] = {0, 0, 0, 0};
+    // phase 3: vertical 5 taps + rounding, still two pixels per operation (v <= 65280 fits a 16-bit lane).  A thread
+    // owns one 4-pixel column group and four consecutive output rows, sliding a 5-row window through registers; a warp
+    // writes 128 contiguous bytes per row.
+    {
+        const int cg = tid & 31, r0 = (tid >> 5) * 4;
+        const uint2* col = sh + r0 * (BL_TW / 4) + cg;
+        uint2 w0 = col[0], w1 = col[BL_TW / 4], w2 = col[2 * (BL_TW / 4)], w3 = col[3 * (BL_TW / 4)];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint16_t* h = &sh[r * BL_TW + c + i];
-            uint32_t v = h[0] + 4u * h[BL_TW] + 6u * h[2 * BL_TW] + 4u * h[3 * BL_TW] + h[4 * BL_TW];
-            o[i >> 2] |= ((v + 128u) >> 8) << ((i & 3) * 8);
+        for (int i = 0; i < 4; ++i) {
+            const uint2 w4 = col[(4 + i) * (BL_TW / 4)];
+            const uint32_t ve = (w0.x + w4.x) + 4u * (w1.x + w3.x) + 6u * w2.x;
+            const uint32_t vo = (w0.y + w4.y) + 4u * (w1.y + w3.y) + 6u * w2.y;
+            const uint32_t re = ((ve + 0x00800080u) >> 8) & 0x00ff00ffu, ro = ((vo + 0x00800080u) >> 8) & 0x00ff00ffu;
+            const uint32_t o = re | (ro << 8);
+            const int y = y0 + r0 + i, x = x0 + cg * 4;
+            if (y < H && x < W) {
+                uint8_t* q = out + (size_t)y * W + x;
+                if ((W & 3) == 0) *reinterpret_cast<uint32_t*>(q) = o;
+                else for (int k = 0; k < min(4, W - x); ++k) q[k] = (uint8_t)(o >> (8 * k));
+            }
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4;
         }
-        if (ALIGNED && x0 + c + 16 <= W) store16(out + (size_t)y * W + x0 + c, o);
-        else store_u8x16_generic(out + (size_t)y * W, x0 + c, W, o);
     }
 }
 
