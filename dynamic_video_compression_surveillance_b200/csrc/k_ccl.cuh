@@ -165,6 +165,12 @@ k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __re
     const uint32_t upr = CONN == 8 ? plane_word<INVERT>(plane, y - 1, j + 1, H, W, wpr) : 0u;
     if (!(up | (upl >> 31) | (upr & 1u))) return;
     const int word = (int)idx, word_up = word - wpr;
+    // The run through bit 0 of this word and the run through bit 0 of the word above both continue from the words to
+    // the left: the thread of word j-1 already links those two horizontal runs, so this pair is skipped.  Inside wide
+    // regions only the left-most word of every row does a union.
+    const uint32_t left = plane_word<INVERT>(plane, y, j - 1, H, W, wpr);
+    const uint32_t up_left = CONN == 8 ? upl : plane_word<INVERT>(plane, y - 1, j - 1, H, W, wpr);
+    const bool skip_first = (cur & 1u) && (up & 1u) && (left >> 31) && (up_left >> 31);
     uint32_t m = cur;
     int slot = 0;
     while (m) {
@@ -177,6 +183,7 @@ k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __re
         uint32_t nm = run;
         if (CONN == 8) nm |= (run << 1) | (run >> 1);
         uint32_t n = up & nm;
+        if (lo == 0 && skip_first) n &= ~run_mask_from(up, 0);
         while (n) {
             const int p = __ffs(n) - 1;
             const int o = node_id(word_up, run_slot(up, p));
@@ -184,7 +191,7 @@ k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __re
             n &= ~run_mask_from(up, run_start(up, p));
         }
         if (CONN == 8) {
-            if (lo == 0 && (upl >> 31)) {
+            if (lo == 0 && (upl >> 31) && !skip_first) {
                 const int o = node_id(word_up - 1, __popc(run_starts(upl)) - 1);
                 if (__ldcg(uf_addr(P, o)) != pa) uf_union(P, id, o);
             }
