@@ -1,9 +1,9 @@
 """Host side of the per-video pipelines: decode -> pinned chunk -> GPU loop -> encode, plus the reporting the
 reference's GUI and performance_analysis.py depend on (file names, ``execution_times.txt`` layout, log lines).
 
-Design (not the reference's): a ``ChunkedReader`` fills a pinned batch buffer from cv2.VideoCapture, the GPU
-loop runs per batch through ``FramePipeline.process_host`` (upload / kernels / download double-buffered inside
-the library), a ``FrameSink`` pair writes the results.  What stays on the host is what SURVEY.md section 8 leaves
+Design (not the reference's): a decode thread fills pinned batch buffers from cv2.VideoCapture, the GPU loop runs
+per batch through ``FramePipeline.process_host`` (upload / kernels / download double-buffered inside the library),
+an encode thread feeds the two VideoWriters.  What stays on the host is what SURVEY.md section 8 leaves
 there: codecs, the optional resize (frame_differencing.py:74,91), the first frame's heavy blur (:77), Farneback
 flow (motion_compression_opt.py:72-82) and contour -> rectangle drawing (:93-97).
 """
@@ -51,31 +51,6 @@ def write_execution_times(path: str, stages: list[StageTiming], total_s: float) 
         f.write(f"Total video processing time: {total_s:.2f} seconds\n")
 
 
-class ChunkedReader:
-    """cv2.VideoCapture -> batches of frames written straight into a pinned [B,H,W,3] buffer."""
-
-    def __init__(self, cap, size_wh, batch: int):
-        self.cap, self.size, self.batch = cap, size_wh, batch
-        w, h = size_wh
-        self.buf = P.pinned_empty((batch, h, w, 3))
-        self.view = self.buf.numpy()
-        self.done = False
-
-    def next_chunk(self) -> int:
-        n = 0
-        w, h = self.size
-        while n < self.batch and not self.done:
-            ok, frame = self.cap.read()
-            if not ok:
-                self.done = True
-                break
-            if (frame.shape[1], frame.shape[0]) != (w, h):
-                frame = cv2.resize(frame, (w, h))             # scale_factor != 1 (frame_differencing.py:91)
-            self.view[n] = frame
-            n += 1
-        return n
-
-
 @dataclass
 class FdRun:
     frames: int = 0
@@ -83,30 +58,113 @@ class FdRun:
     counters: dict = field(default_factory=dict)
 
 
-def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int, device, progress_callback) -> FdRun:
+def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int, device, progress_callback,
+                  threaded: bool = True) -> FdRun:
     """The loop of frame_differencing.py:73-138 for one opened capture.  ``sinks`` = (overlay writer, compressed
-    writer).  Raises on failure; the caller owns the reference's swallow-and-log policy."""
+    writer).  Raises on failure; the caller owns the reference's swallow-and-log policy.
+
+    Three stages run concurrently over a small pool of pinned buffer sets: a decode thread (cap.read -> pinned input
+    batch), this thread (GPU loop on the batch), an encode thread (the two VideoWriters).  cv2 releases the GIL in its
+    codecs, so decode, GPU and encode overlap; output order and the 50-frame progress cadence are unchanged."""
+    import queue
+    import threading
+
     w, h = size_wh
     seed = cv2.GaussianBlur(cv2.cvtColor(cv2.resize(first_frame, (w, h)), cv2.COLOR_BGR2GRAY), (25, 25), 30)
     run = FdRun()
+    n_sets = 3 if threaded else 1
+    shape = (max_batch, h, w, 3)
+    sets = [dict(inp=P.pinned_empty(shape), ov=P.pinned_empty(shape), cp=P.pinned_empty(shape)) for _ in range(n_sets)]
+    for st in sets:
+        st["inp_v"], st["ov_v"], st["cp_v"] = st["inp"].numpy(), st["ov"].numpy(), st["cp"].numpy()
+    free_q, ready_q, done_q = queue.Queue(), queue.Queue(maxsize=n_sets), queue.Queue(maxsize=n_sets)
+    for st in sets:
+        free_q.put(st)
+    errors = []
+    stop = threading.Event()
+
+    def fill(st) -> int:
+        n = 0
+        while n < max_batch:
+            ok, frame = cap.read()
+            if not ok:
+                break
+            if (frame.shape[1], frame.shape[0]) != (w, h):
+                frame = cv2.resize(frame, (w, h))             # scale_factor != 1 (frame_differencing.py:91)
+            st["inp_v"][n] = frame
+            n += 1
+        return n
+
+    def drain(st, n, t0):
+        for i in range(n):
+            sinks[0].write(st["ov_v"][i])
+            sinks[1].write(st["cp_v"][i])
+            run.frames += 1
+            if progress_callback is not None and run.frames % 50 == 0:      # frame_differencing.py:137-138
+                progress_callback(run.frames)
+        run.per_frame_s.extend([(time.time() - t0) / n] * n)
+
+    def decoder():
+        try:
+            while not stop.is_set():
+                st = free_q.get()
+                if st is None:
+                    break
+                t0 = time.time()
+                n = fill(st)
+                ready_q.put((st, n, t0))
+                if n < max_batch:
+                    break
+        except Exception as e:                                   # surfaced by the main thread
+            errors.append(e)
+            ready_q.put((None, 0, 0.0))
+
+    def encoder():
+        try:
+            while True:
+                item = done_q.get()
+                if item is None:
+                    break
+                st, n, t0 = item
+                drain(st, n, t0)
+                free_q.put(st)
+        except Exception as e:
+            errors.append(e)
+            stop.set()
+            while done_q.get() is not None:                      # keep the pipeline from blocking
+                pass
+
     with P.FramePipeline(w, h, "fd", max_batch=max_batch, device=device, **params) as pipe:
         pipe.begin_stream(seed)
-        reader = ChunkedReader(cap, size_wh, max_batch)
-        out_ov, out_cp = P.pinned_empty(reader.buf.shape), P.pinned_empty(reader.buf.shape)
-        v_ov, v_cp = out_ov.numpy(), out_cp.numpy()
-        while True:
-            t0 = time.time()
-            n = reader.next_chunk()
-            if n == 0:
-                break
-            pipe.process_host(reader.buf[:n], out_ov[:n], out_cp[:n])
-            for i in range(n):
-                sinks[0].write(v_ov[i])
-                sinks[1].write(v_cp[i])
-                run.frames += 1
-                if progress_callback is not None and run.frames % 50 == 0:      # frame_differencing.py:137-138
-                    progress_callback(run.frames)
-            run.per_frame_s.extend([(time.time() - t0) / n] * n)
+        if not threaded:
+            st = sets[0]
+            while True:
+                t0 = time.time()
+                n = fill(st)
+                if n == 0:
+                    break
+                pipe.process_host(st["inp"][:n], st["ov"][:n], st["cp"][:n])
+                drain(st, n, t0)
+        else:
+            td, te = threading.Thread(target=decoder, daemon=True), threading.Thread(target=encoder, daemon=True)
+            td.start(); te.start()
+            try:
+                while True:
+                    st, n, t0 = ready_q.get()
+                    if st is None or n == 0 or errors:
+                        break
+                    pipe.process_host(st["inp"][:n], st["ov"][:n], st["cp"][:n])
+                    done_q.put((st, n, t0))
+                    if n < max_batch:
+                        break
+            finally:
+                stop.set()
+                done_q.put(None)
+                free_q.put(None)
+                te.join()
+                td.join(timeout=5)
+            if errors:
+                raise errors[0]
         run.counters = pipe.counters()
     return run
 
