@@ -77,7 +77,9 @@ def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int
     sets = [dict(inp=P.pinned_empty(shape), ov=P.pinned_empty(shape), cp=P.pinned_empty(shape)) for _ in range(n_sets)]
     for st in sets:
         st["inp_v"], st["ov_v"], st["cp_v"] = st["inp"].numpy(), st["ov"].numpy(), st["cp"].numpy()
-    free_q, ready_q, done_q = queue.Queue(), queue.Queue(maxsize=n_sets), queue.Queue(maxsize=n_sets)
+    free_q, ready_q = queue.Queue(), queue.Queue(maxsize=n_sets)
+    enc_q = (queue.Queue(maxsize=n_sets), queue.Queue(maxsize=n_sets))     # one encode thread per VideoWriter
+    lock = threading.Lock()
     for st in sets:
         free_q.put(st)
     errors = []
@@ -119,19 +121,32 @@ def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int
             errors.append(e)
             ready_q.put((None, 0, 0.0))
 
-    def encoder():
+    def encoder(k):
+        """Encode thread of sink k (0: overlay video, 1: compressed video).  The thread that finishes a buffer set
+        last accounts the frames (count, per-frame time, progress callback) and hands the set back to the decoder."""
         try:
             while True:
-                item = done_q.get()
+                item = enc_q[k].get()
                 if item is None:
                     break
                 st, n, t0 = item
-                drain(st, n, t0)
-                free_q.put(st)
+                view = st["ov_v"] if k == 0 else st["cp_v"]
+                for i in range(n):
+                    sinks[k].write(view[i])
+                with lock:
+                    st["pending"] -= 1
+                    last = st["pending"] == 0
+                if last:
+                    for _ in range(n):
+                        run.frames += 1
+                        if progress_callback is not None and run.frames % 50 == 0:      # frame_differencing.py:137-138
+                            progress_callback(run.frames)
+                    run.per_frame_s.extend([(time.time() - t0) / n] * n)
+                    free_q.put(st)
         except Exception as e:
             errors.append(e)
             stop.set()
-            while done_q.get() is not None:                      # keep the pipeline from blocking
+            while enc_q[k].get() is not None:                    # keep the pipeline from blocking
                 pass
 
     with P.FramePipeline(w, h, "fd", max_batch=max_batch, device=device, **params) as pipe:
@@ -146,22 +161,29 @@ def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int
                 pipe.process_host(st["inp"][:n], st["ov"][:n], st["cp"][:n])
                 drain(st, n, t0)
         else:
-            td, te = threading.Thread(target=decoder, daemon=True), threading.Thread(target=encoder, daemon=True)
-            td.start(); te.start()
+            td = threading.Thread(target=decoder, daemon=True)
+            tes = [threading.Thread(target=encoder, args=(k,), daemon=True) for k in (0, 1)]
+            td.start()
+            for t in tes:
+                t.start()
             try:
                 while True:
                     st, n, t0 = ready_q.get()
                     if st is None or n == 0 or errors:
                         break
                     pipe.process_host(st["inp"][:n], st["ov"][:n], st["cp"][:n])
-                    done_q.put((st, n, t0))
+                    st["pending"] = 2
+                    for q in enc_q:
+                        q.put((st, n, t0))
                     if n < max_batch:
                         break
             finally:
                 stop.set()
-                done_q.put(None)
+                for q in enc_q:
+                    q.put(None)
                 free_q.put(None)
-                te.join()
+                for t in tes:
+                    t.join()
                 td.join(timeout=5)
             if errors:
                 raise errors[0]
