@@ -44,6 +44,9 @@ static int set_err(char* dst, int code, const char* fmt, ...) {
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
+static int pack_to_bits(const uint8_t* src, uint32_t* dst, int n, int H, int W, cudaStream_t st);
+static int unpack_from_bits(const uint32_t* src, uint8_t* dst, int n, int H, int W, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // structuring elements -> MorphChain
 // ------------------------------------------------------------------------------------------------
@@ -663,10 +666,9 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         }
         over127 = nonzero = fin;
         if (mask_out) {
-            dim3 gu(cdiv((size_t)((W + 3) / 4) * H, 256), T);
             ProfScope ps(h, DVC_PROF_MISC, 1, st);
-            k_unpack_bits<<<gu, 256, 0, st>>>(fin, mask_out, H, W, wpr);
-            CHECK_LAUNCH();
+            int rc = unpack_from_bits(fin, mask_out, T, H, W, st);
+            if (rc) return rc;
         }
     } else {
         dim3 gb((W + BL_TW - 1) / BL_TW, (H + BL_TH - 1) / BL_TH, T);
@@ -868,27 +870,26 @@ extern "C" int dvc_gray_absdiff_thresh_u8(const uint8_t* bgr, const uint8_t* pre
         else k_diff_thresh_planes<false><<<gd, 256, 0, st>>>(bl, prev_gray, H, W, (uint32_t*)bits.p, wpr, thr);
         CHECK_LAUNCH();
     }
-    if (mask_out) {
-        dim3 gu(cdiv((size_t)((W + 3) / 4) * H, 256), n);
-        k_unpack_bits<<<gu, 256, 0, st>>>((const uint32_t*)bits.p, mask_out, H, W, wpr);
-        CHECK_LAUNCH();
-    }
+    if (mask_out) return unpack_from_bits((const uint32_t*)bits.p, mask_out, n, H, W, st);
     return DVC_OK;
 }
 
 static int pack_to_bits(const uint8_t* src, uint32_t* dst, int n, int H, int W, cudaStream_t st) {
     char* ERRBUF = nullptr;
     const int wpr = words_per_row(W);
-    dim3 g(cdiv((size_t)H * wpr, 256), n);
-    k_pack_bits<<<g, 256, 0, st>>>(src, dst, H, W, wpr);
+    dim3 g(cdiv((size_t)((W + 15) / 16) * H, 256), n);
+    CU(cudaMemsetAsync(dst, 0, (size_t)n * H * wpr * 4, st));           // padding words of each row stay zero
+    if (W % 16 == 0) k_pack_bits<true, false><<<g, 256, 0, st>>>(src, dst, nullptr, H, W, wpr);
+    else k_pack_bits<false, false><<<g, 256, 0, st>>>(src, dst, nullptr, H, W, wpr);
     CHECK_LAUNCH();
     return DVC_OK;
 }
 static int unpack_from_bits(const uint32_t* src, uint8_t* dst, int n, int H, int W, cudaStream_t st) {
     char* ERRBUF = nullptr;
     const int wpr = words_per_row(W);
-    dim3 g(cdiv((size_t)((W + 3) / 4) * H, 256), n);
-    k_unpack_bits<<<g, 256, 0, st>>>(src, dst, H, W, wpr);
+    dim3 g(cdiv((size_t)((W + 15) / 16) * H, 256), n);
+    if (W % 16 == 0) k_unpack_bits<true><<<g, 256, 0, st>>>(src, dst, H, W, wpr);
+    else k_unpack_bits<false><<<g, 256, 0, st>>>(src, dst, H, W, wpr);
     CHECK_LAUNCH();
     return DVC_OK;
 }
@@ -1002,8 +1003,11 @@ extern "C" int dvc_degrade_blend_u8(const uint8_t* bgr, const uint8_t* mask, uin
     ScopedAsyncBuf hi(st), nz(st);
     CU(hi.alloc(pw * 4 * n));
     CU(nz.alloc(pw * 4 * n));
-    dim3 g(cdiv(pw, 256), n);
-    k_flags_from_u8<<<g, 256, 0, st>>>(mask, (uint32_t*)hi.p, (uint32_t*)nz.p, H, W, wpr);
+    dim3 g(cdiv((size_t)((W + 15) / 16) * H, 256), n);
+    CU(cudaMemsetAsync(hi.p, 0, pw * 4 * n, st));
+    CU(cudaMemsetAsync(nz.p, 0, pw * 4 * n, st));
+    if (W % 16 == 0) k_pack_bits<true, true><<<g, 256, 0, st>>>(mask, (uint32_t*)nz.p, (uint32_t*)hi.p, H, W, wpr);
+    else k_pack_bits<false, true><<<g, 256, 0, st>>>(mask, (uint32_t*)nz.p, (uint32_t*)hi.p, H, W, wpr);
     CHECK_LAUNCH();
     rc = launch_degrade(nullptr, bgr, (const uint32_t*)hi.p, (const uint32_t*)nz.p, compressed, overlay, n, H, W, block_size, q,
                         flavour, (Counters*)counters, st);

@@ -254,31 +254,57 @@ k_diff_thresh_planes(const uint8_t* __restrict__ planes, const uint8_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// u8 mask (0 / non-zero) <-> bit-plane, n images per launch (blockIdx.y)
+// u8 mask (0 / non-zero) <-> bit-plane, n images per launch (blockIdx.y).  One thread per 16 pixels: a 16-byte load,
+// SWAR byte tests, multiply-gather of the four flag bits per word, one 16-bit store (and the reverse).
 // ------------------------------------------------------------------------------------------------
+DEVI uint32_t gather_msb4(uint32_t m) { return (((m >> 7) & 0x01010101u) * 0x00204081u >> 21) & 0xfu; }   // bit 8p+7 -> bit p
+DEVI uint32_t nonzero_msb4(uint32_t x) { return (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u; }   // MSB set iff byte != 0
+
+template <bool ALIGNED, bool FLAGS>   // FLAGS: also emit the (> 127) plane
 __global__ void __launch_bounds__(256)
-k_pack_bits(const uint8_t* __restrict__ src, uint32_t* __restrict__ dst, int H, int W, int wpr) {
+k_pack_bits(const uint8_t* __restrict__ src, uint32_t* __restrict__ nonzero, uint32_t* __restrict__ over127, int H, int W,
+            int wpr) {
+    const int gpr = (W + 15) >> 4;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)H * wpr) return;
-    const int y = (int)(gid / wpr), j = (int)(gid % wpr);
+    if (gid >= (long long)gpr * H) return;
+    const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx << 4;
     const uint8_t* row = src + (size_t)blockIdx.y * H * W + (size_t)y * W;
-    uint32_t bits = 0;
-    const int n = min(32, W - j * 32);
-    for (int i = 0; i < n; ++i) bits |= (row[j * 32 + i] != 0 ? 1u : 0u) << i;
-    dst[(size_t)blockIdx.y * H * wpr + gid] = bits;
+    uint32_t v[4];
+    if (ALIGNED) load16(row + x0, v);
+    else load_u8x16_generic(row, x0, W, v);
+    uint32_t nz = 0, hi = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        nz |= gather_msb4(nonzero_msb4(v[q])) << (4 * q);
+        if (FLAGS) hi |= gather_msb4(v[q] & 0x80808080u) << (4 * q);
+    }
+    const size_t wo = (size_t)blockIdx.y * H * wpr + (size_t)y * wpr;
+    reinterpret_cast<uint16_t*>(nonzero + wo)[gx] = (uint16_t)nz;
+    if (FLAGS) reinterpret_cast<uint16_t*>(over127 + wo)[gx] = (uint16_t)hi;
+    // an odd number of 16-pixel groups leaves the upper half of the row's last used word: clear it
+    if (gx == gpr - 1 && (gpr & 1)) {
+        reinterpret_cast<uint16_t*>(nonzero + wo)[gx + 1] = 0;
+        if (FLAGS) reinterpret_cast<uint16_t*>(over127 + wo)[gx + 1] = 0;
+    }
 }
 
+template <bool ALIGNED>
 __global__ void __launch_bounds__(256)
 k_unpack_bits(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int wpr) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 pixels
-    const int qpr = (W + 3) >> 2;
-    if (gid >= (long long)H * qpr) return;
-    const int y = (int)(gid / qpr), x = (int)(gid % qpr) << 2;
-    const uint32_t word = src[(size_t)blockIdx.y * H * wpr + (size_t)y * wpr + (x >> 5)];
-    const uint32_t nib = (word >> (x & 31)) & 0xfu;
+    const int gpr = (W + 15) >> 4;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)gpr * H) return;
+    const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx << 4;
+    const uint32_t bits = reinterpret_cast<const uint16_t*>(src + (size_t)blockIdx.y * H * wpr + (size_t)y * wpr)[gx];
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t nib = (bits >> (4 * q)) & 0xfu;
+        v[q] = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;         // bit p -> byte p = 0xff
+    }
     uint8_t* row = dst + (size_t)blockIdx.y * H * W + (size_t)y * W;
-    const int n = min(4, W - x);
-    for (int i = 0; i < n; ++i) row[x + i] = (nib >> i) & 1u ? 255 : 0;
+    if (ALIGNED) store16(row + x0, v);
+    else store_u8x16_generic(row, x0, W, v);
 }
 
 }  // namespace dvc

@@ -131,25 +131,6 @@ k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t*
     else for (int i = 0; i < npx; ++i) arow[x0 + i] = (uint8_t)(a[i >> 2] >> ((i & 3) * 8));
 }
 
-// acc plane (uint8) -> the two flag planes, for callers that hand in an arbitrary uint8 mask
-__global__ void __launch_bounds__(256)
-k_flags_from_u8(const uint8_t* __restrict__ src, uint32_t* __restrict__ over127, uint32_t* __restrict__ nonzero,
-                int H, int W, int wpr) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)H * wpr) return;
-    const int y = (int)(gid / wpr), j = (int)(gid % wpr);
-    const uint8_t* row = src + (size_t)blockIdx.y * H * W + (size_t)y * W;
-    uint32_t hi = 0, nz = 0;
-    const int n = min(32, W - j * 32);
-    for (int i = 0; i < n; ++i) {
-        const uint32_t v = row[j * 32 + i];
-        hi |= (v > 127 ? 1u : 0u) << i;
-        nz |= (v != 0 ? 1u : 0u) << i;
-    }
-    over127[(size_t)blockIdx.y * H * wpr + gid] = hi;
-    nonzero[(size_t)blockIdx.y * H * wpr + gid] = nz;
-}
-
 // ------------------------------------------------------------------------------------------------
 // morphology chain
 // ------------------------------------------------------------------------------------------------
