@@ -14,6 +14,7 @@
 #include "../../include/dvc_b200.h"
 #include "k_ccl.cuh"
 #include "k_degrade.cuh"
+#include "k_degrade4p.cuh"
 #include "k_front.cuh"
 #include "k_mask.cuh"
 
@@ -267,6 +268,90 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
             CU(cudaFuncSetAttribute(k_degrade4<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             attr_set = true;
         }
+        static const bool packed_env = [] { const char* e = getenv("DVC_K4_PACKED"); return e ? atoi(e) != 0 : true; }();
+        if (packed_env && q >= 0.01f && q <= 1.0e6f) {
+            // packed-pair kernel: quotient by Markstein correction (exact for normal-range q), magic rounding needs |d/q| < 2^22
+            QuantP qp;
+            for (int ne = 0; ne < 3; ++ne) {
+                const float qs = q * (float)(1 << ne);
+                qp.rcp[ne] = 1.0f / qs;
+                qp.nqs[ne] = -qs;
+                qp.o[ne] = q / (float)(1 << ne);
+            }
+            static bool attr_p = false;
+            if (!attr_p) {
+                CU(cudaFuncSetAttribute(k_degrade4p<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CU(cudaFuncSetAttribute(k_degrade4r, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CU(cudaFuncSetAttribute(k_degrade4r, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_p = true;
+            }
+            static const bool rowspan_env = [] { const char* e = getenv("DVC_K4_ROWSPAN"); return e ? atoi(e) != 0 : true; }();
+            const int gpr = W / 8, nbr = H / 4;
+            const bool ptr16 = ((((uintptr_t)frames) | ((uintptr_t)compressed) | ((uintptr_t)overlay)) & 15u) == 0;
+            if (rowspan_env && ptr16 && (gpr <= 256 || W % 16 == 0)) {
+                K4Geom g;
+                if (gpr <= 256) {
+                    g.parts = 1; g.gp = gpr; g.nb = std::max(1, std::min(nbr, std::min(256 / gpr, 256 / wpr))); g.sp = W * 3;
+                    g.span_bytes = g.nb * 4 * W * 3;
+                } else {
+                    g.parts = (gpr + 255) / 256;
+                    g.gp = (((gpr + g.parts - 1) / g.parts) + 15) & ~15;
+                    g.parts = (gpr + g.gp - 1) / g.gp;
+                    g.nb = 1; g.sp = g.gp * 24; g.span_bytes = 4 * g.sp;
+                }
+                g.mask_bytes = 4 * g.nb * wpr * 4;
+                static const int dbg = [] { const char* e = getenv("DVC_K4_DEBUG"); return e ? atoi(e) : 0; }();
+                static const int pad = [] { const char* e = getenv("DVC_K4_SMEM_PAD"); return e ? atoi(e) : 0; }();
+                g.debug = dbg;
+                const size_t smem_r = (size_t)2 * g.span_bytes + 2 * g.mask_bytes + 16 + pad;
+                static const int persist = [] { const char* e = getenv("DVC_K4_PERSIST"); return e ? atoi(e) : 1; }();
+                if (persist) {
+                    static const int env_stages = [] { const char* e = getenv("DVC_K4_STAGES"); return e ? atoi(e) : 6; }();
+                    static const int env_groups = [] { const char* e = getenv("DVC_K4_GROUPS"); return e ? atoi(e) : 2; }();
+                    static const int env_rowcopy = [] { const char* e = getenv("DVC_K4_ROWCOPY"); return e ? atoi(e) : 0; }();
+                    static const int env_ctas = [] { const char* e = getenv("DVC_K4_CTAS"); return e ? atoi(e) : 0; }();
+                    int dev = 0, sms = 0;
+                    CU(cudaGetDevice(&dev));
+                    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                    K4SGeom sg;
+                    sg.g = g;
+                    sg.tiles_per_frame = g.parts == 1 ? (int)cdiv(nbr, g.nb) : nbr * g.parts;
+                    sg.n_tiles = sg.tiles_per_frame * n;
+                    sg.stage_bytes = (g.span_bytes + 2 * g.mask_bytes + 127) & ~127;
+                    sg.ybuf_bytes = (g.span_bytes + 127) & ~127;
+                    static const int env_cps = [] { const char* e = getenv("DVC_K4_CTAS_PER_SM"); return e ? atoi(e) : 1; }();
+                    const int G = env_groups == 1 ? 1 : (env_groups == 3 ? 3 : 2);
+                    const int cps = env_cps == 2 ? 2 : 1;
+                    int S = std::max(G, env_stages);
+                    const size_t smem_cap = cps == 2 ? 110 * 1024 : 224 * 1024;
+                    auto smem_need = [&](int stages) { return (size_t)stages * sg.stage_bytes + (size_t)G * sg.ybuf_bytes + 8 * (2 * stages + G) + 16 + 16 * stages; };
+                    while (smem_need(S) > smem_cap && S > G) --S;
+                    S -= S % G;
+                    sg.stages = S;
+                    sg.row_copies = env_rowcopy;
+                    const size_t smem_s = smem_need(S);
+                    const unsigned ctas = (unsigned)std::min(sg.n_tiles, env_ctas > 0 ? env_ctas : sms * cps);
+                    static bool attr_s = false;
+                    if (!attr_s) {
+                        CU(cudaFuncSetAttribute(k_degrade4s<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                        CU(cudaFuncSetAttribute(k_degrade4s<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                        CU(cudaFuncSetAttribute(k_degrade4s<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                        CU(cudaFuncSetAttribute(k_degrade4s<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                        CU(cudaFuncSetAttribute(k_degrade4s<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                        attr_s = true;
+                    }
+                    if (cps == 2) k_degrade4s<2, 2><<<ctas, 32 + 512, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
+                    else if (G == 1) k_degrade4s<1, 1><<<ctas, 32 + 256, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
+                    else if (G == 3) k_degrade4s<3, 1><<<ctas, 32 + 768, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
+                    else k_degrade4s<2, 1><<<ctas, 32 + 512, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
+                } else {
+                dim3 grid_r(g.parts == 1 ? cdiv(nbr, g.nb) : (unsigned)(nbr * g.parts), n);
+                k_degrade4r<<<grid_r, 256, smem_r, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, g);
+                }
+            } else
+            if (tma) k_degrade4p<true><<<grid, 256, smem, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+            else k_degrade4p<false><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+        } else
         if (luma_dp4a && tma) k_degrade4<true, true><<<grid, 256, smem, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
         else if (luma_dp4a) k_degrade4<true, false><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
         else if (tma) k_degrade4<false, true><<<grid, 256, smem, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);

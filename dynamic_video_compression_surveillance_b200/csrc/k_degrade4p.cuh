@@ -1,0 +1,673 @@
+// K4, packed-pair version (the default for block_size 4): same contract as k_degrade4 in k_degrade.cuh
+// (frame_differencing.py:110-111,115-130), restructured around two facts measured in profiles/r1f:
+// the kernel was issue-bound (70 % issue-slot utilisation, 860 warp instructions per 4x4 block), not
+// HBM-bound.
+//
+//  * Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2, PTX add/mul/fma.rn.f32x2) processes two IEEE
+//    binary32 lanes per instruction with the same per-lane rounding as the scalar instructions.  A thread
+//    owns two adjacent 4x4 blocks, so block A rides in the low lane and block B in the high lane of every
+//    DCT / quantiser instruction: half the floating-point issue slots, bit-identical results.
+//  * round(d / q): the IEEE quotient fl(d / q) is formed without a division by one Markstein correction step,
+//        y0 = fl(d * r),  e = fma(-q, y0, d) (exact),  y = fma(e, r, y0),   r = fl(1 / q) (host, correctly rounded)
+//    which is the correctly rounded quotient (Markstein 1990, Thm. 8; re-checked for this value range against the
+//    hardware division on 3e9 samples, tests/test_oracle_vs_cv2.py::test_markstein_quotient for a sample).  Then
+//    rint() is the usual magic-number add/sub.  No tie detection, no slow path, no second evaluation: the
+//    quantiser is six packed instructions per coefficient pair.
+//  * luma: Y << 14 = 1868 B + 9617 G + 4899 R + 8192 as two IDP.2A (u16 x u8 pairs) per pixel instead of
+//    three-to-four IDP.4A + shift-add, and (s >> 14) | 0x4B000000 (the 2^23 + Y float pattern) is one funnel
+//    shift.
+#pragma once
+#include "k_degrade.cuh"
+
+namespace dvc {
+
+// ---- packed pair of binary32 lanes in a 64-bit register pair ----
+struct P2 { unsigned long long v; };
+DEVI P2 p2(float lo, float hi) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+DEVI void unp2(P2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+
+DEVI P2 add(P2 a, P2 b) { P2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+DEVI P2 sub(P2 a, P2 b) { P2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+DEVI P2 mul(P2 a, P2 b) { P2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+DEVI P2 fma_(P2 a, P2 b, P2 c) { P2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+DEVI float add(float a, float b) { return __fadd_rn(a, b); }
+DEVI float sub(float a, float b) { return __fsub_rn(a, b); }
+DEVI float mul(float a, float b) { return __fmul_rn(a, b); }
+DEVI float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+template <typename T> DEVI T splat(float x);
+template <> DEVI float splat<float>(float x) { return x; }
+template <> DEVI P2 splat<P2>(float x) { return p2(x, x); }
+
+struct QuantP {
+    float rcp[3];    // fl(1 / (q * 2^NE)),  NE = number of even indices among (row, col) = pending scale 2^-NE
+    float nqs[3];    // -(q * 2^NE)
+    float o[3];      // q * 2^-NE: output scale with the inverse butterflies' x0.5 pre-applied
+};
+
+// forward / inverse 4-point DCT with the power-of-two scalings folded out (see dct4_fwd_ns / dct4_inv_ps)
+template <typename T>
+DEVI void dct4_fwd_t(T& x0, T& x1, T& x2, T& x3) {
+    const T c1 = splat<T>(DVC_C1), c3 = splat<T>(DVC_C3), nc1 = splat<T>(-DVC_C1);
+    const T s0 = add(x0, x3), s1 = add(x1, x2), d0 = sub(x0, x3), d1 = sub(x1, x2);
+    x0 = add(s0, s1);
+    x2 = sub(s0, s1);
+    x1 = fma_(c3, d1, mul(c1, d0));
+    x3 = fma_(c3, d0, mul(nc1, d1));          // -(c1 * d1) == (-c1) * d1 exactly
+}
+template <typename T>
+DEVI void dct4_inv_t(T& x0, T& x1, T& x2, T& x3) {
+    const T c1 = splat<T>(DVC_C1), c3 = splat<T>(DVC_C3), nc1 = splat<T>(-DVC_C1);
+    const T e0 = add(x0, x2), e1 = sub(x0, x2);
+    const T o0 = fma_(c3, x3, mul(c1, x1));
+    const T o1 = fma_(c3, x1, mul(nc1, x3));
+    x0 = add(e0, o0);
+    x3 = sub(e0, o0);
+    x1 = add(e1, o1);
+    x2 = sub(e1, o1);
+}
+
+// rint(fl(d_true / q)) * q, scalings folded: d arrives as d_true * 2^NE, leaves as value * 2^-NE
+template <int NE, typename T>
+DEVI T quantise_t(T d, const QuantP& qp) {
+    const T r = splat<T>(qp.rcp[NE]), nq = splat<T>(qp.nqs[NE]), magic = splat<T>(12582912.0f);   // 1.5 * 2^23
+    const T y0 = mul(d, r);
+    const T e = fma_(nq, y0, d);
+    const T y = fma_(e, r, y0);                                // == fl(d / (q 2^NE)), correctly rounded
+    const T n = sub(add(y, magic), magic);                     // round half to even
+    return mul(n, splat<T>(qp.o[NE]));
+}
+
+template <typename T>
+DEVI void degrade_block_t(T (&v)[4][4], const QuantP& qp) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dct4_fwd_t(v[r][0], v[r][1], v[r][2], v[r][3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dct4_fwd_t(v[0][c], v[1][c], v[2][c], v[3][c]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if ((r & 1) == 0) {
+            v[r][0] = quantise_t<2>(v[r][0], qp); v[r][1] = quantise_t<1>(v[r][1], qp);
+            v[r][2] = quantise_t<2>(v[r][2], qp); v[r][3] = quantise_t<1>(v[r][3], qp);
+        } else {
+            v[r][0] = quantise_t<1>(v[r][0], qp); v[r][1] = quantise_t<0>(v[r][1], qp);
+            v[r][2] = quantise_t<1>(v[r][2], qp); v[r][3] = quantise_t<0>(v[r][3], qp);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dct4_inv_t(v[r][0], v[r][1], v[r][2], v[r][3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dct4_inv_t(v[0][c], v[1][c], v[2][c], v[3][c]);
+}
+
+// float bit patterns of 2^23 + Y for the four pixels in three packed BGR words.
+// dp2a.lo: a.lo16 * b.byte0 + a.hi16 * b.byte1; dp2a.hi: a.lo16 * b.byte2 + a.hi16 * b.byte3.
+DEVI void luma4_bits(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t (&y)[4]) {
+    const uint32_t cBG = 1868u | (9617u << 16), cR_ = 4899u, c_B = 1868u << 16, cGR = 9617u | (4899u << 16);
+    const uint32_t s0 = __dp2a_hi(cR_, w0, __dp2a_lo(cBG, w0, 8192u));     // B G R .
+    const uint32_t s1 = __dp2a_lo(cGR, w1, __dp2a_hi(c_B, w0, 8192u));     // . . . B | G R
+    const uint32_t s2 = __dp2a_lo(cR_, w2, __dp2a_hi(cBG, w1, 8192u));     // . . B G | R
+    const uint32_t s3 = __dp2a_hi(cGR, w2, __dp2a_lo(c_B, w2, 8192u));     // . B G R
+    // (s >> 14) | 0x4B000000 in one funnel shift: 0x12C0 << 18 == 0x4B000000
+    y[0] = __funnelshift_r(s0, 0x12C0u, 14); y[1] = __funnelshift_r(s1, 0x12C0u, 14);
+    y[2] = __funnelshift_r(s2, 0x12C0u, 14); y[3] = __funnelshift_r(s3, 0x12C0u, 14);
+}
+
+// four grey output bytes -> the three BGR words of four grey pixels
+DEVI void grey4_words(uint32_t y0, uint32_t y1, uint32_t y2, uint32_t y3, uint32_t& a, uint32_t& b, uint32_t& c) {
+    a = __byte_perm(y0, y1, 0x4000);          // y0 y0 y0 y1
+    b = __byte_perm(y1, y2, 0x4400);          // y1 y1 y2 y2
+    c = __byte_perm(y2, y3, 0x4440);          // y2 y3 y3 y3
+}
+
+// The two 4x4 blocks of one thread, in place in the packed BGR words w[row][6] (block A = words 0..2, B = 3..5).
+DEVI void k4_blocks(uint32_t (&w)[4][6], bool st_a, bool st_b, const QuantP& qp) {
+    if (st_a && st_b) {
+        // ---- both blocks static (97 % of threads on surveillance content): packed lanes A | B ----
+        P2 v[4][4];
+        const P2 bias = p2(8388736.0f, 8388736.0f);                  // 2^23 + 128
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t ya[4], yb[4];
+            luma4_bits(w[r][0], w[r][1], w[r][2], ya);
+            luma4_bits(w[r][3], w[r][4], w[r][5], yb);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[r][c] = sub(p2(__uint_as_float(ya[c]), __uint_as_float(yb[c])), bias);
+        }
+        degrade_block_t(v, qp);
+        const P2 p128 = p2(128.0f, 128.0f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t ya[4], yb[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float a, b;
+                unp2(add(v[r][c], p128), a, b);
+                asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(ya[c]) : "f"(a));
+                asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(yb[c]) : "f"(b));
+            }
+            grey4_words(ya[0], ya[1], ya[2], ya[3], w[r][0], w[r][1], w[r][2]);
+            grey4_words(yb[0], yb[1], yb[2], yb[3], w[r][3], w[r][4], w[r][5]);
+        }
+    } else {
+        // ---- a block with motion in this thread: per block, scalar lanes ----
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            if (b == 0 ? st_a : st_b) {
+                float v[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    uint32_t y[4];
+                    luma4_bits(w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2], y);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) v[r][c] = __fsub_rn(__uint_as_float(y[c]), 8388736.0f);
+                }
+                degrade_block_t(v, qp);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    grey4_words(out_byte_bits(v[r][0]), out_byte_bits(v[r][1]), out_byte_bits(v[r][2]),
+                                out_byte_bits(v[r][3]), w[r][3 * b], w[r][3 * b + 1], w[r][3 * b + 2]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    uint32_t o[3] = {0, 0, 0};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const int i = 12 * b + 3 * p;
+                        int bb = byte_at(w[r], i), gg = byte_at(w[r], i + 1), rr = byte_at(w[r], i + 2);
+                        ycc_roundtrip(bb, gg, rr);
+                        const int j = 3 * p;
+                        o[j >> 2] |= (uint32_t)bb << ((j & 3) * 8);
+                        o[(j + 1) >> 2] |= (uint32_t)gg << (((j + 1) & 3) * 8);
+                        o[(j + 2) >> 2] |= (uint32_t)rr << (((j + 2) & 3) * 8);
+                    }
+                    w[r][3 * b] = o[0]; w[r][3 * b + 1] = o[1]; w[r][3 * b + 2] = o[2];
+                }
+            }
+        }
+    }
+}
+
+template <bool TMA_STORE>
+__global__ void __launch_bounds__(256, 4)
+k_degrade4p(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127,
+            const uint32_t* __restrict__ nonzero, uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay,
+            int H, int W, int wpr, QuantP qp, Counters* __restrict__ counters) {
+    extern __shared__ __align__(128) uint8_t k4_stage[];
+    const int gpr = W >> 3, nbr = H >> 2;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    // CTA staging area as a shared-window address: row r of output o sits at (o * 4 + r) * K4_ROW_BYTES, thread t at 24 t
+    const uint32_t wst = (uint32_t)__cvta_generic_to_shared(k4_stage) + threadIdx.x * 24;
+    unsigned n_motion = 0, n_static = 0;
+    if (gid < gpr * nbr) {
+        const int br = gid / gpr, gx = gid - br * gpr;
+        const size_t frame_off = (size_t)blockIdx.y * H * W * 3;
+        const size_t plane_off = (size_t)blockIdx.y * H * wpr;
+        const size_t base = frame_off + ((size_t)(br * 4) * W + (size_t)gx * 8) * 3;
+        const size_t pitch = (size_t)W * 3;
+        uint32_t w[4][6];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const uint2 t = __ldcs(reinterpret_cast<const uint2*>(frames + base + r * pitch + 8 * i));
+                w[r][2 * i] = t.x; w[r][2 * i + 1] = t.y;
+            }
+        uint32_t hi[4], nz = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const size_t wo = plane_off + (size_t)(br * 4 + r) * wpr;
+            hi[r] = reinterpret_cast<const uint8_t*>(over127 + wo)[gx];
+            nz |= reinterpret_cast<const uint8_t*>(nonzero + wo)[gx];
+        }
+        // ---- overlay: paint (B,G,R) = (0,0,255) where acc > 127 ----
+        if (overlay) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                uint32_t o[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) o[i] = w[r][i];
+                if (hi[r] != 0u) {
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const uint32_t m = hi[r] >> (4 * b);
+                        if (m & 1u) { o[3 * b] = (o[3 * b] & 0xff000000u) | 0x00ff0000u; }
+                        if (m & 2u) { o[3 * b] &= 0x00ffffffu; o[3 * b + 1] = (o[3 * b + 1] & 0xffff0000u) | 0x0000ff00u; }
+                        if (m & 4u) { o[3 * b + 1] &= 0x0000ffffu; o[3 * b + 2] = (o[3 * b + 2] & 0xffffff00u) | 0x000000ffu; }
+                        if (m & 8u) { o[3 * b + 2] = (o[3 * b + 2] & 0x000000ffu) | 0xff000000u; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (TMA_STORE) sts64(wst + r * K4_ROW_BYTES + 8 * i, o[2 * i], o[2 * i + 1]);
+                    else __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(o[2 * i], o[2 * i + 1]));
+                }
+            }
+        }
+        n_motion = __popc(hi[0]) + __popc(hi[1]) + __popc(hi[2]) + __popc(hi[3]);
+        const bool st_a = (nz & 0xfu) == 0u, st_b = (nz >> 4) == 0u;
+        n_static = (st_a ? 1u : 0u) + (st_b ? 1u : 0u);
+        if (compressed) {
+            k4_blocks(w, st_a, st_b, qp);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (TMA_STORE) sts64(wst + (4 + r) * K4_ROW_BYTES + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
+                    else __stcs(reinterpret_cast<uint2*>(compressed + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
+                }
+        }
+    }
+    if (TMA_STORE) {
+        // generic-proxy writes to shared memory -> visible to the async proxy, then one thread issues the bulk stores:
+        // the CTA's 256 groups are contiguous in a row (6 KB per row and output); a CTA that crosses the end of a block
+        // row issues two parts.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        const int g0 = blockIdx.x * blockDim.x;                 // first group of this CTA
+        if (threadIdx.x == 0) {
+            const int total = gpr * nbr;
+            const size_t pitch = (size_t)W * 3;
+            const size_t fo = (size_t)blockIdx.y * H * W * 3;
+            const uint32_t sbase = wst;                          // thread 0: start of the staging area
+            const int g_end = min(g0 + (int)blockDim.x, total);
+            for (int g = g0; g < g_end;) {                       // one part per block row the CTA touches
+                const int brp = g / gpr, gxp = g - brp * gpr;
+                const int np = min(gpr - gxp, g_end - g);
+                const size_t seg = fo + ((size_t)(brp * 4) * W + (size_t)gxp * 8) * 3;
+                const uint32_t soff = (uint32_t)(g - g0) * 24u;
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {
+                    uint8_t* dst = o == 0 ? overlay : compressed;
+                    if (!dst) continue;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        bulk_store(dst + seg + r * pitch, sbase + (o * 4 + r) * K4_ROW_BYTES + soff, (uint32_t)np * 24u);
+                }
+                g += np;
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
+        }
+    }
+    // ---- statistics: warp shuffle reduction, one atomic pair per warp ----
+    if (counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_motion += __shfl_xor_sync(0xffffffffu, n_motion, o);
+            n_static += __shfl_xor_sync(0xffffffffu, n_static, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (n_motion) atomicAdd(&counters->motion_pixels, (unsigned long long)n_motion);
+            if (n_static) atomicAdd(&counters->static_blocks, (unsigned long long)n_static);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Row-span version (default when the geometry allows): a CTA owns whole 4-pixel-high block rows (or an exact
+// part of one for W > 2048), i.e. one contiguous span of the frame.  HBM only ever sees large bulk operations:
+//   * the span (<= 24 KB) and its two mask-plane row groups arrive by cp.async.bulk (TMA) on one mbarrier;
+//   * threads read their 8 px x 4 rows with conflict-free LDS.64 (lane stride 24 B);
+//   * the overlay is the input span painted in place (only where acc > 127), the compressed span is written to
+//     a second buffer; both leave by cp.async.bulk stores issued by one thread.
+// Shared memory: 2 spans + 2 mask groups (~53 KB) -> 4 CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+struct K4Geom {
+    int gp;          // pixel groups (8 px) per CTA row piece
+    int parts;       // CTAs per block row (1 = whole block rows per CTA)
+    int nb;          // block rows per CTA when parts == 1
+    int sp;          // shared-memory row pitch in bytes (= W * 3 when parts == 1, gp * 24 otherwise)
+    int span_bytes;  // bytes of one span buffer
+    int mask_bytes;  // bytes of one mask-plane row group buffer (4 * nb rows of wpr words)
+    int debug;       // measurement switches (DVC_K4_DEBUG): 1 = no stores, 2 = no block arithmetic; 0 in production
+};
+
+DEVI void lds64(uint32_t saddr, uint32_t& a, uint32_t& b) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(saddr));
+}
+DEVI uint32_t lds_u8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+DEVI void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_degrade4r(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127,
+            const uint32_t* __restrict__ nonzero, uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay,
+            int H, int W, int wpr, QuantP qp, Counters* __restrict__ counters, K4Geom g) {
+    extern __shared__ __align__(128) uint8_t k4_smem[];
+    const uint32_t sX = (uint32_t)__cvta_generic_to_shared(k4_smem);       // input span, becomes the overlay span
+    const uint32_t sY = sX + g.span_bytes;                                  // compressed span
+    const uint32_t sMh = sY + g.span_bytes;                                 // over127 rows
+    const uint32_t sMn = sMh + g.mask_bytes;                                // nonzero rows
+    const uint32_t bar = sMn + g.mask_bytes;
+    const int gpr = W >> 3, nbr = H >> 2;
+    const int tid = threadIdx.x;
+    const size_t pitch = (size_t)W * 3;
+    const size_t frame_off = (size_t)blockIdx.y * H * W * 3;
+    const size_t plane_off = (size_t)blockIdx.y * H * wpr;
+    // CTA geometry
+    int br0, nb, g0, ng;
+    if (g.parts == 1) { br0 = blockIdx.x * g.nb; nb = min(g.nb, nbr - br0); g0 = 0; ng = gpr; }
+    else { br0 = blockIdx.x / g.parts; nb = 1; g0 = (blockIdx.x - br0 * g.parts) * g.gp; ng = min(g.gp, gpr - g0); }
+    const size_t span_off = frame_off + (size_t)(br0 * 4) * pitch + (size_t)g0 * 24;
+    const uint32_t mrow_bytes = (uint32_t)wpr * 4u;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t mbytes = (uint32_t)(4 * nb) * mrow_bytes;
+        const uint32_t fbytes = g.parts == 1 ? (uint32_t)(4 * nb) * (uint32_t)pitch : 4u * (uint32_t)ng * 24u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(fbytes + 2u * mbytes) : "memory");
+        if (g.parts == 1) bulk_load(sX, frames + span_off, fbytes, bar);
+        else
+            for (int r = 0; r < 4; ++r) bulk_load(sX + r * g.sp, frames + span_off + r * pitch, (uint32_t)ng * 24u, bar);
+        bulk_load(sMh, over127 + plane_off + (size_t)(br0 * 4) * wpr, mbytes, bar);
+        bulk_load(sMn, nonzero + plane_off + (size_t)(br0 * 4) * wpr, mbytes, bar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar) : "memory");
+        }
+    }
+    __syncthreads();          // the waiter's observation of the completed phase orders the async writes before everybody's reads
+
+    unsigned n_motion = 0, n_static = 0;
+    const int brl = tid / ng, gxl = tid - brl * ng;
+    if (brl < nb) {
+        const uint32_t toff = (uint32_t)(brl * 4) * (uint32_t)g.sp + (uint32_t)gxl * 24u;
+        const uint32_t moff = (uint32_t)(brl * 4) * mrow_bytes + (uint32_t)(g0 + gxl);
+        uint32_t w[4][6];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) lds64(sX + toff + r * g.sp + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
+        uint32_t hi[4], nz = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            hi[r] = lds_u8(sMh + moff + r * mrow_bytes);
+            nz |= lds_u8(sMn + moff + r * mrow_bytes);
+        }
+        // ---- overlay: paint (B,G,R) = (0,0,255) where acc > 127, in place in the input span ----
+        if (overlay) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (hi[r] == 0u) continue;
+                uint32_t o[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) o[i] = w[r][i];
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const uint32_t m = hi[r] >> (4 * b);
+                    if (m & 1u) { o[3 * b] = (o[3 * b] & 0xff000000u) | 0x00ff0000u; }
+                    if (m & 2u) { o[3 * b] &= 0x00ffffffu; o[3 * b + 1] = (o[3 * b + 1] & 0xffff0000u) | 0x0000ff00u; }
+                    if (m & 4u) { o[3 * b + 1] &= 0x0000ffffu; o[3 * b + 2] = (o[3 * b + 2] & 0xffffff00u) | 0x000000ffu; }
+                    if (m & 8u) { o[3 * b + 2] = (o[3 * b + 2] & 0x000000ffu) | 0xff000000u; }
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sts64(sX + toff + r * g.sp + 8 * i, o[2 * i], o[2 * i + 1]);
+            }
+        }
+        n_motion = __popc(hi[0]) + __popc(hi[1]) + __popc(hi[2]) + __popc(hi[3]);
+        const bool st_a = (nz & 0xfu) == 0u, st_b = (nz >> 4) == 0u;
+        n_static = (st_a ? 1u : 0u) + (st_b ? 1u : 0u);
+        if (compressed) {
+            if (!(g.debug & 2)) k4_blocks(w, st_a, st_b, qp);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sts64(sY + toff + r * g.sp + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0 && !(g.debug & 1)) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            uint8_t* dst = o == 0 ? overlay : compressed;
+            if (!dst) continue;
+            const uint32_t src = o == 0 ? sX : sY;
+            if (g.parts == 1) bulk_store(dst + span_off, src, (uint32_t)(4 * nb) * (uint32_t)pitch);
+            else
+                for (int r = 0; r < 4; ++r) bulk_store(dst + span_off + r * pitch, src + r * g.sp, (uint32_t)ng * 24u);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
+    }
+    if (counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_motion += __shfl_xor_sync(0xffffffffu, n_motion, o);
+            n_static += __shfl_xor_sync(0xffffffffu, n_static, o);
+        }
+        if ((tid & 31) == 0) {
+            if (n_motion) atomicAdd(&counters->motion_pixels, (unsigned long long)n_motion);
+            if (n_static) atomicAdd(&counters->static_blocks, (unsigned long long)n_static);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised version (the default): one CTA per SM walks tiles t = blockIdx.x, blockIdx.x +
+// gridDim.x, ... over all frames of the launch.  A tile is the K4Geom span (whole block rows, or part of one for
+// W > 2048).
+//   warp 0 (one elected lane)  producer: cp.async.bulk loads of span + mask rows into a ring of `stages` input
+//                              buffers (mbarrier expect_tx) and the cp.async.bulk stores of finished tiles;
+//   G consumer groups of 256   wait for "full", LDS.64 their 8 px x 4 rows, paint the overlay in place in the
+//   threads                    input buffer, run k4_blocks, STS.64 the compressed pixels into the group's
+//                              output buffer, fence.proxy.async, arrive on "done".
+// Shared memory: `stages` x (span + 2 mask row groups) + G x span (6 x 25 KB + 2 x 23 KB at 1080p).
+// HBM sees a steady stream of large bulk operations whose depth is `stages`, independent of CTA launch / drain
+// behaviour; consumers never touch global memory (statistics: one atomic pair per warp per launch).
+// ------------------------------------------------------------------------------------------------
+struct K4SGeom {
+    K4Geom g;
+    int stages;            // input ring depth (multiple of the number of consumer groups)
+    int tiles_per_frame;
+    int n_tiles;           // tiles_per_frame * frames
+    int stage_bytes;       // span_bytes + 2 * mask_bytes, rounded up to 128
+    int ybuf_bytes;        // span_bytes rounded up to 128
+    int row_copies;        // 1: always move spans row by row (5.7 KB pieces) instead of one bulk operation
+};
+
+DEVI void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+DEVI void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+// tile walker: (frame, tile-in-frame) advanced by the grid stride without divisions
+struct K4Walk {
+    int f, l, df, dl, tpf;
+    DEVI void init(int t0, int stride, int tiles_per_frame) {
+        tpf = tiles_per_frame; f = t0 / tpf; l = t0 - f * tpf; df = stride / tpf; dl = stride - df * tpf;
+    }
+    DEVI void next() { f += df; l += dl; if (l >= tpf) { l -= tpf; ++f; } }
+};
+struct K4Tile { size_t span_off, mask_off; int nbv, g0, ng; };
+DEVI K4Tile k4_tile(const K4Walk& wk, const K4Geom& g, int H, int W, int wpr) {
+    const int gpr = W >> 3, nbr = H >> 2;
+    K4Tile r;
+    int br0;
+    if (g.parts == 1) { br0 = wk.l * g.nb; r.nbv = min(g.nb, nbr - br0); r.g0 = 0; r.ng = gpr; }
+    else { br0 = wk.l / g.parts; r.nbv = 1; r.g0 = (wk.l - br0 * g.parts) * g.gp; r.ng = min(g.gp, gpr - r.g0); }
+    r.span_off = ((size_t)wk.f * H + (size_t)(br0 * 4)) * W * 3 + (size_t)r.g0 * 24;
+    r.mask_off = ((size_t)wk.f * H + (size_t)(br0 * 4)) * wpr;
+    return r;
+}
+
+template <int G, int MINB>
+__global__ void __launch_bounds__(32 + G * 256, MINB)
+k_degrade4s(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127,
+            const uint32_t* __restrict__ nonzero, uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay,
+            int H, int W, int wpr, QuantP qp, Counters* __restrict__ counters, K4SGeom sg) {
+    extern __shared__ __align__(128) uint8_t k4_smem[];
+    const K4Geom& g = sg.g;
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(k4_smem);
+    const int S = sg.stages;
+    const uint32_t ybufs = s0 + (uint32_t)S * (uint32_t)sg.stage_bytes;     // G output buffers
+    const uint32_t bars = ybufs + (uint32_t)G * (uint32_t)sg.ybuf_bytes;    // full[S], done[S], yfree[G]
+    const uint32_t desc = (bars + 8u * (uint32_t)(2 * S + G) + 15u) & ~15u;    // per stage: {nbv, g0, ng, -}
+    const int tid = threadIdx.x;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int nj = first < sg.n_tiles ? (sg.n_tiles - first + stride - 1) / stride : 0;
+    const uint32_t pitch = (uint32_t)W * 3u;
+    const uint32_t mrow_bytes = (uint32_t)wpr * 4u;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * (S + s)), "r"(256));
+        }
+        for (int q = 0; q < G; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * (2 * S + q)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid < 32) {
+        // ------------------------------ producer ------------------------------
+        if (tid == 0) {
+            const bool whole = g.parts == 1 && !sg.row_copies;
+            K4Walk wl, ws;                       // load walker runs `S` tiles ahead of the store walker
+            wl.init(first, stride, sg.tiles_per_frame);
+            ws = wl;
+            auto issue_load = [&](int j) {
+                const int s = j % S;
+                const K4Tile t = k4_tile(wl, g, H, W, wpr);
+                wl.next();
+                const uint32_t sX = s0 + (uint32_t)s * (uint32_t)sg.stage_bytes;
+                const uint32_t sMh = sX + g.span_bytes, sMn = sMh + g.mask_bytes;
+                const uint32_t full = bars + 8u * s;
+                const uint32_t mbytes = (uint32_t)(4 * t.nbv) * mrow_bytes;
+                const uint32_t rows = g.parts == 1 ? (uint32_t)(4 * t.nbv) : 4u;
+                const uint32_t rbytes = g.parts == 1 ? pitch : (uint32_t)t.ng * 24u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc + 16u * s), "r"(t.nbv), "r"(t.g0), "r"(t.ng), "r"(0) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(rows * rbytes + 2u * mbytes) : "memory");
+                if (whole) bulk_load(sX, frames + t.span_off, rows * rbytes, full);
+                else
+                    for (uint32_t r = 0; r < rows; ++r) bulk_load(sX + r * g.sp, frames + t.span_off + (size_t)r * pitch, rbytes, full);
+                bulk_load(sMh, over127 + t.mask_off, mbytes, full);
+                bulk_load(sMn, nonzero + t.mask_off, mbytes, full);
+            };
+            for (int j = 0; j < min(S, nj); ++j) issue_load(j);
+            for (int j = 0; j < nj; ++j) {
+                const int s = j % S, grp = j % G;
+                mbar_wait(bars + 8u * (S + s), (uint32_t)(j / S) & 1u);           // consumers are done with tile j
+                if (!(g.debug & 1)) {
+                    const K4Tile t = k4_tile(ws, g, H, W, wpr);
+                    const uint32_t sX = s0 + (uint32_t)s * (uint32_t)sg.stage_bytes;
+                    const uint32_t sY = ybufs + (uint32_t)grp * (uint32_t)sg.ybuf_bytes;
+                    const uint32_t rows = g.parts == 1 ? (uint32_t)(4 * t.nbv) : 4u;
+                    const uint32_t rbytes = g.parts == 1 ? pitch : (uint32_t)t.ng * 24u;
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        uint8_t* dst = o == 0 ? overlay : compressed;
+                        if (!dst) continue;
+                        const uint32_t src = o == 0 ? sX : sY;
+                        if (whole) bulk_store(dst + t.span_off, src, rows * rbytes);
+                        else
+                            for (uint32_t r = 0; r < rows; ++r) bulk_store(dst + t.span_off + (size_t)r * pitch, src + r * g.sp, rbytes);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // input stage and output buffer are free again
+                }
+                ws.next();
+                mbar_arrive(bars + 8u * (2 * S + grp));                                  // yfree[grp]
+                if (j + S < nj) issue_load(j + S);
+            }
+        }
+        return;
+    }
+
+    // ------------------------------ consumers ------------------------------
+    const int ctid = tid - 32, grp = ctid >> 8, t = ctid & 255;
+    const int gpr = W >> 3;
+    int brl = 0, gxl = t;
+    if (g.parts == 1) { brl = t / gpr; gxl = t - brl * gpr; }
+    const uint32_t toff = (uint32_t)(brl * 4) * (uint32_t)g.sp + (uint32_t)gxl * 24u;
+    const uint32_t sY = ybufs + (uint32_t)grp * (uint32_t)sg.ybuf_bytes;
+    const uint32_t yfree = bars + 8u * (2 * S + grp);
+    unsigned n_motion = 0, n_static = 0;
+    int n_mine = 0;
+    for (int j = grp; j < nj; j += G, ++n_mine) {
+        const int s = j % S;
+        const uint32_t sX = s0 + (uint32_t)s * (uint32_t)sg.stage_bytes;
+        const uint32_t sMh = sX + g.span_bytes, sMn = sMh + g.mask_bytes;
+        mbar_wait(bars + 8u * s, (uint32_t)(j / S) & 1u);
+        uint32_t nbv, tg0, tng, unused;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(nbv), "=r"(tg0), "=r"(tng), "=r"(unused) : "r"(desc + 16u * s));
+        const bool active = brl < (int)nbv && gxl < (int)tng;
+        uint32_t w[4][6];
+        bool st_a = false, st_b = false;
+        if (active) {
+            const uint32_t moff = (uint32_t)(brl * 4) * mrow_bytes + tg0 + (uint32_t)gxl;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) lds64(sX + toff + r * g.sp + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
+            uint32_t hi[4], nz = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                hi[r] = lds_u8(sMh + moff + r * mrow_bytes);
+                nz |= lds_u8(sMn + moff + r * mrow_bytes);
+            }
+            if (overlay) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (hi[r] == 0u) continue;
+                    uint32_t o[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) o[i] = w[r][i];
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const uint32_t m = hi[r] >> (4 * b);
+                        if (m & 1u) { o[3 * b] = (o[3 * b] & 0xff000000u) | 0x00ff0000u; }
+                        if (m & 2u) { o[3 * b] &= 0x00ffffffu; o[3 * b + 1] = (o[3 * b + 1] & 0xffff0000u) | 0x0000ff00u; }
+                        if (m & 4u) { o[3 * b + 1] &= 0x0000ffffu; o[3 * b + 2] = (o[3 * b + 2] & 0xffffff00u) | 0x000000ffu; }
+                        if (m & 8u) { o[3 * b + 2] = (o[3 * b + 2] & 0x000000ffu) | 0xff000000u; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) sts64(sX + toff + r * g.sp + 8 * i, o[2 * i], o[2 * i + 1]);
+                }
+            }
+            n_motion += __popc(hi[0]) + __popc(hi[1]) + __popc(hi[2]) + __popc(hi[3]);
+            st_a = (nz & 0xfu) == 0u; st_b = (nz >> 4) == 0u;
+            n_static += (st_a ? 1u : 0u) + (st_b ? 1u : 0u);
+            if (compressed && !(g.debug & 2)) k4_blocks(w, st_a, st_b, qp);
+        }
+        if (compressed) {
+            if (n_mine > 0) mbar_wait(yfree, (uint32_t)(n_mine - 1) & 1u);      // the previous tile's store has read the buffer
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) sts64(sY + toff + r * g.sp + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bars + 8u * (S + s));
+    }
+    if (counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_motion += __shfl_xor_sync(0xffffffffu, n_motion, o);
+            n_static += __shfl_xor_sync(0xffffffffu, n_static, o);
+        }
+        if ((tid & 31) == 0) {
+            if (n_motion) atomicAdd(&counters->motion_pixels, (unsigned long long)n_motion);
+            if (n_static) atomicAdd(&counters->static_blocks, (unsigned long long)n_static);
+        }
+    }
+}
+
+}  // namespace dvc

@@ -47,8 +47,8 @@ def main():
                 i = hdr.index(m)
                 print(f"  {m:75s} {r[i]:>18s} {units[i]}")
     for name in sorted(seen):
-        src = run(["-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + name.split("<")[0].split("::")[-1], "--launch-count", "1"]) if False else \
-            run(["-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + name.split("<")[0].split("::")[-1]])
+        src = run(["-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + name.split("<")[0].split("::")[-1].split()[-1], "--launch-count", "1"]) if False else \
+            run(["-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + name.split("<")[0].split("::")[-1].split()[-1]])
         lines = [l for l in src.splitlines() if l and not l.startswith("==")]
         recs = list(csv.reader(io.StringIO("\n".join(lines))))
         try:
