@@ -297,7 +297,7 @@ def run_b200(args, rank, world, local_rank):
     k4_bytes = K4_ALG_BYTES_PER_PX * px * frames_per_launch
     k4_gbs = k4_bytes / (k4_ms / max(1, k4_launches) * 1e-3) / 1e9 if k4_ms > 0 else 0.0
     kernel_ms = {k: v[0] for k, v in prof.items() if v[1]}
-    roofline = {"bound": "hbm", "kernel": "k_degrade4 (K4: overlay + YCrCb + 4x4 DCT degrade + statistics)",
+    roofline = {"bound": "hbm", "kernel": "k_degrade4s (K4, persistent TMA ring: overlay + YCrCb + 4x4 DCT degrade + statistics)",
                 "achieved": k4_gbs, "peak": peak, "unit": "GB/s", "frac": k4_gbs / peak, "peak_source": peak_src,
                 "traffic": None, "alg_bytes_per_px": K4_ALG_BYTES_PER_PX, "frames_per_launch": frames_per_launch,
                 "avg_launch_ms": k4_ms / max(1, k4_launches), "kernel_share_of_step": k4_ms / ms_serial if ms_serial else None,

@@ -859,7 +859,10 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
     CU(cudaSetDevice(h->cfg.device));
     int rc = alloc_staging(h);
     if (rc) return rc;
-    const int Tc = h->cfg.max_batch;
+    // chunk size of the copy pipeline: small enough that the first upload and the last download (the only copies
+    // nothing overlaps) are short against the PCIe-bound steady state, large enough for full-size kernels
+    static const int host_chunk = [] { const char* e = getenv("DVC_HOST_CHUNK"); return e ? std::max(1, atoi(e)) : 8; }();
+    const int Tc = std::min(h->cfg.max_batch, host_chunk);
     const int64_t nchunks = (n_frames + Tc - 1) / Tc;
     CU(cudaDeviceSynchronize());          // join whatever dvc_process_batch left in flight
     for (int64_t c = 0; c < nchunks; ++c) {
