@@ -66,6 +66,7 @@ SYMBOLS = {
     "dvc_temporal_ema_u8": (C.c_int, [_P, _P, _P, _I, _I, _I, _D, _P]),
     "dvc_morph_u8": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "dvc_contour_filter_u8": (C.c_int, [_P, _P, _I, _I, _I, _D, _P]),
+    "dvc_mask_rectangles_u8": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "dvc_degrade_blend_u8": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
 }
 

@@ -1077,6 +1077,41 @@ extern "C" int dvc_contour_filter_u8(const uint8_t* src, uint8_t* dst, int32_t n
     return unpack_from_bits((const uint32_t*)b.p, dst, n, H, W, st);
 }
 
+extern "C" int dvc_mask_rectangles_u8(const uint8_t* src, uint8_t* dst, int32_t n, int32_t H, int32_t W, void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, H, W, "dvc_mask_rectangles_u8");
+    if (rc || n == 0) return rc;
+    if (!src || !dst) return set_err(nullptr, DVC_ERR_INVALID, "dvc_mask_rectangles_u8: null pointer");
+    if (W > 32767 || H > 32767) return set_err(nullptr, DVC_ERR_UNSUPPORTED, "dvc_mask_rectangles_u8: image larger than 32767");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpr = words_per_row(W);
+    const size_t pw = (size_t)H * wpr;
+    const int fr = std::min(n, 4);
+    const size_t d = ccl_dense_ints(H, W) * sizeof(int) * fr, o = ccl_overflow_ints(H, W) * sizeof(int) * fr;
+    ScopedAsyncBuf a(st), b(st), p0(st), pov(st), bd(st), bo(st);
+    CU(a.alloc(pw * 4 * n));
+    CU(b.alloc(pw * 4 * n));
+    CU(p0.alloc(d)); CU(pov.alloc(o)); CU(bd.alloc(3 * d)); CU(bo.alloc(3 * o));
+    rc = pack_to_bits(src, (uint32_t*)a.p, n, H, W, st);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(b.p, 0, pw * 4 * n, st));
+    BBoxArrays bb;
+    for (int k = 0; k < 3; ++k) { bb.d[k] = (int*)((char*)bd.p + k * d); bb.ov[k] = (int*)((char*)bo.p + k * o); }
+    for (int i0 = 0; i0 < n; i0 += fr) {
+        const int m = std::min(fr, n - i0);
+        dim3 grid(cdiv(pw, 256), m), grow((H + 7) / 8, m);
+        const uint32_t* r = (const uint32_t*)a.p + (size_t)i0 * pw;
+        CU(cudaMemsetAsync(bd.p, 0x7f, 3 * d, st));           // 0x7f7f7f7f: larger than any coordinate or negated coordinate
+        CU(cudaMemsetAsync(bo.p, 0x7f, 3 * o, st));
+        k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, nullptr, nullptr, H, W, wpr);
+        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, H, W, wpr);
+        k_ccl_bbox<<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, bb, H, W, wpr);
+        k_ccl_paint_rects<<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, bb, (uint32_t*)b.p + (size_t)i0 * pw, H, W, wpr);
+        CHECK_LAUNCH();
+    }
+    return unpack_from_bits((const uint32_t*)b.p, dst, n, H, W, st);
+}
+
 extern "C" int dvc_degrade_blend_u8(const uint8_t* bgr, const uint8_t* mask, uint8_t* compressed, uint8_t* overlay, int32_t n,
                                     int32_t H, int32_t W, int32_t block_size, float q, int32_t flavour, uint64_t* counters,
                                     void* stream) {

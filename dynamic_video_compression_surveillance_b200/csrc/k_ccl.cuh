@@ -285,4 +285,82 @@ k_ccl_select(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __r
     out[(size_t)blockIdx.y * plane_words + idx] = keep;
 }
 
+// ---- bounding rectangles of the 8-connected components (motion_compression_opt.py:93-97) ------------------
+//     contours = findContours(mask, RETR_EXTERNAL); for c: x, y, w, h = boundingRect(c); rectangle((x, y), (x + w, y + h), 255, FILLED)
+// Only outermost contours are returned, but a component nested in a hole of another lies inside that one's
+// rectangle, so painting the rectangle of every 8-connected component gives the same image.  cv2.rectangle
+// includes both corners: columns min_x .. max_x + 1 and rows min_y .. max_y + 1, clipped to the image.
+// The root of a set is its smallest node id = its first run in raster order, so min_y is the root's own row;
+// min_x, -max_x and -max_y are reduced with atomicMin into per-node arrays (same dense / overflow layout).
+struct BBoxArrays { int* d[3]; int* ov[3]; };        // [0] min_x, [1] -max_x, [2] -max_y
+DEVI UF bbox_view(const BBoxArrays& b, int k, size_t plane_words, int frame) { return uf_of_frame(b.d[k], b.ov[k], plane_words, frame); }
+
+__global__ void __launch_bounds__(256)
+k_ccl_bbox(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov, BBoxArrays bb, int H, int W, int wpr) {
+    const size_t plane_words = (size_t)H * wpr;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane_words) return;
+    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
+    const UF MINX = bbox_view(bb, 0, plane_words, blockIdx.y), NMAXX = bbox_view(bb, 1, plane_words, blockIdx.y),
+             NMAXY = bbox_view(bb, 2, plane_words, blockIdx.y);
+    uint32_t m = planes[(size_t)blockIdx.y * plane_words + idx];
+    int slot = 0;
+    while (m) {
+        int lo;
+        const uint32_t run = lowest_run(m, lo);
+        m &= ~run;
+        const int hi = 31 - __clz(run);
+        const int root = uf_find(P, node_id((int)idx, slot++));
+        atomicMin(uf_addr(MINX, root), j * 32 + lo);
+        atomicMin(uf_addr(NMAXX, root), -(j * 32 + hi));
+        atomicMin(uf_addr(NMAXY, root), -y);
+    }
+}
+
+// One warp paints one rectangle at a time: lanes that own a root publish it by ballot, all 32 lanes OR its words.
+__global__ void __launch_bounds__(256)
+k_ccl_paint_rects(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov, BBoxArrays bb,
+                  uint32_t* __restrict__ out, int H, int W, int wpr) {
+    const size_t plane_words = (size_t)H * wpr;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in_range = idx < plane_words;
+    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
+    const UF MINX = bbox_view(bb, 0, plane_words, blockIdx.y), NMAXX = bbox_view(bb, 1, plane_words, blockIdx.y),
+             NMAXY = bbox_view(bb, 2, plane_words, blockIdx.y);
+    uint32_t* o = out + (size_t)blockIdx.y * plane_words;
+    uint32_t m = in_range ? planes[(size_t)blockIdx.y * plane_words + idx] : 0u;
+    int slot = 0;
+    while (__any_sync(0xffffffffu, m != 0u)) {
+        int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+        if (m) {
+            int lo;
+            const uint32_t run = lowest_run(m, lo);
+            m &= ~run;
+            const int id = node_id((int)idx, slot++);
+            if (__ldcg(uf_addr(P, id)) == id) {                 // a root: owns the rectangle of its component
+                x0 = __ldcg(uf_addr(MINX, id));
+                x1 = min(W - 1, -__ldcg(uf_addr(NMAXX, id)) + 1);
+                y0 = (int)(idx / wpr);
+                y1 = min(H - 1, -__ldcg(uf_addr(NMAXY, id)) + 1);
+            }
+        }
+        uint32_t owners = __ballot_sync(0xffffffffu, x1 >= x0 && y1 >= y0);
+        while (owners) {
+            const int src = __ffs(owners) - 1;
+            owners &= owners - 1;
+            const int rx0 = __shfl_sync(0xffffffffu, x0, src), rx1 = __shfl_sync(0xffffffffu, x1, src);
+            const int ry0 = __shfl_sync(0xffffffffu, y0, src), ry1 = __shfl_sync(0xffffffffu, y1, src);
+            const int jw0 = rx0 >> 5, nw = (rx1 >> 5) - jw0 + 1, total = nw * (ry1 - ry0 + 1);
+            for (int i = lane; i < total; i += 32) {
+                const int r = i / nw, c = i - r * nw, jw = jw0 + c;
+                const int b0 = max(rx0, jw * 32) - jw * 32, b1 = min(rx1, jw * 32 + 31) - jw * 32;
+                const uint32_t bits = (0xffffffffu >> (31 - b1)) & (0xffffffffu << b0);
+                atomicOr(o + (size_t)(ry0 + r) * wpr + jw, bits);
+            }
+        }
+    }
+}
+
 }  // namespace dvc

@@ -1,7 +1,7 @@
 """Drop-in for the reference module of the same name: ``windows.py`` imports ``process_single_video_of`` from
 here (windows.py:13,151).  Contracts follow motion_compression_opt.py:8-247.  GPU (C ABI): the K-frame window
-vote (:84-86), close/open (:89-90) and all of compress_with_motion's arithmetic (:152-183).  Host, as scoped by
-SURVEY.md section 8: Farneback flow + cartToPolar (:72-82), contours -> rectangles (:93-97), codecs.
+vote (:84-86), close/open (:89-90), contours -> bounding rectangles (:93-97) and all of compress_with_motion's
+arithmetic (:152-183).  Host, as scoped by SURVEY.md section 8: Farneback flow + cartToPolar (:72-82), codecs.
 """
 import logging
 import os
@@ -66,15 +66,15 @@ def temporal_smoothing_flow(video_path, output_dir, flow_threshold=0.5, alpha_fr
             prev_gray = gray
         if not frames:
             break
-        smoothed = _hl.smooth_masks_gpu(raws, history, window_size, alpha_fraction, morph_kernel)
+        rects = _hl.smooth_rect_masks_gpu(raws, history, window_size, alpha_fraction, morph_kernel)
         seen = history + raws
         # while the stream is shorter than the window keep all of it (the vote's L = len(deque) must match);
         # afterwards the last window_size-1 raw masks are enough
         history = seen if n_frames + len(raws) < window_size else (seen[-(window_size - 1):] if window_size > 1 else [])
-        for frame, mask in zip(frames, smoothed):
+        for frame, mask in zip(frames, rects):
             n_frames += 1
             out_overlay.write(frame)
-            out_mask.write(_hl.rectangles_from_mask(mask))
+            out_mask.write(mask)
     cap.release()
     out_overlay.release()
     out_mask.release()

@@ -201,6 +201,15 @@ def smooth_masks_gpu(raw_masks: list, history: list, window_size: int, alpha_fra
     return P.morph(closed, "open", morph_kernel, "ellipse").cpu().numpy()
 
 
+def smooth_rect_masks_gpu(raw_masks: list, history: list, window_size: int, alpha_fraction: float, morph_kernel: int):
+    """smooth_masks_gpu followed by contours -> bounding rectangles (motion_compression_opt.py:93-97), all on the GPU:
+    the chunk's mask.mp4 frames."""
+    stack = torch.from_numpy(np.stack(history + raw_masks)).cuda()
+    voted = P.temporal_ring(stack, window_size, alpha_fraction)[len(history):].contiguous()
+    closed = P.morph(voted, "close", morph_kernel, "ellipse")
+    return P.mask_rectangles(P.morph(closed, "open", morph_kernel, "ellipse")).cpu().numpy()
+
+
 def degrade_mco_gpu(frames: list, masks: list) -> np.ndarray:
     """compress_with_motion's arithmetic (motion_compression_opt.py:152-183) for a chunk."""
     comp, _ = P.degrade_blend(torch.from_numpy(np.stack(frames)).cuda(), torch.from_numpy(np.stack(masks)).cuda(),
@@ -209,7 +218,12 @@ def degrade_mco_gpu(frames: list, masks: list) -> np.ndarray:
 
 
 def rectangles_from_mask(mask: np.ndarray) -> np.ndarray:
-    """contours -> bounding rectangles (motion_compression_opt.py:93-97); host, SURVEY.md section 8f rank 2."""
+    """contours -> bounding rectangles (motion_compression_opt.py:93-97) on one host mask through the GPU stage op."""
+    return P.mask_rectangles(torch.from_numpy(np.ascontiguousarray(mask))[None].cuda())[0].cpu().numpy()
+
+
+def _rectangles_from_mask_cv2(mask: np.ndarray) -> np.ndarray:
+    """The reference's own lines, kept for comparison in tools/ only."""
     out = np.zeros_like(mask)
     contours, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
     for c in contours:

@@ -257,6 +257,16 @@ def contour_filter(masks: torch.Tensor, min_area: float = 500) -> torch.Tensor:
     return out
 
 
+def mask_rectangles(masks: torch.Tensor) -> torch.Tensor:
+    """motion_compression_opt.py:93-97 on [N,H,W] masks: every 8-connected component becomes its bounding
+    rectangle, drawn the way cv2.rectangle((x, y), (x + w, y + h), 255, -1) draws it (both corners included)."""
+    _dev_u8(masks, "masks")
+    n, h, w = masks.shape
+    out = torch.empty_like(masks)
+    _lib_call("dvc_mask_rectangles_u8", masks.data_ptr(), out.data_ptr(), n, h, w, _stream_ptr(None))
+    return out
+
+
 def degrade_blend(bgr: torch.Tensor, mask: torch.Tensor, block_size: int = 4, quantization_level: float = 100,
                   flavour: str = "fd", want_overlay: bool = True, counters: torch.Tensor | None = None):
     """frame_differencing.py:110-111,115-130 (flavour 'fd') or motion_compression_opt.py:152-183 ('mco') on

@@ -174,6 +174,10 @@ int dvc_morph_u8(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n, int32_t H,
  * frame_differencing.py:100-104.  n images. */
 int dvc_contour_filter_u8(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n, int32_t H, int32_t W,
                           double min_area, void* stream);
+/* findContours(RETR_EXTERNAL) + boundingRect + rectangle((x, y), (x + w, y + h), 255, FILLED),
+ * motion_compression_opt.py:93-97: every 8-connected component is replaced by its bounding rectangle
+ * grown by one column and one row (cv2.rectangle includes both corners), clipped to the image.  n images. */
+int dvc_mask_rectangles_u8(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n, int32_t H, int32_t W, void* stream);
 /* overlay paint + colour round trip + block-DCT degrade, frame_differencing.py:110-111,115-130
  * (flavour FD) or motion_compression_opt.py:152-183 (flavour MCO).  mask_dev [n][H][W] is
  * accumulated_mask (any uint8 values).  Either output may be NULL.  counters_dev (5 x uint64 in

@@ -271,6 +271,31 @@ def contour_filter_cv2(mask: np.ndarray, min_area: float) -> np.ndarray:
     return out
 
 
+def mask_rectangles(mask: np.ndarray) -> np.ndarray:
+    """contours -> bounding rectangles (motion_compression_opt.py:93-97), restated without contour tracing:
+    every 8-connected component is replaced by the rectangle columns min_x..max_x+1, rows min_y..max_y+1
+    (cv2.rectangle includes the corner (x + w, y + h)), clipped to the image.  Components nested inside a hole of
+    another one are not returned by RETR_EXTERNAL, but their rectangles lie inside the outer rectangle."""
+    from scipy import ndimage
+    h, w = mask.shape
+    lab, n = ndimage.label(mask != 0, structure=np.ones((3, 3), int))
+    out = np.zeros((h, w), np.uint8)
+    for sl in ndimage.find_objects(lab):
+        out[sl[0].start:min(h, sl[0].stop + 1), sl[1].start:min(w, sl[1].stop + 1)] = 255
+    return out
+
+
+def mask_rectangles_cv2(mask: np.ndarray) -> np.ndarray:
+    """The literal reference lines (motion_compression_opt.py:93-97)."""
+    import cv2
+    contours, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    out = np.zeros_like(mask)
+    for c in contours:
+        x, y, w, h = cv2.boundingRect(c)
+        cv2.rectangle(out, (x, y), (x + w, y + h), 255, -1)
+    return out
+
+
 # ----------------------------------------------------------------------------
 # block DCT degrade (frame_differencing.py:117-127; motion_compression_opt.py:156-183)
 # ----------------------------------------------------------------------------

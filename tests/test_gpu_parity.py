@@ -155,6 +155,32 @@ def test_contour_filter(P, shape):
             assert np.array_equal(got[i], so.contour_filter_cv2(masks[i], min_area)), (i, min_area)
 
 
+@pytest.mark.parametrize("shape", [(96, 128), (61, 83), (120, 160), (32, 200), (7, 5), (1, 40), (270, 480)])
+def test_mask_rectangles(P, shape):
+    r = rng(19)
+    masks = [_blob_mask(r, shape, int(r.integers(1, 12))) for _ in range(8)]
+    masks += [(r.random(shape) < d).astype(np.uint8) * 255 for d in (0.002, 0.03, 0.3, 0.6, 0.0, 1.0)]
+    masks = np.stack(masks)
+    got = host(P.mask_rectangles(dev(masks)))
+    for i in range(len(masks)):
+        assert np.array_equal(got[i], so.mask_rectangles_cv2(masks[i])), i
+
+
+def test_mask_rectangles_1080p(P):
+    r = rng(20)
+    m = np.zeros((2, 1080, 1920), np.uint8)
+    for k in range(2):
+        for _ in range(40):
+            cx, cy = int(r.integers(0, 1920)), int(r.integers(0, 1080))
+            cv2.ellipse(m[k], (cx, cy), (int(r.integers(3, 120)), int(r.integers(3, 80))), float(r.integers(0, 180)), 0, 360, 255,
+                        int(r.choice([-1, 2, 5])))
+        noise = r.random(m[k].shape) < 0.0005
+        m[k][noise] = 255
+    got = host(P.mask_rectangles(dev(m)))
+    for k in range(2):
+        assert np.array_equal(got[k], so.mask_rectangles_cv2(m[k]))
+
+
 def test_contour_filter_1080p_blobs(P):
     r = rng(10)
     m = np.zeros((1080, 1920), np.uint8)

@@ -132,6 +132,16 @@ def test_contour_filter(seed):
         assert np.array_equal(so.contour_filter(m, min_area), so.contour_filter_cv2(m, min_area)), (seed, min_area)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_mask_rectangles(seed):
+    rng = _rng(300 + seed)
+    shape = [(96, 128), (61, 83), (120, 160), (32, 200), (5, 7), (1, 30)][seed % 6]
+    m = _random_blob_mask(rng, shape, int(rng.integers(1, 12)))
+    assert np.array_equal(so.mask_rectangles(m), so.mask_rectangles_cv2(m)), seed
+    sparse = (rng.random(shape) < 0.03).astype(np.uint8) * 255
+    assert np.array_equal(so.mask_rectangles(sparse), so.mask_rectangles_cv2(sparse)), seed
+
+
 def test_contour_filter_dense_random():
     rng = _rng(7)
     for density in (0.3, 0.5, 0.6, 0.8):
