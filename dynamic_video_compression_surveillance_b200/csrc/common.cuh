@@ -75,6 +75,23 @@ DEVI void gray16_dp4a(const uint32_t (&w)[12], uint32_t (&g)[4]) {
     }
 }
 
+// Same result through IDP.2A (u16 x u8 pairs): the doubled coefficients 7470 / 38470 / 19596 fit 16 bits, so a pixel
+// is two dot products (three source bytes, one of the four products multiplies by zero) and the gray value is byte 2
+// of the sum.  dp2a.lo: a.lo16 * b.byte0 + a.hi16 * b.byte1; dp2a.hi: a.lo16 * b.byte2 + a.hi16 * b.byte3.
+DEVI void gray16_dp2a(const uint32_t (&w)[12], uint32_t (&g)[4]) {
+    const uint32_t cBG = 7470u | (38470u << 16), cR_ = 19596u, c_B = 7470u << 16, cGR = 38470u | (19596u << 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        const uint32_t s0 = __dp2a_hi(cR_, a, __dp2a_lo(cBG, a, 32768u));      // B G R .
+        const uint32_t s1 = __dp2a_lo(cGR, b, __dp2a_hi(c_B, a, 32768u));      // . . . B | G R
+        const uint32_t s2 = __dp2a_lo(cR_, c, __dp2a_hi(cBG, b, 32768u));      // . . B G | R
+        const uint32_t s3 = __dp2a_hi(cGR, c, __dp2a_lo(c_B, c, 32768u));      // . B G R
+        const uint32_t lo = __byte_perm(s0, s1, 0x0062u), hi = __byte_perm(s2, s3, 0x0062u);
+        g[q] = __byte_perm(lo, hi, 0x5410u);
+    }
+}
+
 // per-byte |a - b| > thr  ->  4 mask bits (bit p = byte p).  thr < 128 uses a SWAR compare + multiply gather.
 DEVI uint32_t diff_gt_bits4(uint32_t a, uint32_t b, uint32_t thr) {
     const uint32_t d = __vabsdiffu4(a, b);

@@ -308,7 +308,7 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                 if (persist) {
                     static const int env_stages = [] { const char* e = getenv("DVC_K4_STAGES"); return e ? atoi(e) : 6; }();
                     static const int env_groups = [] { const char* e = getenv("DVC_K4_GROUPS"); return e ? atoi(e) : 2; }();
-                    static const int env_rowcopy = [] { const char* e = getenv("DVC_K4_ROWCOPY"); return e ? atoi(e) : 0; }();
+                    static const int env_piece = [] { const char* e = getenv("DVC_K4_PIECE"); return e ? atoi(e) : 0; }();
                     static const int env_ctas = [] { const char* e = getenv("DVC_K4_CTAS"); return e ? atoi(e) : 0; }();
                     int dev = 0, sms = 0;
                     CU(cudaGetDevice(&dev));
@@ -324,11 +324,13 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                     const int cps = env_cps == 2 ? 2 : 1;
                     int S = std::max(G, env_stages);
                     const size_t smem_cap = cps == 2 ? 110 * 1024 : 224 * 1024;
-                    auto smem_need = [&](int stages) { return (size_t)stages * sg.stage_bytes + (size_t)G * sg.ybuf_bytes + 8 * (2 * stages + G) + 16 + 16 * stages; };
+                    auto smem_need = [&](int stages) { return (size_t)stages * sg.stage_bytes + (size_t)G * sg.ybuf_bytes + 8 * (2 * stages) + 16 + 16 * stages; };
                     while (smem_need(S) > smem_cap && S > G) --S;
                     S -= S % G;
                     sg.stages = S;
-                    sg.row_copies = env_rowcopy;
+                    // bulk-copy granularity: whole spans by default (piece sizes from 1.4 KB to the full 23 KB span were
+                    // measured: no gain from smaller pieces, profiles/README.md r1l)
+                    sg.piece_bytes = env_piece > 0 ? ((env_piece + 15) & ~15) : 32768;
                     const size_t smem_s = smem_need(S);
                     const unsigned ctas = (unsigned)std::min(sg.n_tiles, env_ctas > 0 ? env_ctas : sms * cps);
                     static bool attr_s = false;
@@ -389,7 +391,7 @@ struct dvc_handle {
     bool aligned;                 // W % 16 == 0: vector paths
     long long n_masks;            // masks produced so far in this stream
     int seg_len;
-    bool gray_dp4a;               // DVC_GRAY_DP4A=1: IDP.4A variant of the gray conversion
+    int gray_impl;                // DVC_GRAY_IMPL: 0 = PRMT + IMAD, 1 = IDP.4A, 2 = IDP.2A (default) gray conversion in K1
     // state
     uint8_t* prev_gray[2];
     int cur;
@@ -473,8 +475,8 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     const int T = cfg->max_batch;
     const char* sl = getenv("DVC_SEG_LEN");
     h->seg_len = sl ? std::max(1, atoi(sl)) : 8;
-    const char* gd = getenv("DVC_GRAY_DP4A");
-    h->gray_dp4a = gd && atoi(gd) != 0;
+    const char* gd = getenv("DVC_GRAY_IMPL");
+    h->gray_impl = gd ? atoi(gd) : 2;
     CU(cudaSetDevice(cfg->device));
     for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&h->prev_gray[i], h->plane_bytes)); CU(cudaMemset(h->prev_gray[i], 0, h->plane_bytes)); }
     for (int s = 0; s < 2; ++s)
@@ -728,8 +730,10 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         uint8_t* pg_in = h->prev_gray[h->cur];
         uint8_t* pg_out = h->prev_gray[h->cur ^ 1];
         { ProfScope ps(h, DVC_PROF_FRONT, 1, st);
-        if (h->aligned && h->gray_dp4a)
-            k_gray_diff_thresh<true, true><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);
+        if (h->aligned && h->gray_impl == 2)
+            k_gray_diff_thresh<true, 2><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);
+        else if (h->aligned && h->gray_impl == 1)
+            k_gray_diff_thresh<true, 1><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);
         else if (h->aligned)
             k_gray_diff_thresh<true><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);
         else

@@ -458,14 +458,20 @@ k_degrade4r(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ ove
 // Persistent, warp-specialised version (the default): one CTA per SM walks tiles t = blockIdx.x, blockIdx.x +
 // gridDim.x, ... over all frames of the launch.  A tile is the K4Geom span (whole block rows, or part of one for
 // W > 2048).
-//   warp 0 (one elected lane)  producer: cp.async.bulk loads of span + mask rows into a ring of `stages` input
-//                              buffers (mbarrier expect_tx) and the cp.async.bulk stores of finished tiles;
+//   loader warp (last warp)    waits for "free[s]", then cp.async.bulk loads of span + mask rows into stage s of a
+//                              ring of `stages` input buffers, completing on "full[s]" (mbarrier expect_tx).  Its
+//                              per-tile instruction chain is a barrier wait and a handful of copies, nothing else.
 //   G consumer groups of 256   wait for "full", LDS.64 their 8 px x 4 rows, paint the overlay in place in the
-//   threads                    input buffer, run k4_blocks, STS.64 the compressed pixels into the group's
-//                              output buffer, fence.proxy.async, arrive on "done".
+//   threads                    input buffer, run k4_blocks, STS.64 the compressed pixels into the group's output
+//                              buffer, fence.proxy.async, group barrier; then the group's 8 issuer lanes send the
+//                              tile out with cp.async.bulk stores (overlay from the input stage, compressed from
+//                              the output buffer) and, one tile later, after cp.async.bulk.wait_group.read, hand
+//                              the stage back to the loader ("free") and the output buffer back to the group.
+// Copies can be cut into pieces (piece_bytes, dealt out over the loader's lanes / the issuer lanes); measured from
+// 1.4 KB to the whole 23 KB span without a gain, so the default is one bulk operation per span (profiles/README.md, r1l).
 // Shared memory: `stages` x (span + 2 mask row groups) + G x span (6 x 25 KB + 2 x 23 KB at 1080p).
-// HBM sees a steady stream of large bulk operations whose depth is `stages`, independent of CTA launch / drain
-// behaviour; consumers never touch global memory (statistics: one atomic pair per warp per launch).
+// HBM sees a steady stream of bulk operations whose depth is `stages`, independent of CTA launch / drain behaviour;
+// consumers never touch global memory (statistics: one atomic pair per warp per launch).
 // ------------------------------------------------------------------------------------------------
 struct K4SGeom {
     K4Geom g;
@@ -474,8 +480,10 @@ struct K4SGeom {
     int n_tiles;           // tiles_per_frame * frames
     int stage_bytes;       // span_bytes + 2 * mask_bytes, rounded up to 128
     int ybuf_bytes;        // span_bytes rounded up to 128
-    int row_copies;        // 1: always move spans row by row (5.7 KB pieces) instead of one bulk operation
+    int piece_bytes;       // bulk-copy granularity inside a contiguous span (multiple of 16)
 };
+
+constexpr int K4S_ISSUERS = 8;          // lanes 0..7 of a consumer group's first warp issue its stores
 
 DEVI void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -485,12 +493,13 @@ DEVI void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 DEVI void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+DEVI void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 
-// tile walker: (frame, tile-in-frame) advanced by the grid stride without divisions
+// tile walker: (frame, tile-in-frame) advanced by a fixed number of tiles without divisions
 struct K4Walk {
     int f, l, df, dl, tpf;
-    DEVI void init(int t0, int stride, int tiles_per_frame) {
-        tpf = tiles_per_frame; f = t0 / tpf; l = t0 - f * tpf; df = stride / tpf; dl = stride - df * tpf;
+    DEVI void init(int t0, int step, int tiles_per_frame) {
+        tpf = tiles_per_frame; f = t0 / tpf; l = t0 - f * tpf; df = step / tpf; dl = step - df * tpf;
     }
     DEVI void next() { f += df; l += dl; if (l >= tpf) { l -= tpf; ++f; } }
 };
@@ -516,90 +525,71 @@ k_degrade4s(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ ove
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(k4_smem);
     const int S = sg.stages;
     const uint32_t ybufs = s0 + (uint32_t)S * (uint32_t)sg.stage_bytes;     // G output buffers
-    const uint32_t bars = ybufs + (uint32_t)G * (uint32_t)sg.ybuf_bytes;    // full[S], done[S], yfree[G]
-    const uint32_t desc = (bars + 8u * (uint32_t)(2 * S + G) + 15u) & ~15u;    // per stage: {nbv, g0, ng, -}
+    const uint32_t bars = ybufs + (uint32_t)G * (uint32_t)sg.ybuf_bytes;    // full[S], free[S]
+    const uint32_t desc = (bars + 8u * (uint32_t)(2 * S) + 15u) & ~15u;     // per stage: {nbv, g0, ng, -}
     const int tid = threadIdx.x;
     const int first = blockIdx.x, stride = gridDim.x;
     const int nj = first < sg.n_tiles ? (sg.n_tiles - first + stride - 1) / stride : 0;
     const uint32_t pitch = (uint32_t)W * 3u;
     const uint32_t mrow_bytes = (uint32_t)wpr * 4u;
+    const bool contiguous = g.parts == 1;
+    const uint32_t piece = (uint32_t)sg.piece_bytes;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * (S + s)), "r"(256));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * (S + s)), "r"(K4S_ISSUERS));
         }
-        for (int q = 0; q < G; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * (2 * S + q)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (tid < 32) {
-        // ------------------------------ producer ------------------------------
-        if (tid == 0) {
-            const bool whole = g.parts == 1 && !sg.row_copies;
-            K4Walk wl, ws;                       // load walker runs `S` tiles ahead of the store walker
-            wl.init(first, stride, sg.tiles_per_frame);
-            ws = wl;
-            auto issue_load = [&](int j) {
-                const int s = j % S;
-                const K4Tile t = k4_tile(wl, g, H, W, wpr);
-                wl.next();
-                const uint32_t sX = s0 + (uint32_t)s * (uint32_t)sg.stage_bytes;
-                const uint32_t sMh = sX + g.span_bytes, sMn = sMh + g.mask_bytes;
-                const uint32_t full = bars + 8u * s;
-                const uint32_t mbytes = (uint32_t)(4 * t.nbv) * mrow_bytes;
-                const uint32_t rows = g.parts == 1 ? (uint32_t)(4 * t.nbv) : 4u;
-                const uint32_t rbytes = g.parts == 1 ? pitch : (uint32_t)t.ng * 24u;
+    if (tid >= G * 256) {
+        // ------------------------------ loader warp ------------------------------
+        const int lane = tid - G * 256;
+        K4Walk wl;
+        wl.init(first, stride, sg.tiles_per_frame);
+        for (int j = 0; j < nj; ++j) {
+            const int s = j % S;
+            const K4Tile t = k4_tile(wl, g, H, W, wpr);
+            wl.next();
+            const uint32_t sX = s0 + (uint32_t)s * (uint32_t)sg.stage_bytes;
+            const uint32_t sMh = sX + g.span_bytes, sMn = sMh + g.mask_bytes;
+            const uint32_t full = bars + 8u * s;
+            const uint32_t mbytes = (uint32_t)(4 * t.nbv) * mrow_bytes;
+            const uint32_t rows = contiguous ? (uint32_t)(4 * t.nbv) : 4u;
+            const uint32_t rbytes = contiguous ? pitch : (uint32_t)t.ng * 24u;
+            if (j >= S) mbar_wait(bars + 8u * (S + s), (uint32_t)(j / S - 1) & 1u);       // the stage's previous tile has left
+            if (lane == 0) {
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc + 16u * s), "r"(t.nbv), "r"(t.g0), "r"(t.ng), "r"(0) : "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(rows * rbytes + 2u * mbytes) : "memory");
-                if (whole) bulk_load(sX, frames + t.span_off, rows * rbytes, full);
-                else
-                    for (uint32_t r = 0; r < rows; ++r) bulk_load(sX + r * g.sp, frames + t.span_off + (size_t)r * pitch, rbytes, full);
-                bulk_load(sMh, over127 + t.mask_off, mbytes, full);
-                bulk_load(sMn, nonzero + t.mask_off, mbytes, full);
-            };
-            for (int j = 0; j < min(S, nj); ++j) issue_load(j);
-            for (int j = 0; j < nj; ++j) {
-                const int s = j % S, grp = j % G;
-                mbar_wait(bars + 8u * (S + s), (uint32_t)(j / S) & 1u);           // consumers are done with tile j
-                if (!(g.debug & 1)) {
-                    const K4Tile t = k4_tile(ws, g, H, W, wpr);
-                    const uint32_t sX = s0 + (uint32_t)s * (uint32_t)sg.stage_bytes;
-                    const uint32_t sY = ybufs + (uint32_t)grp * (uint32_t)sg.ybuf_bytes;
-                    const uint32_t rows = g.parts == 1 ? (uint32_t)(4 * t.nbv) : 4u;
-                    const uint32_t rbytes = g.parts == 1 ? pitch : (uint32_t)t.ng * 24u;
-#pragma unroll
-                    for (int o = 0; o < 2; ++o) {
-                        uint8_t* dst = o == 0 ? overlay : compressed;
-                        if (!dst) continue;
-                        const uint32_t src = o == 0 ? sX : sY;
-                        if (whole) bulk_store(dst + t.span_off, src, rows * rbytes);
-                        else
-                            for (uint32_t r = 0; r < rows; ++r) bulk_store(dst + t.span_off + (size_t)r * pitch, src + r * g.sp, rbytes);
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // input stage and output buffer are free again
-                }
-                ws.next();
-                mbar_arrive(bars + 8u * (2 * S + grp));                                  // yfree[grp]
-                if (j + S < nj) issue_load(j + S);
             }
+            if (contiguous) {
+                const uint32_t total = rows * rbytes;
+                for (uint32_t off = (uint32_t)lane * piece; off < total; off += 32u * piece)
+                    bulk_load(sX + off, frames + t.span_off + off, min(piece, total - off), full);
+            } else {
+                for (uint32_t r = lane; r < rows; r += 32) bulk_load(sX + r * g.sp, frames + t.span_off + (size_t)r * pitch, rbytes, full);
+            }
+            if (lane == 30) bulk_load(sMh, over127 + t.mask_off, mbytes, full);
+            if (lane == 31) bulk_load(sMn, nonzero + t.mask_off, mbytes, full);
         }
         return;
     }
 
     // ------------------------------ consumers ------------------------------
-    const int ctid = tid - 32, grp = ctid >> 8, t = ctid & 255;
+    const int grp = tid >> 8, t = tid & 255;
+    const bool issuer = t < K4S_ISSUERS;
     const int gpr = W >> 3;
     int brl = 0, gxl = t;
-    if (g.parts == 1) { brl = t / gpr; gxl = t - brl * gpr; }
+    if (contiguous) { brl = t / gpr; gxl = t - brl * gpr; }
     const uint32_t toff = (uint32_t)(brl * 4) * (uint32_t)g.sp + (uint32_t)gxl * 24u;
     const uint32_t sY = ybufs + (uint32_t)grp * (uint32_t)sg.ybuf_bytes;
-    const uint32_t yfree = bars + 8u * (2 * S + grp);
     unsigned n_motion = 0, n_static = 0;
-    int n_mine = 0;
-    for (int j = grp; j < nj; j += G, ++n_mine) {
+    K4Walk ws;                              // this group's tiles, for the store addresses
+    ws.init(first + grp * stride, G * stride, sg.tiles_per_frame);
+    int s_prev = -1;
+    for (int j = grp; j < nj; j += G) {
         const int s = j % S;
         const uint32_t sX = s0 + (uint32_t)s * (uint32_t)sg.stage_bytes;
         const uint32_t sMh = sX + g.span_bytes, sMn = sMh + g.mask_bytes;
@@ -608,7 +598,6 @@ k_degrade4s(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ ove
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(nbv), "=r"(tg0), "=r"(tng), "=r"(unused) : "r"(desc + 16u * s));
         const bool active = brl < (int)nbv && gxl < (int)tng;
         uint32_t w[4][6];
-        bool st_a = false, st_b = false;
         if (active) {
             const uint32_t moff = (uint32_t)(brl * 4) * mrow_bytes + tg0 + (uint32_t)gxl;
 #pragma unroll
@@ -641,22 +630,50 @@ k_degrade4s(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ ove
                 }
             }
             n_motion += __popc(hi[0]) + __popc(hi[1]) + __popc(hi[2]) + __popc(hi[3]);
-            st_a = (nz & 0xfu) == 0u; st_b = (nz >> 4) == 0u;
+            const bool st_a = (nz & 0xfu) == 0u, st_b = (nz >> 4) == 0u;
             n_static += (st_a ? 1u : 0u) + (st_b ? 1u : 0u);
             if (compressed && !(g.debug & 2)) k4_blocks(w, st_a, st_b, qp);
         }
-        if (compressed) {
-            if (n_mine > 0) mbar_wait(yfree, (uint32_t)(n_mine - 1) & 1u);      // the previous tile's store has read the buffer
-            if (active) {
+        // the previous tile's stores have read their shared-memory sources: its input stage goes back to the loader,
+        // the output buffer back to the group
+        if (issuer && s_prev >= 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(bars + 8u * (S + s_prev));
+        }
+        group_sync(1 + grp);
+        if (compressed && active) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) sts64(sY + toff + r * g.sp + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
-            }
+                for (int i = 0; i < 3; ++i) sts64(sY + toff + r * g.sp + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(bars + 8u * (S + s));
+        group_sync(1 + grp);
+        if (issuer) {
+            if (!(g.debug & 1)) {
+                const K4Tile tl = k4_tile(ws, g, H, W, wpr);
+                const uint32_t rows = contiguous ? 4u * nbv : 4u;
+                const uint32_t rbytes = contiguous ? pitch : tng * 24u;
+                const uint32_t np = contiguous ? (rows * rbytes + piece - 1) / piece : rows;       // pieces per output
+                for (uint32_t i = (uint32_t)t; i < 2u * np; i += K4S_ISSUERS) {
+                    const uint32_t o = i >= np ? 1u : 0u, k = i - o * np;
+                    uint8_t* dst = o == 0 ? overlay : compressed;
+                    if (!dst) continue;
+                    const uint32_t src = o == 0 ? sX : sY;
+                    if (contiguous) {
+                        const uint32_t off = k * piece;
+                        bulk_store(dst + tl.span_off + off, src + off, min(piece, rows * rbytes - off));
+                    } else {
+                        bulk_store(dst + tl.span_off + (size_t)k * pitch, src + k * g.sp, rbytes);
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            s_prev = s;
+        }
+        ws.next();
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // shared memory must outlive the reads
     if (counters) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

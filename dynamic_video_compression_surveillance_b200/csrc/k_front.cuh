@@ -39,7 +39,7 @@ DEVI void store_u8x16_generic(uint8_t* row, int x0, int W, const uint32_t (&v)[4
 // ring:   raw-mask ring buffer, plane of frame f lives in slot f % ring_cap
 // f0:     global index of frames[0] within the stream
 // ------------------------------------------------------------------------------------------------
-template <bool ALIGNED, bool DP4A = false>
+template <bool ALIGNED, int GRAY = 0>   // GRAY: 0 = PRMT + IMAD, 1 = IDP.4A, 2 = IDP.2A
 __global__ void __launch_bounds__(256)
 k_gray_diff_thresh(const uint8_t* __restrict__ frames, int T, int H, int W,
                    const uint8_t* __restrict__ prev_gray_in, uint8_t* __restrict__ gray_state_out,
@@ -66,7 +66,7 @@ k_gray_diff_thresh(const uint8_t* __restrict__ frames, int T, int H, int W,
             load16(fr + x0 * 3 + 16, *reinterpret_cast<uint32_t(*)[4]>(&w[4]));
             load16(fr + x0 * 3 + 32, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
         } else load_bgr16_generic(fr, x0, W, w);
-        if (DP4A) gray16_dp4a(w, pg); else gray16(w, pg);
+        if (GRAY == 2) gray16_dp2a(w, pg); else if (GRAY == 1) gray16_dp4a(w, pg); else gray16(w, pg);
     }
     for (int t = t0; t < t1; ++t) {
         const uint8_t* fr = frames + (size_t)t * frame_bytes + row_off;
@@ -76,7 +76,7 @@ k_gray_diff_thresh(const uint8_t* __restrict__ frames, int T, int H, int W,
             load16(fr + x0 * 3 + 32, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
         } else load_bgr16_generic(fr, x0, W, w);
         uint32_t g[4];
-        if (DP4A) gray16_dp4a(w, g); else gray16(w, g);
+        if (GRAY == 2) gray16_dp2a(w, g); else if (GRAY == 1) gray16_dp4a(w, g); else gray16(w, g);
         uint32_t bits = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) bits |= diff_gt_bits4(g[q], pg[q], thr) << (4 * q);

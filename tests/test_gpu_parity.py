@@ -357,17 +357,17 @@ def test_window_loop_against_oracle(P, cfg, noise):
     pipe.close()
 
 
-def test_window_front_end_dp4a_variant(P, monkeypatch):
-    """DVC_GRAY_DP4A=1 selects the IDP.4A gray conversion in K1: masks must not change (random frames make
-    every gray value matter, threshold 3 keeps the mask non-trivial)."""
+def test_window_front_end_gray_variants(P, monkeypatch):
+    """DVC_GRAY_IMPL selects the gray conversion in K1 (0 PRMT + IMAD, 1 IDP.4A, 2 IDP.2A = default): masks must not
+    change (random frames make every gray value matter, threshold 3 keeps the mask non-trivial)."""
     r = rng(31)
     h, w, n = 64, 160, 12
     frames = r.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
     frames[1::2] = np.clip(frames[0:-1:2].astype(int) + r.integers(-4, 5, frames[1::2].shape), 0, 255).astype(np.uint8)
     cfg = dict(window_size=3, alpha_fraction=0.5, morph_kernel=0, kernel_size=0, motion_threshold=3.0)
     ref = loops.window_loop(list(frames), degrade=False, **cfg)
-    for flag in ("0", "1"):
-        monkeypatch.setenv("DVC_GRAY_DP4A", flag)
+    for flag in ("0", "1", "2"):
+        monkeypatch.setenv("DVC_GRAY_IMPL", flag)
         pipe = P.FramePipeline(w, h, "window", max_batch=16, **cfg)
         pipe.begin_stream(so.bgr2gray(frames[0]))
         mk = torch.empty((n - 1, h, w), dtype=torch.uint8, device="cuda")

@@ -1,14 +1,9 @@
-run() { python bench.py --steps 20 --no-cpu-baseline --no-e2e --no-overlap > gpurun_out/b.log 2>&1; tail -1 gpurun_out/b.log | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('$1', round(d['value']), d['roofline']['kernel_ms_in_timed_region'], d['clocks']['power_w_max'])"; }
+# A/B of env switches inside one job (same box): one bench per argument, prints loop fps and per-kernel-group ms
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=serial,temperature.gpu,memory.used --format=csv,noheader
-run first
-python -m pytest tests/test_gpu_parity.py -q -x -k "contour or morph" 2>&1 | tail -1
-nvidia-smi --query-gpu=serial,temperature.gpu,memory.used --format=csv,noheader
-run after_pytest_small
-python -m pytest tests -m gpu -q -x 2>&1 | tail -1
-nvidia-smi --query-gpu=serial,temperature.gpu,memory.used --format=csv,noheader
-run after_pytest_full
-sleep 20
-run after_sleep
+nvidia-smi --query-gpu=serial,temperature.gpu --format=csv,noheader
+run() { python bench.py --steps 10 --no-cpu-baseline --no-e2e > gpurun_out/b.log 2>&1; tail -1 gpurun_out/b.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']; print('$1', round(d['value']), 'serial', round(r['serialised_fps_per_gpu']), {k: round(v,1) for k,v in r['kernel_ms_in_timed_region'].items()}, 'K4 frac', round(r['frac'],3))"; }
+for v in "$@"; do
+  env $v bash -c "$(declare -f run); run '$v'"
+done
