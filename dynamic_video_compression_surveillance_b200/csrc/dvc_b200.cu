@@ -368,6 +368,14 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
             return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "MCO flavour needs W, H multiples of 8");
         }
         dim3 grid(cdiv((size_t)(W / bs) * (H / bs), 128), n);
+        static const bool k8_env = [] { const char* e = getenv("DVC_K4_BLOCK8_FAST"); return e ? atoi(e) != 0 : true; }();
+        const bool ptr8 = ((((uintptr_t)frames) | ((uintptr_t)compressed) | ((uintptr_t)overlay)) & 7u) == 0;
+        if (bs == 8 && k8_env && ptr8 && q >= 0.01f && q <= 1.0e6f) {
+            QuantP qp;
+            for (int ne = 0; ne < 3; ++ne) { qp.rcp[ne] = 1.0f / q; qp.nqs[ne] = -q; qp.o[ne] = q; }     // no folded scalings in the 8-point path
+            if (flavour == DVC_DEGRADE_FD) k_degrade8<0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+            else k_degrade8<1><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+        } else
         if (flavour == DVC_DEGRADE_FD && bs == 4)
             k_degrade_generic<4, 0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, q, counters);
         else if (flavour == DVC_DEGRADE_FD)

@@ -306,6 +306,194 @@ k_degrade4p(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ ove
 
 
 // ------------------------------------------------------------------------------------------------
+// block_size 8 (frame_differencing.py:203 main config; motion_compression_opt.py:152-183): one thread per 8x8 block,
+// 8 rows x 24 bytes moved with 8-byte vector loads / stores (a warp covers 768 contiguous bytes per row), the pixels
+// stay packed in registers.  FLAVOUR 0 = FD (luma quantised, chroma 128), 1 = MCO (Y, Cr and Cb quantised, then
+// YCrCb -> BGR -> gray, replicated).  The quotient d / q is the exact IEEE one (quantise_t, Markstein step); the
+// 8-point DCT itself is a plain float32 DCT-II (cv2's 8x8 routine is not reproduced bit for bit).
+// ------------------------------------------------------------------------------------------------
+DEVI void degrade_plane8(float (&v)[8][8], const QuantP& qp) {
+    float t[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) t[c] = v[r][c];
+        dct8_fwd(t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[r][c] = t[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t[r] = v[r][c];
+        dct8_fwd(t);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r][c] = quantise_t<0>(t[r], qp);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) t[c] = v[r][c];
+        dct8_inv(t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[r][c] = t[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t[r] = v[r][c];
+        dct8_inv(t);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r][c] = t[r];
+    }
+}
+
+template <int FLAVOUR>
+__global__ void __launch_bounds__(128)
+k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127, const uint32_t* __restrict__ nonzero,
+           uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay, int H, int W, int wpr, QuantP qp,
+           Counters* __restrict__ counters) {
+    const int nbx = W >> 3, nby = H >> 3;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n_motion = 0, n_static = 0;
+    if (gid < nbx * nby) {
+        const int by = gid / nbx, bx = gid - by * nbx;
+        const size_t pitch = (size_t)W * 3;
+        const size_t base = (size_t)blockIdx.y * H * pitch + (size_t)(by * 8) * pitch + (size_t)bx * 24;
+        const size_t plane_off = (size_t)blockIdx.y * H * wpr + (size_t)(by * 8) * wpr;
+        uint32_t w[8][6];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const uint2 t = __ldcs(reinterpret_cast<const uint2*>(frames + base + r * pitch + 8 * i));
+                w[r][2 * i] = t.x; w[r][2 * i + 1] = t.y;
+            }
+        uint32_t nz = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t hb = reinterpret_cast<const uint8_t*>(over127 + plane_off + (size_t)r * wpr)[bx];
+            nz |= reinterpret_cast<const uint8_t*>(nonzero + plane_off + (size_t)r * wpr)[bx];
+            n_motion += __popc(hb);
+            if (overlay) {
+                uint32_t o[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) o[i] = w[r][i];
+                if (hb) {
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const uint32_t m = hb >> (4 * b);
+                        if (m & 1u) { o[3 * b] = (o[3 * b] & 0xff000000u) | 0x00ff0000u; }
+                        if (m & 2u) { o[3 * b] &= 0x00ffffffu; o[3 * b + 1] = (o[3 * b + 1] & 0xffff0000u) | 0x0000ff00u; }
+                        if (m & 4u) { o[3 * b + 1] &= 0x0000ffffu; o[3 * b + 2] = (o[3 * b + 2] & 0xffffff00u) | 0x000000ffu; }
+                        if (m & 8u) { o[3 * b + 2] = (o[3 * b + 2] & 0x000000ffu) | 0xff000000u; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    __stcs(reinterpret_cast<uint2*>(overlay + base + r * pitch + 8 * i), make_uint2(o[2 * i], o[2 * i + 1]));
+            }
+        }
+        const bool is_static = nz == 0u;
+        n_static = is_static ? 1u : 0u;
+        if (compressed) {
+            if (!is_static) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    uint32_t o[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        int bb = byte_at(w[r], 3 * p), gg = byte_at(w[r], 3 * p + 1), rr = byte_at(w[r], 3 * p + 2);
+                        ycc_roundtrip(bb, gg, rr);
+                        const int j = 3 * p;
+                        o[j >> 2] |= (uint32_t)bb << ((j & 3) * 8);
+                        o[(j + 1) >> 2] |= (uint32_t)gg << (((j + 1) & 3) * 8);
+                        o[(j + 2) >> 2] |= (uint32_t)rr << (((j + 2) & 3) * 8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) w[r][i] = o[i];
+                }
+            } else if (FLAVOUR == 0) {
+                float v[8][8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    uint32_t ya[4], yb[4];
+                    luma4_bits(w[r][0], w[r][1], w[r][2], ya);
+                    luma4_bits(w[r][3], w[r][4], w[r][5], yb);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        v[r][c] = __fsub_rn(__uint_as_float(ya[c]), 8388736.0f);
+                        v[r][4 + c] = __fsub_rn(__uint_as_float(yb[c]), 8388736.0f);
+                    }
+                }
+                degrade_plane8(v, qp);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    grey4_words(out_byte_bits(v[r][0]), out_byte_bits(v[r][1]), out_byte_bits(v[r][2]), out_byte_bits(v[r][3]),
+                                w[r][0], w[r][1], w[r][2]);
+                    grey4_words(out_byte_bits(v[r][4]), out_byte_bits(v[r][5]), out_byte_bits(v[r][6]), out_byte_bits(v[r][7]),
+                                w[r][3], w[r][4], w[r][5]);
+                }
+            } else {
+                // MCO: quantise Y, Cr, Cb (motion_compression_opt.py:162-168); YCrCb -> BGR (:171); BGR -> gray, replicated (:181-183)
+                uint32_t q8[3][8][2];           // quantised channel bytes, 8 per row packed in two words
+                float v[8][8];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int b = byte_at(w[r], 3 * c), gg = byte_at(w[r], 3 * c + 1), rr = byte_at(w[r], 3 * c + 2);
+                            const int y = luma_of(b, gg, rr);
+                            int val = y;
+                            if (k == 1) val = sat8(((rr - y) * 11682 + (128 << 14) + 8192) >> 14);
+                            if (k == 2) val = sat8(((b - y) * 9241 + (128 << 14) + 8192) >> 14);
+                            v[r][c] = (float)(val - 128);
+                        }
+                    degrade_plane8(v, qp);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        q8[k][r][0] = out_byte_bits(v[r][0]) | (out_byte_bits(v[r][1]) << 8) | (out_byte_bits(v[r][2]) << 16) | (out_byte_bits(v[r][3]) << 24);
+                        q8[k][r][1] = out_byte_bits(v[r][4]) | (out_byte_bits(v[r][5]) << 8) | (out_byte_bits(v[r][6]) << 16) | (out_byte_bits(v[r][7]) << 24);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    uint32_t gy[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int y = (int)byte_at(q8[0][r], c), cr = (int)byte_at(q8[1][r], c) - 128, cb = (int)byte_at(q8[2][r], c) - 128;
+                        const int b = sat8(y + ((29049 * cb + 8192) >> 14));
+                        const int gg = sat8(y + ((-5636 * cb - 11698 * cr + 8192) >> 14));
+                        const int rr = sat8(y + ((22987 * cr + 8192) >> 14));
+                        gy[c] = gray_of(b, gg, rr);
+                    }
+                    grey4_words(gy[0], gy[1], gy[2], gy[3], w[r][0], w[r][1], w[r][2]);
+                    grey4_words(gy[4], gy[5], gy[6], gy[7], w[r][3], w[r][4], w[r][5]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    __stcs(reinterpret_cast<uint2*>(compressed + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
+        }
+    }
+    if (counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_motion += __shfl_xor_sync(0xffffffffu, n_motion, o);
+            n_static += __shfl_xor_sync(0xffffffffu, n_static, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (n_motion) atomicAdd(&counters->motion_pixels, (unsigned long long)n_motion);
+            if (n_static) atomicAdd(&counters->static_blocks, (unsigned long long)n_static);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row-span version (default when the geometry allows): a CTA owns whole 4-pixel-high block rows (or an exact
 // part of one for W > 2048), i.e. one contiguous span of the frame.  HBM only ever sees large bulk operations:
 //   * the span (<= 24 KB) and its two mask-plane row groups arrive by cp.async.bulk (TMA) on one mbarrier;
