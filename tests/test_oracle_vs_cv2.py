@@ -196,3 +196,20 @@ def test_overlay():
     ov = so.overlay_paint(frame, acc)
     assert np.array_equal(ov[acc > 127], np.tile(np.array([0, 0, 255], np.uint8), ((acc > 127).sum(), 1)))
     assert np.array_equal(ov[acc <= 127], frame[acc <= 127])
+
+
+def test_markstein_quotient():
+    """K4 forms np.round(d / q)'s quotient without a division: y0 = d * r, e = fma(-q, y0, d), y = fma(e, r, y0) with
+    r = float32(1 / q) equals the IEEE float32 quotient d / q (k_degrade4p.cuh::quantise_t).  fma is emulated in
+    float64: the products of two float32 are exact there and the sums below stay inside 53 bits for this value range."""
+    rng = _rng(77)
+    d = np.concatenate([rng.integers(-8192, 8193, 400000).astype(np.float32),
+                        (rng.standard_normal(400000) * 300).astype(np.float32)])
+    for q in (0.25, 0.3, 1.0, 3.0, 7.3, 10.0, 33.333, 100.0, 127.0, 250.0, 1000.5):
+        for ne in (0, 1, 2):
+            qs = np.float32(q) * np.float32(1 << ne)
+            r = np.float32(1.0) / qs
+            y0 = d * r
+            e = (d.astype(np.float64) - qs.astype(np.float64) * y0.astype(np.float64)).astype(np.float32)
+            y = (y0.astype(np.float64) + e.astype(np.float64) * np.float64(r)).astype(np.float32)
+            assert np.array_equal(y, d / qs), (q, ne)
