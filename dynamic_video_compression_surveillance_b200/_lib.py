@@ -21,7 +21,7 @@ class DvcConfig(C.Structure):
                 ("motion_threshold", C.c_float), ("min_area", C.c_double), ("kernel_size", C.c_int32),
                 ("release_factor", C.c_double), ("quantization_level", C.c_float), ("window_size", C.c_int32),
                 ("alpha_fraction", C.c_double), ("morph_kernel", C.c_int32), ("morph_shape", C.c_int32),
-                ("max_batch", C.c_int32), ("device", C.c_int32)]
+                ("max_batch", C.c_int32), ("device", C.c_int32), ("src_width", C.c_int32), ("src_height", C.c_int32)]
 
 
 class DvcCounters(C.Structure):
@@ -67,6 +67,7 @@ SYMBOLS = {
     "dvc_morph_u8": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "dvc_contour_filter_u8": (C.c_int, [_P, _P, _I, _I, _I, _D, _P]),
     "dvc_mask_rectangles_u8": (C.c_int, [_P, _P, _I, _I, _I, _P]),
+    "dvc_resize_linear_u8": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "dvc_degrade_blend_u8": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
 }
 

@@ -223,6 +223,61 @@ static void ccl_scratch_free(CclScratch& sc) {
     sc = CclScratch();
 }
 
+// ------------------------------------------------------------------------------------------------
+// cv2.resize INTER_LINEAR tables (OpenCV resize(): scale = 1 / ((double)dst / src); fx = (float)((d + 0.5) * scale - 0.5);
+// sx = floor(fx); fx -= sx; columns clamp (sx, fx) at the image border, rows keep fx and clip the row index instead;
+// coefficients = cvRound(float * 2048))
+// ------------------------------------------------------------------------------------------------
+struct ResizeHostTables { std::vector<int> xofs, yofs; std::vector<short> xa, yb; };
+static void make_resize_tables(int sH, int sW, int dH, int dW, ResizeHostTables& t) {
+    auto fill = [](int sn, int dn, bool clamp, std::vector<int>& ofs, std::vector<short>& co) {
+        ofs.resize(dn); co.resize(2 * (size_t)dn);
+        const double inv = (double)dn / sn, scale = 1.0 / inv;
+        for (int d = 0; d < dn; ++d) {
+            float f = (float)((d + 0.5) * scale - 0.5);
+            int i = (int)std::floor(f);
+            f -= (float)i;
+            if (clamp) {
+                if (i < 0) { i = 0; f = 0.0f; }
+                if (i >= sn - 1) { i = sn - 1; f = 0.0f; }
+            }
+            ofs[d] = i;
+            co[2 * d] = (short)lrintf((1.0f - f) * 2048.0f);
+            co[2 * d + 1] = (short)lrintf(f * 2048.0f);
+        }
+    };
+    fill(sW, dW, true, t.xofs, t.xa);
+    fill(sH, dH, false, t.yofs, t.yb);
+}
+// device copy of the tables in one allocation: [xofs dW ints][yofs dH ints][xa dW short2][yb dH short2]
+static size_t resize_tables_bytes(int dH, int dW) { return (size_t)(dW + dH) * (sizeof(int) + sizeof(short2)); }
+static ResizeTables resize_tables_view(void* dev, int dH, int dW) {
+    ResizeTables v;
+    char* p = (char*)dev;
+    v.xofs = (const int*)p; p += (size_t)dW * sizeof(int);
+    v.yofs = (const int*)p; p += (size_t)dH * sizeof(int);
+    v.xa = (const short2*)p; p += (size_t)dW * sizeof(short2);
+    v.yb = (const short2*)p;
+    return v;
+}
+static void resize_tables_pack(const ResizeHostTables& t, int dH, int dW, std::vector<char>& blob) {
+    blob.resize(resize_tables_bytes(dH, dW));
+    char* p = blob.data();
+    memcpy(p, t.xofs.data(), (size_t)dW * sizeof(int)); p += (size_t)dW * sizeof(int);
+    memcpy(p, t.yofs.data(), (size_t)dH * sizeof(int)); p += (size_t)dH * sizeof(int);
+    memcpy(p, t.xa.data(), (size_t)dW * sizeof(short2)); p += (size_t)dW * sizeof(short2);
+    memcpy(p, t.yb.data(), (size_t)dH * sizeof(short2));
+}
+static int launch_resize(char* ERRBUF, const uint8_t* src, uint8_t* dst, int n, int sH, int sW, int dH, int dW, int cn,
+                         const ResizeTables& t, cudaStream_t st) {
+    dim3 grid(cdiv((size_t)dW * dH, 256), n);
+    if (cn == 3) k_resize_linear<3><<<grid, 256, 0, st>>>(src, dst, sH, sW, dH, dW, t);
+    else if (cn == 1) k_resize_linear<1><<<grid, 256, 0, st>>>(src, dst, sH, sW, dH, dW, t);
+    else return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "resize: %d channels (1 or 3 supported)", cn);
+    CHECK_LAUNCH();
+    return DVC_OK;
+}
+
 static bool g_dct8_ready = false;
 static int ensure_dct8(char* ERRBUF) {
     if (g_dct8_ready) return DVC_OK;
@@ -424,6 +479,10 @@ struct dvc_handle {
     cudaStream_t s_h2d, s_d2h;
     cudaEvent_t ev_h2d[2], ev_d2h[2];
     uint8_t *st_in[2], *st_ov[2], *st_cp[2], *st_mask[2];
+    uint8_t* st_src[2];           // source-size upload buffers when the handle resizes (cfg.src_width / src_height)
+    void* resize_tables;          // device copy of the cv2.resize tables
+    bool resizing;
+    size_t src_frame_bytes;
     bool staging;
     // profiling: CUDA events around each kernel group, on the launching stream
     bool prof;
@@ -441,6 +500,7 @@ static int alloc_staging(dvc_handle* h) {
         CU(cudaMalloc(&h->st_ov[b], fb));
         CU(cudaMalloc(&h->st_cp[b], fb));
         CU(cudaMalloc(&h->st_mask[b], h->plane_bytes * h->cfg.max_batch));
+        if (h->resizing) CU(cudaMalloc(&h->st_src[b], h->src_frame_bytes * h->cfg.max_batch));
         CU(cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
     }
@@ -486,6 +546,17 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     const char* gd = getenv("DVC_GRAY_IMPL");
     h->gray_impl = gd ? atoi(gd) : 2;
     CU(cudaSetDevice(cfg->device));
+    h->resizing = cfg->src_width > 0 && cfg->src_height > 0 && (cfg->src_width != cfg->width || cfg->src_height != cfg->height);
+    h->src_frame_bytes = h->resizing ? (size_t)cfg->src_width * cfg->src_height * 3 : h->frame_bytes;
+    h->resize_tables = nullptr;
+    if (h->resizing) {
+        ResizeHostTables ht;
+        make_resize_tables(cfg->src_height, cfg->src_width, h->H, h->W, ht);
+        std::vector<char> blob;
+        resize_tables_pack(ht, h->H, h->W, blob);
+        CU(cudaMalloc(&h->resize_tables, blob.size()));
+        CU(cudaMemcpy(h->resize_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    }
     for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&h->prev_gray[i], h->plane_bytes)); CU(cudaMemset(h->prev_gray[i], 0, h->plane_bytes)); }
     for (int s = 0; s < 2; ++s)
         for (int k = 0; k < 3; ++k) {
@@ -534,7 +605,7 @@ extern "C" int dvc_destroy(dvc_handle* h) {
     cudaDeviceSynchronize();
     cudaFree(h->prev_gray[0]); cudaFree(h->prev_gray[1]); cudaFree(h->acc); cudaFree(h->ring);
     for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(h->bits[s][k]);
-    cudaFree(h->blurred); cudaFree(h->counters_dev);
+    cudaFree(h->blurred); cudaFree(h->counters_dev); cudaFree(h->resize_tables);
     if (h->s_mask) cudaStreamDestroy(h->s_mask);
     if (h->s_k4) cudaStreamDestroy(h->s_k4);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
@@ -543,6 +614,7 @@ extern "C" int dvc_destroy(dvc_handle* h) {
     if (h->staging) {
         for (int b = 0; b < 2; ++b) {
             cudaFree(h->st_in[b]); cudaFree(h->st_ov[b]); cudaFree(h->st_cp[b]); cudaFree(h->st_mask[b]);
+            if (h->resizing) cudaFree(h->st_src[b]);
             cudaEventDestroy(h->ev_h2d[b]); cudaEventDestroy(h->ev_d2h[b]);
         }
         cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h);
@@ -883,6 +955,14 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
         const int T = (int)std::min<int64_t>(Tc, n_frames - f0);
         // the input buffer is free once the degrade kernel that read it (chunk c-2) is done
         if (c >= 2) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_k4[b], 0));
+        if (h->resizing) {
+            // frames arrive at the capture's size: upload, then the reference's cv2.resize (frame_differencing.py:91) on the GPU
+            CU(cudaMemcpyAsync(h->st_src[b], frames_host + (size_t)f0 * h->src_frame_bytes, (size_t)T * h->src_frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+            rc = launch_resize(h->err, h->st_src[b], h->st_in[b], T, h->cfg.src_height, h->cfg.src_width, h->H, h->W, 3,
+                               resize_tables_view(h->resize_tables, h->H, h->W), h->s_h2d);
+            if (rc) { cudaDeviceSynchronize(); return rc; }
+            h->launches += 1;
+        } else
         CU(cudaMemcpyAsync(h->st_in[b], frames_host + (size_t)f0 * h->frame_bytes, (size_t)T * h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
         CU(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
         CU(cudaStreamWaitEvent(h->s_mask, h->ev_h2d[b], 0));
@@ -1087,6 +1167,26 @@ extern "C" int dvc_contour_filter_u8(const uint8_t* src, uint8_t* dst, int32_t n
     rc = launch_contour_filter(nullptr, (const uint32_t*)a.p, (uint32_t*)b.p, n, H, W, min_area, sc, st);
     if (rc) return rc;
     return unpack_from_bits((const uint32_t*)b.p, dst, n, H, W, st);
+}
+
+extern "C" int dvc_resize_linear_u8(const uint8_t* src, uint8_t* dst, int32_t n, int32_t src_h, int32_t src_w, int32_t dst_h,
+                                    int32_t dst_w, int32_t channels, void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, src_h, src_w, "dvc_resize_linear_u8");
+    if (rc || n == 0) return rc;
+    if (dst_h <= 0 || dst_w <= 0) return set_err(nullptr, DVC_ERR_INVALID, "dvc_resize_linear_u8: bad destination size %dx%d", dst_w, dst_h);
+    if (!src || !dst) return set_err(nullptr, DVC_ERR_INVALID, "dvc_resize_linear_u8: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    ResizeHostTables ht;
+    make_resize_tables(src_h, src_w, dst_h, dst_w, ht);
+    std::vector<char> blob;
+    resize_tables_pack(ht, dst_h, dst_w, blob);
+    ScopedAsyncBuf tb(st);
+    CU(tb.alloc(blob.size()));
+    CU(cudaMemcpyAsync(tb.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+    rc = launch_resize(nullptr, src, dst, n, src_h, src_w, dst_h, dst_w, channels, resize_tables_view(tb.p, dst_h, dst_w), st);
+    CU(cudaStreamSynchronize(st));          // the pageable host blob must outlive the copy
+    return rc;
 }
 
 extern "C" int dvc_mask_rectangles_u8(const uint8_t* src, uint8_t* dst, int32_t n, int32_t H, int32_t W, void* stream) {

@@ -307,4 +307,39 @@ k_unpack_bits(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst, int H
     else store_u8x16_generic(row, x0, W, v);
 }
 
+// ------------------------------------------------------------------------------------------------
+// cv2.resize(frame, (w, h)) with the default INTER_LINEAR on uint8 (frame_differencing.py:74,91): two-pass fixed
+// point with 11-bit coefficients.  Host tables (make_resize_tables in dvc_b200.cu) hold, per output column, the left
+// source column and the coefficient pair (a0, a1), per output row the top source row and (b0, b1), computed with the
+// float / double expressions of OpenCV so the integers are the same.  Per output value:
+//     h_r = S[r][x0] * a0 + S[r][x1] * a1              (r = the two source rows, clipped to the image)
+//     out = (((b0 * (h_0 >> 4)) >> 16) + ((b1 * (h_1 >> 4)) >> 16) + 2) >> 2
+// Checked bit for bit against cv2 for down- and upscales (oracle/stage_ops.py::resize_linear).
+// One thread per output pixel (all channels); grid (ceil(dW * dH / 256), n).
+// ------------------------------------------------------------------------------------------------
+struct ResizeTables { const int* xofs; const short2* xa; const int* yofs; const short2* yb; };
+
+template <int CN>
+__global__ void __launch_bounds__(256)
+k_resize_linear(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int sH, int sW, int dH, int dW, ResizeTables t) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= dW * dH) return;
+    const int dy = gid / dW, dx = gid - dy * dW;
+    const int x0 = t.xofs[dx], x1 = min(x0 + 1, sW - 1);
+    const short2 a = t.xa[dx], b = t.yb[dy];
+    const int sy = t.yofs[dy];
+    const int y0 = min(max(sy, 0), sH - 1), y1 = min(max(sy + 1, 0), sH - 1);
+    const uint8_t* s = src + (size_t)blockIdx.y * sH * sW * CN;
+    const uint8_t* r0 = s + (size_t)y0 * sW * CN;
+    const uint8_t* r1 = s + (size_t)y1 * sW * CN;
+    uint8_t* o = dst + ((size_t)blockIdx.y * dH * dW + gid) * CN;
+#pragma unroll
+    for (int c = 0; c < CN; ++c) {
+        const int h0 = (int)r0[x0 * CN + c] * a.x + (int)r0[x1 * CN + c] * a.y;
+        const int h1 = (int)r1[x0 * CN + c] * a.x + (int)r1[x1 * CN + c] * a.y;
+        const int v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[c] = (uint8_t)min(255, max(0, v));
+    }
+}
+
 }  // namespace dvc

@@ -4,8 +4,8 @@ reference's GUI and performance_analysis.py depend on (file names, ``execution_t
 Design (not the reference's): a decode thread fills pinned batch buffers from cv2.VideoCapture, the GPU loop runs
 per batch through ``FramePipeline.process_host`` (upload / kernels / download double-buffered inside the library),
 an encode thread feeds the two VideoWriters.  What stays on the host is what SURVEY.md section 8 leaves
-there: codecs, the optional resize (frame_differencing.py:74,91), the first frame's heavy blur (:77), Farneback
-flow (motion_compression_opt.py:72-82) and contour -> rectangle drawing (:93-97).
+there: codecs, the first frame's resize + heavy blur (frame_differencing.py:74,77; once per stream), Farneback
+flow (motion_compression_opt.py:72-82).
 """
 from __future__ import annotations
 
@@ -74,7 +74,9 @@ def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int
     run = FdRun()
     n_sets = 3 if threaded else 1
     shape = (max_batch, h, w, 3)
-    sets = [dict(inp=P.pinned_empty(shape), ov=P.pinned_empty(shape), cp=P.pinned_empty(shape)) for _ in range(n_sets)]
+    src_w, src_h = first_frame.shape[1], first_frame.shape[0]      # scale_factor != 1: frames are uploaded as decoded and
+    in_shape = (max_batch, src_h, src_w, 3)                          # resized on the GPU (frame_differencing.py:91)
+    sets = [dict(inp=P.pinned_empty(in_shape), ov=P.pinned_empty(shape), cp=P.pinned_empty(shape)) for _ in range(n_sets)]
     for st in sets:
         st["inp_v"], st["ov_v"], st["cp_v"] = st["inp"].numpy(), st["ov"].numpy(), st["cp"].numpy()
     free_q, ready_q = queue.Queue(), queue.Queue(maxsize=n_sets)
@@ -91,8 +93,6 @@ def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int
             ok, frame = cap.read()
             if not ok:
                 break
-            if (frame.shape[1], frame.shape[0]) != (w, h):
-                frame = cv2.resize(frame, (w, h))             # scale_factor != 1 (frame_differencing.py:91)
             st["inp_v"][n] = frame
             n += 1
         return n
@@ -149,7 +149,7 @@ def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int
             while enc_q[k].get() is not None:                    # keep the pipeline from blocking
                 pass
 
-    with P.FramePipeline(w, h, "fd", max_batch=max_batch, device=device, **params) as pipe:
+    with P.FramePipeline(w, h, "fd", max_batch=max_batch, device=device, src_size=(src_w, src_h), **params) as pipe:
         pipe.begin_stream(seed)
         if not threaded:
             st = sets[0]

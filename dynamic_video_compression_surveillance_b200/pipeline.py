@@ -51,7 +51,8 @@ class FramePipeline:
     def __init__(self, width: int, height: int, mode: str = "fd", *, block_size: int = 4, motion_threshold: float = 0.5,
                  min_area: float = 500, kernel_size: int = 7, release_factor: float = 0.5,
                  quantization_level: float = 100, window_size: int = 30, alpha_fraction: float = 0.2,
-                 morph_kernel: int = 2, morph_shape: str = "ellipse", max_batch: int = 16, device: int | None = None):
+                 morph_kernel: int = 2, morph_shape: str = "ellipse", max_batch: int = 16, device: int | None = None,
+                 src_size: tuple | None = None):
         _require_cuda()
         self._lib = _lib.load()
         self.width, self.height, self.mode = int(width), int(height), mode
@@ -65,6 +66,10 @@ class FramePipeline:
         cfg.window_size, cfg.alpha_fraction = int(window_size), float(alpha_fraction)
         cfg.morph_kernel, cfg.morph_shape = int(morph_kernel), _SHAPES[morph_shape]
         cfg.max_batch, cfg.device = int(max_batch), self.device
+        # frames given to process_host at another size (width, height): the library resizes them as cv2.resize does
+        self.src_width, self.src_height = (int(src_size[0]), int(src_size[1])) if src_size else (self.width, self.height)
+        if (self.src_width, self.src_height) != (self.width, self.height):
+            cfg.src_width, cfg.src_height = self.src_width, self.src_height
         self.cfg = cfg
         self.max_batch = int(max_batch)
         self._h = C.c_void_p()
@@ -180,7 +185,7 @@ class FramePipeline:
             return a.ctypes.data
         n = int(frames.shape[0])
         fshape = (n, self.height, self.width, 3)
-        self._check(self._lib.dvc_process_host(self._h, host_ptr(frames, fshape, "frames"), n,
+        self._check(self._lib.dvc_process_host(self._h, host_ptr(frames, (n, self.src_height, self.src_width, 3), "frames"), n,
                                                host_ptr(overlay, fshape, "overlay"),
                                                host_ptr(compressed, fshape, "compressed"),
                                                host_ptr(mask, fshape[:3], "mask")))
@@ -254,6 +259,17 @@ def contour_filter(masks: torch.Tensor, min_area: float = 500) -> torch.Tensor:
     n, h, w = masks.shape
     out = torch.empty_like(masks)
     _lib_call("dvc_contour_filter_u8", masks.data_ptr(), out.data_ptr(), n, h, w, float(min_area), _stream_ptr(None))
+    return out
+
+
+def resize_linear(images: torch.Tensor, dsize_wh) -> torch.Tensor:
+    """cv2.resize(img, (w, h)) (INTER_LINEAR, uint8) on [N,H,W,3] or [N,H,W] images (frame_differencing.py:74,91)."""
+    _dev_u8(images, "images")
+    n, h, w = images.shape[:3]
+    cn = 1 if images.dim() == 3 else int(images.shape[3])
+    dw, dh = int(dsize_wh[0]), int(dsize_wh[1])
+    out = torch.empty((n, dh, dw) if images.dim() == 3 else (n, dh, dw, cn), dtype=torch.uint8, device=images.device)
+    _lib_call("dvc_resize_linear_u8", images.data_ptr(), out.data_ptr(), n, h, w, dh, dw, cn, _stream_ptr(None))
     return out
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DVC_ABI_VERSION 1
+#define DVC_ABI_VERSION 2
 
 enum {
     DVC_OK = 0,
@@ -74,6 +74,9 @@ typedef struct dvc_config {
     int32_t morph_shape;          /* DVC_SHAPE_ELLIPSE as in motion_compression_opt.py:62 */
     int32_t max_batch;            /* frames per device batch / pipelined host chunk (>= 1) */
     int32_t device;               /* CUDA device ordinal */
+    int32_t src_width, src_height; /* 0, or the size of the frames handed to dvc_process_host when it differs from
+                                    * width x height: the library then does the reference's cv2.resize (default
+                                    * INTER_LINEAR, frame_differencing.py:74,91) on the GPU after the upload */
 } dvc_config;
 
 typedef struct dvc_handle dvc_handle;
@@ -174,6 +177,11 @@ int dvc_morph_u8(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n, int32_t H,
  * frame_differencing.py:100-104.  n images. */
 int dvc_contour_filter_u8(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n, int32_t H, int32_t W,
                           double min_area, void* stream);
+/* cv2.resize(src, (dst_w, dst_h)) with the default INTER_LINEAR on uint8, frame_differencing.py:74,91 (scale_factor != 1):
+ * OpenCV's 11-bit fixed-point bilinear, bit for bit.  n images [src_h][src_w][channels] -> [dst_h][dst_w][channels],
+ * channels 1 or 3. */
+int dvc_resize_linear_u8(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n, int32_t src_h, int32_t src_w, int32_t dst_h,
+                         int32_t dst_w, int32_t channels, void* stream);
 /* findContours(RETR_EXTERNAL) + boundingRect + rectangle((x, y), (x + w, y + h), 255, FILLED),
  * motion_compression_opt.py:93-97: every 8-connected component is replaced by its bounding rectangle
  * grown by one column and one row (cv2.rectangle includes both corners), clipped to the image.  n images. */

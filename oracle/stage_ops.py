@@ -271,6 +271,38 @@ def contour_filter_cv2(mask: np.ndarray, min_area: float) -> np.ndarray:
     return out
 
 
+def resize_linear(src: np.ndarray, dsize_wh) -> np.ndarray:
+    """cv2.resize(src, (w, h)) with the default INTER_LINEAR on uint8 (frame_differencing.py:74,91), restated:
+    OpenCV's two-pass fixed-point bilinear with 11-bit coefficients.  Columns clamp (index, fraction) at the border,
+    rows keep the fraction and clip the row index; out = (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2."""
+    dw, dh = int(dsize_wh[0]), int(dsize_wh[1])
+    sh, sw = src.shape[:2]
+    s = src.reshape(sh, sw, -1).astype(np.int64)
+
+    def tables(dn, sn, clamp):
+        scale = 1.0 / (dn / sn)
+        d = np.arange(dn, dtype=np.float64)
+        f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+        i = np.floor(f).astype(np.int64)
+        f = (f - i.astype(np.float32)).astype(np.float32)
+        if clamp:
+            lo, hi = i < 0, i >= sn - 1
+            i = np.where(lo, 0, np.where(hi, sn - 1, i))
+            f = np.where(lo | hi, np.float32(0), f).astype(np.float32)
+        a0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int64)
+        a1 = np.rint(f * np.float32(2048)).astype(np.int64)
+        return i, a0, a1
+
+    xi, a0, a1 = tables(dw, sw, True)
+    yi, b0, b1 = tables(dh, sh, False)
+    x1 = np.minimum(xi + 1, sw - 1)
+    rows = s[:, xi, :] * a0[None, :, None] + s[:, x1, :] * a1[None, :, None]
+    r0, r1 = rows[np.clip(yi, 0, sh - 1)], rows[np.clip(yi + 1, 0, sh - 1)]
+    out = (((b0[:, None, None] * (r0 >> 4)) >> 16) + ((b1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    out = np.clip(out, 0, 255).astype(np.uint8)
+    return out.reshape((dh, dw) if src.ndim == 2 else (dh, dw, src.shape[2]))
+
+
 def mask_rectangles(mask: np.ndarray) -> np.ndarray:
     """contours -> bounding rectangles (motion_compression_opt.py:93-97), restated without contour tracing:
     every 8-connected component is replaced by the rectangle columns min_x..max_x+1, rows min_y..max_y+1

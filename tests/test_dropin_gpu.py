@@ -99,6 +99,27 @@ def test_process_single_video_fd(tmp_path, dropin_modules):
     assert os.path.exists(os.path.join(str(tmp_path / "out2"), "cam0", "execution_times.txt"))
 
 
+def test_fd_scale_factor_resizes_on_gpu(tmp_path, dropin_modules):
+    """The reference's __main__ configuration (frame_differencing.py:198-208: block_size 8, scale_factor 0.5): frames are
+    uploaded at the capture size and resized by the library (cv2.resize default interpolation, bit for bit), so the loop
+    statistics must equal the oracle's on cv2-resized decoded frames."""
+    fd, _ = dropin_modules
+    h, w, n = 192, 256, 40
+    src = str(tmp_path / "cam2.mp4")
+    _write_clip(src, _smooth_clip(h, w, n, 7))
+    decoded = _read_all(src)
+    stats = {}
+    out_dir = str(tmp_path / "out")
+    fd.filter_and_dilate_movements(src, out_dir, block_size=8, scale_factor=0.5, stats_out=stats, max_batch=16)
+    vdir = os.path.join(out_dir, "cam2")
+    outs = _read_all(os.path.join(vdir, "compressed_final_video.mp4"))
+    assert len(outs) == n - 1 and outs[0].shape[:2] == (h // 2, w // 2)
+    small = [cv2.resize(f, (w // 2, h // 2)) for f in decoded]
+    ref = loops.fd_loop(small, block_size=8, degrade=False)
+    assert stats["frames"] == n - 1
+    assert stats["motion_pixels"] == int(sum((a > 127).sum() for a in ref["acc"]))
+
+
 def test_fd_error_convention(tmp_path, dropin_modules):
     fd, _ = dropin_modules
     assert fd.process_single_video_fd(str(tmp_path / "missing.mp4"), str(tmp_path / "o")) is None     # logs, never raises

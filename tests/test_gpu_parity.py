@@ -181,6 +181,23 @@ def test_mask_rectangles_1080p(P):
         assert np.array_equal(got[k], so.mask_rectangles_cv2(m[k]))
 
 
+@pytest.mark.parametrize("shape", [(48, 64), (120, 160), (37, 53), (270, 480), (1080, 1920)])
+def test_resize_linear(P, shape):
+    r = rng(56)
+    h, w = shape
+    img = r.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    for sf in ((0.5, 1.5, 0.3) if h >= 1080 else (0.5, 0.75, 0.3, 0.9, 0.25, 0.6, 0.99, 0.123, 1.0, 1.1, 1.5, 2.0)):
+        dw, dh = int(w * sf), int(h * sf)
+        if dw < 1 or dh < 1:
+            continue
+        got = host(P.resize_linear(dev(img), (dw, dh)))
+        for i in range(2):
+            assert np.array_equal(got[i], cv2.resize(img[i], (dw, dh))), (shape, sf, i)
+    g = np.ascontiguousarray(img[..., 1])
+    got = host(P.resize_linear(dev(g), (w // 2, h // 2)))
+    assert np.array_equal(got[0], cv2.resize(g[0], (w // 2, h // 2)))
+
+
 def test_contour_filter_1080p_blobs(P):
     r = rng(10)
     m = np.zeros((1080, 1920), np.uint8)

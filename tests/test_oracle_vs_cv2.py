@@ -213,3 +213,19 @@ def test_markstein_quotient():
             e = (d.astype(np.float64) - qs.astype(np.float64) * y0.astype(np.float64)).astype(np.float32)
             y = (y0.astype(np.float64) + e.astype(np.float64) * np.float64(r)).astype(np.float32)
             assert np.array_equal(y, d / qs), (q, ne)
+
+
+@pytest.mark.parametrize("shape", [(48, 64), (120, 160), (37, 53), (270, 480)])
+def test_resize_linear(shape):
+    """frame_differencing.py:74,91: cv2.resize default interpolation on uint8, incl. the __main__ scale 0.5."""
+    import cv2
+    rng = _rng(55)
+    h, w = shape
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    for sf in (0.5, 0.75, 0.3, 0.9, 0.25, 0.6, 0.99, 0.123, 1.0, 1.1, 1.5, 2.0):
+        dw, dh = int(w * sf), int(h * sf)
+        if dw < 1 or dh < 1:
+            continue
+        assert np.array_equal(so.resize_linear(img, (dw, dh)), cv2.resize(img, (dw, dh))), (shape, sf)
+    g = img[..., 0].copy()
+    assert np.array_equal(so.resize_linear(g, (w // 2, h // 2)), cv2.resize(g, (w // 2, h // 2)))
