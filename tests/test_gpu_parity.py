@@ -277,8 +277,10 @@ def test_degrade_fd_quantiser_ties_and_levels(P, q):
         assert np.array_equal(comp[i], so.degrade_fd(frames[i], acc[i], 4, q)), (q, i)
 
 
-@pytest.mark.parametrize("shape", [(48, 72), (8, 8), (4, 24), (100, 104)])
+@pytest.mark.parametrize("shape", [(48, 72), (8, 8), (4, 24), (100, 104), (8, 2064), (12, 2056), (8, 4112), (4, 16), (260, 16)])
 def test_degrade_fd_widths_multiple_of_8(P, shape):
+    # (8, 2064): row split into uneven parts; (12, 2056): W > 2048 and W % 16 != 0 (falls back to the non-ring kernel);
+    # (260, 16): many block rows per tile, last tile of a frame shorter
     r = rng(22)
     exact = so.cv2_dct4_matches_closed_form()
     frames = r.integers(0, 256, (2,) + shape + (3,), dtype=np.uint8)
@@ -288,6 +290,30 @@ def test_degrade_fd_widths_multiple_of_8(P, shape):
     for i in range(2):
         assert np.array_equal(ov[i], so.overlay_paint(frames[i], acc[i]))
         _check_degraded(comp[i], so.degrade_fd(frames[i], acc[i], 4, 100), frames[i], acc[i], 4, 100, exact)
+
+
+def test_degrade_fd_ring_wraps_many_tiles_per_cta(P):
+    """The persistent K4 walks ~20 tiles per CTA here (24 frames x 120 block rows over 148 CTAs), so every stage of its
+    shared-memory ring is reused several times with both barrier parities; moving rectangles put motion in many tiles."""
+    r = rng(23)
+    n, h, w = 24, 480, 640
+    exact = so.cv2_dct4_matches_closed_form()
+    frames = r.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    acc = np.zeros((n, h, w), np.uint8)
+    for i in range(n):
+        for k in range(3):
+            y, x = int(r.integers(0, h - 60)), int(r.integers(0, w - 90))
+            acc[i, y:y + int(r.integers(5, 60)), x:x + int(r.integers(5, 90))] = int(r.integers(1, 256))
+    cnt = torch.zeros(5, dtype=torch.int64, device="cuda")
+    comp, ov = P.degrade_blend(dev(frames), dev(acc), 4, 100, "fd", True, counters=cnt)
+    comp, ov = host(comp), host(ov)
+    for i in range(n):
+        assert np.array_equal(ov[i], so.overlay_paint(frames[i], acc[i])), i
+        _check_degraded(comp[i], so.degrade_fd(frames[i], acc[i], 4, 100), frames[i], acc[i], 4, 100, exact)
+    c = cnt.cpu().numpy()
+    assert c[2] == int((acc > 127).sum())
+    nz_blocks = (acc.reshape(n, h // 4, 4, w // 4, 4) != 0).any(axis=(2, 4))
+    assert c[4] == int((~nz_blocks).sum())
 
 
 def test_degrade_mco(P):
