@@ -971,6 +971,8 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
             CU(cudaStreamWaitEvent(h->s_mask, h->ev_d2h[b], 0));     // output staging of chunk c-2 downloaded
             CU(cudaStreamWaitEvent(h->s_k4, h->ev_d2h[b], 0));
         }
+        static const bool no_kernels = [] { const char* e = getenv("DVC_HOST_NOKERNEL"); return e && atoi(e) != 0; }();   // copy-pipeline probe
+        if (no_kernels) { CU(cudaEventRecord(h->ev_k4[b], h->s_k4)); h->ev_used[b] = true; rc = DVC_OK; } else
         rc = process_batch_impl(h, h->st_in[b], T, overlay_host ? h->st_ov[b] : nullptr, compressed_host ? h->st_cp[b] : nullptr,
                                 mask_host ? h->st_mask[b] : nullptr, h->s_mask, h->s_k4, b);
         if (rc) { cudaDeviceSynchronize(); return rc; }

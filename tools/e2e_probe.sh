@@ -1,7 +1,7 @@
-for c in 8 16 32; do
-  export DVC_HOST_CHUNK=$c
-  CUDA_VISIBLE_DEVICES=0 python tools/e2e_probe.py
-  export START_AT=$(python -c "import time; print(time.time() + 25)")
-  CUDA_VISIBLE_DEVICES=0 python tools/e2e_probe.py & CUDA_VISIBLE_DEVICES=1 python tools/e2e_probe.py & wait
-  unset START_AT
+# usage: bash tools/e2e_probe.sh "ENV=.. ENV=.." ...   : each argument is one configuration, run alone on GPU 0 and then on 2 GPUs at once
+for cfg in "$@"; do
+  echo "== $cfg"
+  env $cfg CUDA_VISIBLE_DEVICES=0 python tools/e2e_probe.py
+  START_AT=$(python -c "import time; print(time.time() + 25)")
+  env $cfg START_AT=$START_AT CUDA_VISIBLE_DEVICES=0 python tools/e2e_probe.py & env $cfg START_AT=$START_AT CUDA_VISIBLE_DEVICES=1 python tools/e2e_probe.py & wait
 done
