@@ -159,7 +159,8 @@ static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, 
     // large halo get bands at least twice the halo so the redundant rows stay under a third.
     const size_t row_bytes = 2 * (size_t)wpr * 4;
     const size_t limit = (size_t)g_morph_smem_limit - 64;
-    int band = (int)(36 * 1024 / row_bytes) - halo;
+    static const int target_kb = [] { const char* e = getenv("DVC_MORPH_SMEM_KB"); return e ? std::max(4, atoi(e)) : 36; }();
+    int band = (int)((size_t)target_kb * 1024 / row_bytes) - halo;
     band = std::max(band, std::max(16, 2 * halo));
     band = std::min<int>(band, (int)(limit / row_bytes) - halo);
     if (band < 1) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "morphology chain halo %d rows x %d words does not fit in shared memory", halo, wpr);
