@@ -94,6 +94,12 @@ DEVI void gray16_dp2a(const uint32_t (&w)[12], uint32_t (&g)[4]) {
 
 // per-byte |a - b| > thr  ->  4 mask bits (bit p = byte p).  thr < 128 uses a SWAR compare + multiply gather.
 DEVI uint32_t diff_gt_bits4(uint32_t a, uint32_t b, uint32_t thr) {
+    if (thr == 0u) {
+        // the reference's default (motion_threshold 0.5 -> diff > 0): a byte differs iff its XOR is non-zero
+        const uint32_t x = a ^ b;
+        const uint32_t m = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) >> 7;
+        return ((m * 0x00204081u) >> 21) & 0xfu;
+    }
     const uint32_t d = __vabsdiffu4(a, b);
     if (thr < 128u) {
         const uint32_t k7 = (0x7fu - thr) * 0x01010101u;

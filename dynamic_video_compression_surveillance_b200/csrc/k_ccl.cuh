@@ -77,7 +77,7 @@ DEVI int run_slot(uint32_t u, int p) { return __popc(run_starts(u) & (0xffffffff
 template <bool INVERT>
 DEVI uint32_t plane_word(const uint32_t* plane, int y, int j, int H, int W, int wpr) {
     if (y < 0 || y >= H || j < 0 || j >= wpr) return 0u;
-    const uint32_t w = plane[(size_t)y * wpr + j];
+    const uint32_t w = plane[y * wpr + j];
     return INVERT ? (~w & valid_mask(j, W)) : w;
 }
 
@@ -152,9 +152,9 @@ template <bool INVERT, int CONN>
 __global__ void __launch_bounds__(256)
 k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov, int H, int W, int wpr) {
     const size_t plane_words = (size_t)H * wpr;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= plane_words) return;
-    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
+    if (idx >= (uint32_t)plane_words) return;
+    const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
     if (y == 0) return;
     const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
@@ -208,9 +208,9 @@ __global__ void __launch_bounds__(256)
 k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov,
            uint32_t* __restrict__ filled, int H, int W, int wpr) {
     const size_t plane_words = (size_t)H * wpr;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= plane_words) return;
-    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
+    if (idx >= (uint32_t)plane_words) return;
+    const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     uint32_t m = plane_word<true>(planes + (size_t)blockIdx.y * plane_words, y, j, H, W, wpr);
     uint32_t outside = 0;
@@ -229,9 +229,9 @@ __global__ void __launch_bounds__(256)
 k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __restrict__ pov, int* __restrict__ a0,
            int* __restrict__ aov, int H, int W, int wpr) {
     const size_t plane_words = (size_t)H * wpr;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= plane_words) return;
-    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
+    if (idx >= (uint32_t)plane_words) return;
+    const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
     const uint32_t* F = filled + (size_t)blockIdx.y * plane_words;
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(256)
 k_ccl_select(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __restrict__ pov, int* __restrict__ a0,
              int* __restrict__ aov, uint32_t* __restrict__ out, int H, int W, int wpr, int twice_min_area_floor) {
     const size_t plane_words = (size_t)H * wpr;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= plane_words) return;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint32_t)plane_words) return;
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
     uint32_t m = filled[(size_t)blockIdx.y * plane_words + idx];
@@ -298,9 +298,9 @@ DEVI UF bbox_view(const BBoxArrays& b, int k, size_t plane_words, int frame) { r
 __global__ void __launch_bounds__(256)
 k_ccl_bbox(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov, BBoxArrays bb, int H, int W, int wpr) {
     const size_t plane_words = (size_t)H * wpr;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= plane_words) return;
-    const int y = (int)(idx / wpr), j = (int)(idx % wpr);
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
+    if (idx >= (uint32_t)plane_words) return;
+    const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     const UF MINX = bbox_view(bb, 0, plane_words, blockIdx.y), NMAXX = bbox_view(bb, 1, plane_words, blockIdx.y),
              NMAXY = bbox_view(bb, 2, plane_words, blockIdx.y);

@@ -114,7 +114,7 @@ k_bgr2gray(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, int H, i
         load16(fr + x0 * 3 + 16, *reinterpret_cast<uint32_t(*)[4]>(&w[4]));
         load16(fr + x0 * 3 + 32, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
     } else load_bgr16_generic(fr, x0, W, w);
-    gray16(w, g);
+    gray16_dp2a(w, g);
     if (ALIGNED) store16(out + x0, g);
     else store_u8x16_generic(out, x0, W, g);
 }
@@ -158,7 +158,7 @@ k_gray_blur5(const uint8_t* __restrict__ frames, uint8_t* __restrict__ blurred, 
             load16(row + x * 3 + 16, *reinterpret_cast<uint32_t(*)[4]>(&w[4]));
             load16(row + x * 3 + 32, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
         } else load_bgr16_generic(row, x, W, w);
-        gray16(w, gg);
+        gray16_dp2a(w, gg);
         *reinterpret_cast<uint4*>(&sg[r * BL_GP + BL_PAD + g * 16]) = make_uint4(gg[0], gg[1], gg[2], gg[3]);
     }
     __syncthreads();

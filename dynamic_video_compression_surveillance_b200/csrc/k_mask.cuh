@@ -85,6 +85,15 @@ __global__ void __launch_bounds__(256)
 k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t* __restrict__ over127,
       uint32_t* __restrict__ nonzero, uint8_t* __restrict__ acc_all, int T, int H, int W, int wpr, float alpha,
       float beta) {
+    __shared__ uint8_t s_lut[512];                           // [dilated bit][acc] -> acc'
+    {
+        const float on = __fmul_rn(255.0f, beta);
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+            const float sv = __fmaf_rn((float)(i & 255), alpha, (i >> 8) ? on : 0.0f);
+            s_lut[i] = (uint8_t)max(0, min(255, __float2int_rn(sv)));
+        }
+    }
+    __syncthreads();
     const int gpr = (W + 15) >> 4;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)gpr * H) return;
@@ -95,7 +104,9 @@ k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t*
     uint8_t* arow = acc + (size_t)y * W;
     if (ALIGNED) { uint4 t = *reinterpret_cast<const uint4*>(arow + x0); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
     else { for (int i = 0; i < 4; ++i) a[i] = 0; for (int i = 0; i < npx; ++i) a[i >> 2] |= (uint32_t)arow[x0 + i] << ((i & 3) * 8); }
-    const float on = __fmul_rn(255.0f, beta);
+    // accumulator update as a table: acc' depends only on (acc, dilated bit), so the float expression of cv2.addWeighted
+    // is evaluated once per CTA for the 2 x 256 cases (no int <-> float conversions, which run on the quarter-rate XU
+    // pipe, in the per-frame loop)
     for (int t = 0; t < T; ++t) {
         const size_t woff = (size_t)t * plane_words + (size_t)y * wpr;
         const uint32_t bits = reinterpret_cast<const uint16_t*>(dilated + woff)[gx];
@@ -107,15 +118,12 @@ k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t*
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     const int i = q * 4 + p;
-                    const float av = (float)((a[q] >> (8 * p)) & 0xffu);
-                    const float s = __fmaf_rn(av, alpha, ((bits >> i) & 1u) ? on : 0.0f);
-                    int v = __float2int_rn(s);
-                    v = max(0, min(255, v));
-                    nw |= (uint32_t)v << (8 * p);
-                    hi |= (v > 127 ? 1u : 0u) << i;
-                    nz |= (v != 0 ? 1u : 0u) << i;
+                    const uint32_t v = s_lut[(((bits >> i) & 1u) << 8) | ((a[q] >> (8 * p)) & 0xffu)];
+                    nw |= v << (8 * p);
                 }
                 a[q] = nw;
+                hi |= ((((nw >> 7) & 0x01010101u) * 0x00204081u >> 21) & 0xfu) << (4 * q);                                   // byte > 127
+                nz |= (((((nw | ((nw & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu) << (4 * q);  // byte != 0
             }
             if (npx < 16) { const uint32_t m = (1u << npx) - 1u; hi &= m; nz &= m; }
         }
