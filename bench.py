@@ -42,7 +42,7 @@ def parse_args():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--frames", type=int, default=1800)
     p.add_argument("--resolution", default="1080p")
-    p.add_argument("--max-batch", type=int, default=int(os.environ.get("DVC_BENCH_BATCH", "128")))
+    p.add_argument("--max-batch", type=int, default=int(os.environ.get("DVC_BENCH_BATCH", "225")))
     p.add_argument("--e2e-frames", type=int, default=256)
     p.add_argument("--mode", default="window", choices=["window", "fd"])
     p.add_argument("--no-cpu-baseline", action="store_true")

@@ -133,7 +133,15 @@ static void window_min_counts(double alpha, int K, MinCounts& mc) {
 // ------------------------------------------------------------------------------------------------
 // launch helpers (all asynchronous on `st`)
 // ------------------------------------------------------------------------------------------------
+// Function attributes and __constant__ uploads are per device: one-time set-up is tracked per CUDA device ordinal so that
+// handles on several GPUs in one process all get it.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() { int d = 0; cudaGetDevice(&d); d &= 63; if (done[d]) return false; done[d] = true; return true; }
+};
+
 static int g_morph_smem_limit = 0;
+static PerDeviceOnce g_morph_once;
 
 static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, int n, int H, int W,
                               const MorphChain& ch, cudaStream_t st) {
@@ -142,7 +150,7 @@ static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, 
         if (src != dst) CU(cudaMemcpyAsync(dst, src, (size_t)n * H * wpr * 4, cudaMemcpyDeviceToDevice, st));
         return DVC_OK;
     }
-    if (!g_morph_smem_limit) {
+    if (g_morph_once.need()) {
         int dev = 0, lim = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -279,16 +287,15 @@ static int launch_resize(char* ERRBUF, const uint8_t* src, uint8_t* dst, int n, 
     return DVC_OK;
 }
 
-static bool g_dct8_ready = false;
+static PerDeviceOnce g_dct8_once;
 static int ensure_dct8(char* ERRBUF) {
-    if (g_dct8_ready) return DVC_OK;
+    if (!g_dct8_once.need()) return DVC_OK;
     float t[8][4];
     const double pi = 3.14159265358979323846;
     for (int k = 0; k < 8; ++k)
         for (int n = 0; n < 4; ++n)
             t[k][n] = (float)((k == 0 ? std::sqrt(1.0 / 8.0) : 0.5) * std::cos(pi * (2 * n + 1) * k / 16.0));
     CU(cudaMemcpyToSymbol(c_dct8, t, sizeof(t)));
-    g_dct8_ready = true;
     return DVC_OK;
 }
 
@@ -318,11 +325,10 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         static const bool tma_env = [] { const char* e = getenv("DVC_K4_TMA_STORE"); return e ? atoi(e) != 0 : true; }();
         const bool tma = tma_env && W % 16 == 0;
         const size_t smem = tma ? (size_t)K4_STAGE_BYTES : 0;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_set;
+        if (attr_set.need()) {
             CU(cudaFuncSetAttribute(k_degrade4<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CU(cudaFuncSetAttribute(k_degrade4<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            attr_set = true;
         }
         static const bool packed_env = [] { const char* e = getenv("DVC_K4_PACKED"); return e ? atoi(e) != 0 : true; }();
         if (packed_env && q >= 0.01f && q <= 1.0e6f) {
@@ -334,12 +340,11 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                 qp.nqs[ne] = -qs;
                 qp.o[ne] = q / (float)(1 << ne);
             }
-            static bool attr_p = false;
-            if (!attr_p) {
+            static PerDeviceOnce attr_p;
+            if (attr_p.need()) {
                 CU(cudaFuncSetAttribute(k_degrade4p<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 CU(cudaFuncSetAttribute(k_degrade4r, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 CU(cudaFuncSetAttribute(k_degrade4r, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_p = true;
             }
             static const bool rowspan_env = [] { const char* e = getenv("DVC_K4_ROWSPAN"); return e ? atoi(e) != 0 : true; }();
             const int gpr = W / 8, nbr = H / 4;
@@ -389,14 +394,13 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                     sg.piece_bytes = env_piece > 0 ? ((env_piece + 15) & ~15) : 32768;
                     const size_t smem_s = smem_need(S);
                     const unsigned ctas = (unsigned)std::min(sg.n_tiles, env_ctas > 0 ? env_ctas : sms * cps);
-                    static bool attr_s = false;
-                    if (!attr_s) {
+                    static PerDeviceOnce attr_s;
+                    if (attr_s.need()) {
                         CU(cudaFuncSetAttribute(k_degrade4s<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                         CU(cudaFuncSetAttribute(k_degrade4s<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                         CU(cudaFuncSetAttribute(k_degrade4s<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                         CU(cudaFuncSetAttribute(k_degrade4s<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
                         CU(cudaFuncSetAttribute(k_degrade4s<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-                        attr_s = true;
                     }
                     if (cps == 2) k_degrade4s<2, 2><<<ctas, 32 + 512, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
                     else if (G == 1) k_degrade4s<1, 1><<<ctas, 32 + 256, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);

@@ -448,6 +448,33 @@ def test_two_stream_overlap_matches_strict_order(P):
         assert np.array_equal(res[1][2], np.stack(ref["mask" if mode == "window" else "acc"])), mode
 
 
+def test_handles_on_two_devices_in_one_process(P):
+    """One process driving several GPUs (the sharding module uses one process per GPU, the C ABI does not require it):
+    kernel attributes and constant tables are set up per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n = 96, 128, 20
+    frames = make_clip((h, w), n, seed=4).frames()
+    kw = dict(window_size=5, alpha_fraction=0.2, morph_kernel=2, kernel_size=7)
+    ref = loops.window_loop(list(frames), **kw)
+    ref8 = loops.fd_loop(list(frames), block_size=8, degrade=False)
+    for device in (1, 0):
+        pipe = P.FramePipeline(w, h, "window", max_batch=8, device=device, **kw)
+        pipe.begin_stream(so.bgr2gray(frames[0]))
+        ov = np.empty((n - 1, h, w, 3), np.uint8); cp = np.empty_like(ov); mk = np.empty((n - 1, h, w), np.uint8)
+        pipe.process_host(np.ascontiguousarray(frames[1:]), ov, cp, mk)
+        pipe.close()
+        assert np.array_equal(mk, np.stack(ref["mask"])), device
+        assert np.array_equal(ov, np.stack(ref["overlay"])), device
+        pipe = P.FramePipeline(w, h, "fd", max_batch=8, device=device, block_size=8)      # the 8x8 kernel's constant table
+        pipe.begin_stream(loops.first_frame_gray_fd(frames[0]))
+        pipe.process_host(np.ascontiguousarray(frames[1:]), ov, cp, mk)
+        pipe.close()
+        assert np.array_equal(mk, np.stack(ref8["acc"])), device
+    torch.cuda.set_device(0)
+
+
 def test_state_handoff_between_handles(P):
     """Frame-chunk sharding: a second handle continues a stream from a state blob."""
     from dynamic_video_compression_surveillance_b200.synth import make_clip
