@@ -434,7 +434,7 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
             QuantP qp;
             for (int ne = 0; ne < 3; ++ne) { qp.rcp[ne] = 1.0f / q; qp.nqs[ne] = -q; qp.o[ne] = q; }     // no folded scalings in the 8-point path
             if (flavour == DVC_DEGRADE_FD) k_degrade8<0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
-            else k_degrade8<1><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+            else k_degrade8<1><<<grid, 128, K8_SMEM_MCO, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
         } else
         if (flavour == DVC_DEGRADE_FD && bs == 4)
             k_degrade_generic<4, 0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, q, counters);

@@ -305,6 +305,19 @@ k_degrade4p(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ ove
 }
 
 
+DEVI void lds64(uint32_t saddr, uint32_t& a, uint32_t& b) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(saddr));
+}
+DEVI uint32_t lds_u8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+DEVI void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // block_size 8 (frame_differencing.py:203 main config; motion_compression_opt.py:152-183): one thread per 8x8 block,
 // 8 rows x 24 bytes moved with 8-byte vector loads / stores (a warp covers 768 contiguous bytes per row), the pixels
@@ -348,8 +361,13 @@ DEVI void degrade_plane8(float (&v)[8][8], const QuantP& qp) {
     }
 }
 
+// MCO keeps the thread's 8 x 24 input bytes and two quantised channel planes in shared memory ([row][thread], lane stride
+// 24 / 8 bytes: conflict-free) instead of registers, so the 64-float DCT block fits in 128 registers: 4 CTAs per SM instead
+// of the 2 a 255-register version gets.
+constexpr int K8_SMEM_MCO = 128 * (8 * 24 + 2 * 8 * 8);      // 40 960 bytes
+
 template <int FLAVOUR>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127, const uint32_t* __restrict__ nonzero,
            uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay, int H, int W, int wpr, QuantP qp,
            Counters* __restrict__ counters) {
@@ -436,34 +454,51 @@ k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
                 }
             } else {
                 // MCO: quantise Y, Cr, Cb (motion_compression_opt.py:162-168); YCrCb -> BGR (:171); BGR -> gray, replicated (:181-183)
-                uint32_t q8[3][8][2];           // quantised channel bytes, 8 per row packed in two words
-                float v[8][8];
+                extern __shared__ __align__(16) uint8_t k8_smem[];
+                const uint32_t sW = (uint32_t)__cvta_generic_to_shared(k8_smem) + threadIdx.x * 24u;           // + r * 128 * 24
+                const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(k8_smem) + 128u * 8u * 24u + threadIdx.x * 8u;   // + (k * 8 + r) * 128 * 8
 #pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) sts64(sW + r * (128 * 24) + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
+                float v[8][8];
+#pragma unroll 1
                 for (int k = 0; k < 3; ++k) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
+                    for (int r = 0; r < 8; ++r) {
+                        uint32_t x[6];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) lds64(sW + r * (128 * 24) + 8 * i, x[2 * i], x[2 * i + 1]);
+                        uint32_t ya[4], yb[4];
+                        luma4_bits(x[0], x[1], x[2], ya);
+                        luma4_bits(x[3], x[4], x[5], yb);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const int b = byte_at(w[r], 3 * c), gg = byte_at(w[r], 3 * c + 1), rr = byte_at(w[r], 3 * c + 2);
-                            const int y = luma_of(b, gg, rr);
+                            const int y = (int)((c < 4 ? ya[c] : yb[c - 4]) & 0xffu);
                             int val = y;
-                            if (k == 1) val = sat8(((rr - y) * 11682 + (128 << 14) + 8192) >> 14);
-                            if (k == 2) val = sat8(((b - y) * 9241 + (128 << 14) + 8192) >> 14);
+                            if (k == 1) val = sat8((((int)byte_at(x, 3 * c + 2) - y) * 11682 + (128 << 14) + 8192) >> 14);
+                            if (k == 2) val = sat8((((int)byte_at(x, 3 * c) - y) * 9241 + (128 << 14) + 8192) >> 14);
                             v[r][c] = (float)(val - 128);
                         }
+                    }
                     degrade_plane8(v, qp);
+                    if (k < 2) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        q8[k][r][0] = out_byte_bits(v[r][0]) | (out_byte_bits(v[r][1]) << 8) | (out_byte_bits(v[r][2]) << 16) | (out_byte_bits(v[r][3]) << 24);
-                        q8[k][r][1] = out_byte_bits(v[r][4]) | (out_byte_bits(v[r][5]) << 8) | (out_byte_bits(v[r][6]) << 16) | (out_byte_bits(v[r][7]) << 24);
+                        for (int r = 0; r < 8; ++r)
+                            sts64(sQ + (k * 8 + r) * (128 * 8),
+                                  out_byte_bits(v[r][0]) | (out_byte_bits(v[r][1]) << 8) | (out_byte_bits(v[r][2]) << 16) | (out_byte_bits(v[r][3]) << 24),
+                                  out_byte_bits(v[r][4]) | (out_byte_bits(v[r][5]) << 8) | (out_byte_bits(v[r][6]) << 16) | (out_byte_bits(v[r][7]) << 24));
                     }
                 }
+                // v now holds the quantised Cb plane (before the + 128 / clip / truncation)
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    uint32_t gy[8];
+                    uint32_t qy[2], qr[2], gy[8];
+                    lds64(sQ + r * (128 * 8), qy[0], qy[1]);
+                    lds64(sQ + (8 + r) * (128 * 8), qr[0], qr[1]);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const int y = (int)byte_at(q8[0][r], c), cr = (int)byte_at(q8[1][r], c) - 128, cb = (int)byte_at(q8[2][r], c) - 128;
+                        const int y = (int)byte_at(qy, c), cr = (int)byte_at(qr, c) - 128, cb = (int)out_byte_bits(v[r][c]) - 128;
                         const int b = sat8(y + ((29049 * cb + 8192) >> 14));
                         const int gg = sat8(y + ((-5636 * cb - 11698 * cr + 8192) >> 14));
                         const int rr = sat8(y + ((22987 * cr + 8192) >> 14));
@@ -511,19 +546,6 @@ struct K4Geom {
     int mask_bytes;  // bytes of one mask-plane row group buffer (4 * nb rows of wpr words)
     int debug;       // measurement switches (DVC_K4_DEBUG): 1 = no stores, 2 = no block arithmetic; 0 in production
 };
-
-DEVI void lds64(uint32_t saddr, uint32_t& a, uint32_t& b) {
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(saddr));
-}
-DEVI uint32_t lds_u8(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
-DEVI void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
-}
 
 __global__ void __launch_bounds__(256, 4)
 k_degrade4r(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127,
