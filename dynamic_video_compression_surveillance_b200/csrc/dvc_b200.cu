@@ -216,18 +216,20 @@ static int launch_contour_filter(char* ERRBUF, const uint32_t* raw, uint32_t* ou
 static size_t ccl_dense_ints(int H, int W) { return (size_t)H * words_per_row(W) + 1; }
 static size_t ccl_overflow_ints(int H, int W) { return (size_t)H * words_per_row(W) * 15; }
 
+// A dense + overflow pair shares one allocation (uf_addr reaches the overflow part through a 32-bit offset from the dense one).
 static int ccl_scratch_alloc(char* ERRBUF, CclScratch& sc, int frames, int H, int W) {
     const size_t pw = (size_t)H * words_per_row(W);
     const size_t d = ccl_dense_ints(H, W) * sizeof(int) * frames, o = ccl_overflow_ints(H, W) * sizeof(int) * frames;
+    if ((d + o) / sizeof(int) >= 0x7fffffffull) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "contour filter scratch exceeds 2^31 nodes");
     sc.frames = frames;
-    CU(cudaMalloc(&sc.pa0, d)); CU(cudaMalloc(&sc.paov, o));
-    CU(cudaMalloc(&sc.pb0, d)); CU(cudaMalloc(&sc.pbov, o));
-    CU(cudaMalloc(&sc.ar0, d)); CU(cudaMalloc(&sc.arov, o));
+    CU(cudaMalloc(&sc.pa0, d + o)); sc.paov = sc.pa0 + d / sizeof(int);
+    CU(cudaMalloc(&sc.pb0, d + o)); sc.pbov = sc.pb0 + d / sizeof(int);
+    CU(cudaMalloc(&sc.ar0, d + o)); sc.arov = sc.ar0 + d / sizeof(int);
     CU(cudaMalloc(&sc.filled, pw * 4 * frames));
     return DVC_OK;
 }
 static void ccl_scratch_free(CclScratch& sc) {
-    cudaFree(sc.pa0); cudaFree(sc.paov); cudaFree(sc.pb0); cudaFree(sc.pbov); cudaFree(sc.ar0); cudaFree(sc.arov);
+    cudaFree(sc.pa0); cudaFree(sc.pb0); cudaFree(sc.ar0);
     cudaFree(sc.filled);
     sc = CclScratch();
 }
@@ -1161,14 +1163,14 @@ extern "C" int dvc_contour_filter_u8(const uint8_t* src, uint8_t* dst, int32_t n
     const size_t pw = (size_t)H * words_per_row(W);
     const int fr = std::min(n, 8);
     const size_t d = ccl_dense_ints(H, W) * sizeof(int) * fr, o = ccl_overflow_ints(H, W) * sizeof(int) * fr;
-    ScopedAsyncBuf a(st), b(st), pa0(st), paov(st), pb0(st), pbov(st), ar0(st), arov(st), fl(st);
+    ScopedAsyncBuf a(st), b(st), pa(st), pb(st), ar(st), fl(st);
     CU(a.alloc(pw * 4 * n));
     CU(b.alloc(pw * 4 * n));
-    CU(pa0.alloc(d)); CU(paov.alloc(o)); CU(pb0.alloc(d)); CU(pbov.alloc(o)); CU(ar0.alloc(d)); CU(arov.alloc(o));
+    CU(pa.alloc(d + o)); CU(pb.alloc(d + o)); CU(ar.alloc(d + o));      // dense + overflow pairs, one allocation each
     CU(fl.alloc(pw * 4 * fr));
     CclScratch sc;
-    sc.pa0 = (int*)pa0.p; sc.paov = (int*)paov.p; sc.pb0 = (int*)pb0.p; sc.pbov = (int*)pbov.p;
-    sc.ar0 = (int*)ar0.p; sc.arov = (int*)arov.p; sc.filled = (uint32_t*)fl.p; sc.frames = fr;
+    sc.pa0 = (int*)pa.p; sc.paov = sc.pa0 + d / sizeof(int); sc.pb0 = (int*)pb.p; sc.pbov = sc.pb0 + d / sizeof(int);
+    sc.ar0 = (int*)ar.p; sc.arov = sc.ar0 + d / sizeof(int); sc.filled = (uint32_t*)fl.p; sc.frames = fr;
     rc = pack_to_bits(src, (uint32_t*)a.p, n, H, W, st);
     if (rc) return rc;
     rc = launch_contour_filter(nullptr, (const uint32_t*)a.p, (uint32_t*)b.p, n, H, W, min_area, sc, st);
@@ -1207,10 +1209,11 @@ extern "C" int dvc_mask_rectangles_u8(const uint8_t* src, uint8_t* dst, int32_t 
     const size_t pw = (size_t)H * wpr;
     const int fr = std::min(n, 4);
     const size_t d = ccl_dense_ints(H, W) * sizeof(int) * fr, o = ccl_overflow_ints(H, W) * sizeof(int) * fr;
-    ScopedAsyncBuf a(st), b(st), p0(st), pov(st), bd(st), bo(st);
+    ScopedAsyncBuf a(st), b(st), pp(st), bbuf(st);
     CU(a.alloc(pw * 4 * n));
     CU(b.alloc(pw * 4 * n));
-    CU(p0.alloc(d)); CU(pov.alloc(o)); CU(bd.alloc(3 * d)); CU(bo.alloc(3 * o));
+    CU(pp.alloc(d + o)); CU(bbuf.alloc(3 * (d + o)));                     // dense + overflow pairs, one allocation each
+    struct { void* p; } p0{pp.p}, pov{(char*)pp.p + d}, bd{bbuf.p}, bo{(char*)bbuf.p + 3 * d};
     rc = pack_to_bits(src, (uint32_t*)a.p, n, H, W, st);
     if (rc) return rc;
     CU(cudaMemsetAsync(b.p, 0, pw * 4 * n, st));

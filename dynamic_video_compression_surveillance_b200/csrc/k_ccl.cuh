@@ -20,19 +20,21 @@
 namespace dvc {
 
 struct UF {
-    int* p0;     // [1 + plane_words]: p0[0] = outside, p0[1 + w] = slot 0 of word w
-    int* pov;    // [plane_words * 15]: slots 1..15
+    int* base;     // dense part: base[0] = outside, base[1 + w] = slot 0 of word w
+    int ov_off;    // offset (in ints, from base) of the overflow part [plane_words * 15]: slots 1..15
 };
 
 DEVI int node_id(int word, int slot) { return ((word + 1) << 4) | slot; }
+// One pointer + a 32-bit offset: the dense and overflow arrays of a pair live in one allocation (see ccl_pair_alloc),
+// so the address is a single IMAD.WIDE instead of two 64-bit multiply-adds and a pointer select.
 DEVI int* uf_addr(const UF& u, int id) {
     const int s = id & 15, w = id >> 4;
-    return s == 0 ? u.p0 + w : u.pov + (size_t)(w - 1) * 15 + (s - 1);
+    return u.base + (s == 0 ? w : u.ov_off + (w - 1) * 15 + (s - 1));
 }
 DEVI UF uf_of_frame(int* p0, int* pov, size_t plane_words, int frame) {
     UF u;
-    u.p0 = p0 + (size_t)frame * (plane_words + 1);
-    u.pov = pov + (size_t)frame * plane_words * 15;
+    u.base = p0 + (size_t)frame * (plane_words + 1);
+    u.ov_off = (int)((pov + (size_t)frame * plane_words * 15) - u.base);
     return u;
 }
 
@@ -97,7 +99,7 @@ k_ccl_rowlink(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __
     const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
-    if (BORDER && y == 0 && lane == 0) P.p0[0] = 0;
+    if (BORDER && y == 0 && lane == 0) P.base[0] = 0;
     const bool edge_row = BORDER && (y == 0 || y == H - 1);
     const int last_word = (W - 1) >> 5, last_bit = (W - 1) & 31;
     int carry_root = -1;                      // root of the run leaving the previous chunk through bit 31 (-1: none)
