@@ -310,6 +310,23 @@ def run_b200(args, rank, world, local_rank):
                                                "frac": (value / world) * px * SURVEY_LOOP_BYTES_PER_PX / 1e9 / peak},
                          "this_design": {"bytes_per_px": ACTUAL_LOOP_BYTES_PER_PX,
                                          "frac": (value / world) * px * ACTUAL_LOOP_BYTES_PER_PX / 1e9 / peak}}}
+    # K4 writes twice what it reads, and HBM absorbs writes more slowly than a read/write mix: report the kernel's write rate
+    # next to a write-only (fill) rate measured here, as context for `frac` (which stays against the copy peak)
+    try:
+        fill_buf = torch.empty(1 << 31, dtype=torch.uint8, device=dev)
+        best = None
+        for _ in range(6):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(); fill_buf.zero_(); f1.record(); torch.cuda.synchronize()
+            t_ms = f0.elapsed_time(f1)
+            best = t_ms if best is None else min(best, t_ms)
+        fill_gbs = fill_buf.numel() / (best * 1e-3) / 1e9
+        del fill_buf
+        k4_write_gbs = 6.0 * px * frames_per_launch / (k4_ms / max(1, k4_launches) * 1e-3) / 1e9 if k4_ms > 0 else 0.0
+        roofline["write_path"] = {"written_bytes_per_px": 6.0, "achieved_write": k4_write_gbs, "fill_peak_measured_here": fill_gbs,
+                                  "unit": "GB/s", "frac_of_fill_peak": k4_write_gbs / fill_gbs if fill_gbs else None}
+    except Exception:
+        pass
     traffic_file = os.path.join(ROOT, "profiles", "k4_dram_bytes_per_launch.json")
     if os.path.exists(traffic_file):
         try:
