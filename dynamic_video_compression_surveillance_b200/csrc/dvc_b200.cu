@@ -382,30 +382,29 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                     sg.n_tiles = sg.tiles_per_frame * n;
                     sg.stage_bytes = (g.span_bytes + 2 * g.mask_bytes + 127) & ~127;
                     sg.ybuf_bytes = (g.span_bytes + 127) & ~127;
-                    static const int env_cps = [] { const char* e = getenv("DVC_K4_CTAS_PER_SM"); return e ? atoi(e) : 1; }();
                     const int G = env_groups == 1 ? 1 : (env_groups == 3 ? 3 : 2);
-                    const int cps = env_cps == 2 ? 2 : 1;
                     int S = std::max(G, env_stages);
-                    const size_t smem_cap = cps == 2 ? 110 * 1024 : 224 * 1024;
+                    const size_t smem_cap = 224 * 1024;
                     auto smem_need = [&](int stages) { return (size_t)stages * sg.stage_bytes + (size_t)G * sg.ybuf_bytes + 8 * (2 * stages) + 16 + 16 * stages; };
-                    while (smem_need(S) > smem_cap && S > G) --S;
-                    S -= S % G;
+                    while (smem_need(S) > smem_cap && S > 2) --S;
+                    // A group hands a stage back only while it works on its next tile, so every group needs a second stage to
+                    // move on to: with stages <= groups the ring would wait on itself.
+                    if (S <= G || smem_need(S) > smem_cap) {
+                        return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "K4 ring: %d stages for %d consumer groups do not fit (%zu bytes of shared memory)", S, G, smem_need(S));
+                    }
                     sg.stages = S;
                     // bulk-copy granularity: whole spans by default (piece sizes from 1.4 KB to the full 23 KB span were
                     // measured: no gain from smaller pieces, profiles/README.md r1l)
                     sg.piece_bytes = env_piece > 0 ? ((env_piece + 15) & ~15) : 32768;
                     const size_t smem_s = smem_need(S);
-                    const unsigned ctas = (unsigned)std::min(sg.n_tiles, env_ctas > 0 ? env_ctas : sms * cps);
+                    const unsigned ctas = (unsigned)std::min(sg.n_tiles, env_ctas > 0 ? env_ctas : sms);
                     static PerDeviceOnce attr_s;
                     if (attr_s.need()) {
                         CU(cudaFuncSetAttribute(k_degrade4s<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                         CU(cudaFuncSetAttribute(k_degrade4s<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                         CU(cudaFuncSetAttribute(k_degrade4s<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                        CU(cudaFuncSetAttribute(k_degrade4s<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-                        CU(cudaFuncSetAttribute(k_degrade4s<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
                     }
-                    if (cps == 2) k_degrade4s<2, 2><<<ctas, 32 + 512, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
-                    else if (G == 1) k_degrade4s<1, 1><<<ctas, 32 + 256, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
+                    if (G == 1) k_degrade4s<1, 1><<<ctas, 32 + 256, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
                     else if (G == 3) k_degrade4s<3, 1><<<ctas, 32 + 768, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
                     else k_degrade4s<2, 1><<<ctas, 32 + 512, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
                 } else {

@@ -67,14 +67,23 @@ DEVI void dct4_inv_t(T& x0, T& x1, T& x2, T& x3) {
     x2 = sub(e1, o1);
 }
 
-// rint(fl(d_true / q)) * q, scalings folded: d arrives as d_true * 2^NE, leaves as value * 2^-NE
-template <int NE, typename T>
+// n * o for a packed pair with two scalar multiplications.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 in
+// spite of the explicit rounding modifiers (it does not for scalar f32, and it sees through fma(n, o, -0.0)); the products of
+// coefficient columns 0 and 2 feed the additions of the inverse row butterflies, and the fused form changed one result bit in
+// ~1e-4 of the blocks at small q.  A scalar FMUL cannot be folded into a packed FADD2.
+DEVI float dequant(float n, float o) { return __fmul_rn(n, o); }
+DEVI P2 dequant(P2 n, float o) { float a, b; unp2(n, a, b); return p2(__fmul_rn(a, o), __fmul_rn(b, o)); }
+
+// rint(fl(d_true / q)) * q, scalings folded: d arrives as d_true * 2^NE, leaves as value * 2^-NE.
+// FEEDS_ADD: the result is an operand of an addition (see dequant).
+template <int NE, bool FEEDS_ADD, typename T>
 DEVI T quantise_t(T d, const QuantP& qp) {
     const T r = splat<T>(qp.rcp[NE]), nq = splat<T>(qp.nqs[NE]), magic = splat<T>(12582912.0f);   // 1.5 * 2^23
     const T y0 = mul(d, r);
     const T e = fma_(nq, y0, d);
     const T y = fma_(e, r, y0);                                // == fl(d / (q 2^NE)), correctly rounded
     const T n = sub(add(y, magic), magic);                     // round half to even
+    if (FEEDS_ADD) return dequant(n, qp.o[NE]);
     return mul(n, splat<T>(qp.o[NE]));
 }
 
@@ -86,12 +95,13 @@ DEVI void degrade_block_t(T (&v)[4][4], const QuantP& qp) {
     for (int c = 0; c < 4; ++c) dct4_fwd_t(v[0][c], v[1][c], v[2][c], v[3][c]);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
+        // columns 0 and 2 enter the inverse row butterflies through additions, columns 1 and 3 through multiplications
         if ((r & 1) == 0) {
-            v[r][0] = quantise_t<2>(v[r][0], qp); v[r][1] = quantise_t<1>(v[r][1], qp);
-            v[r][2] = quantise_t<2>(v[r][2], qp); v[r][3] = quantise_t<1>(v[r][3], qp);
+            v[r][0] = quantise_t<2, true>(v[r][0], qp); v[r][1] = quantise_t<1, false>(v[r][1], qp);
+            v[r][2] = quantise_t<2, true>(v[r][2], qp); v[r][3] = quantise_t<1, false>(v[r][3], qp);
         } else {
-            v[r][0] = quantise_t<1>(v[r][0], qp); v[r][1] = quantise_t<0>(v[r][1], qp);
-            v[r][2] = quantise_t<1>(v[r][2], qp); v[r][3] = quantise_t<0>(v[r][3], qp);
+            v[r][0] = quantise_t<1, true>(v[r][0], qp); v[r][1] = quantise_t<0, false>(v[r][1], qp);
+            v[r][2] = quantise_t<1, true>(v[r][2], qp); v[r][3] = quantise_t<0, false>(v[r][3], qp);
         }
     }
 #pragma unroll
@@ -341,7 +351,7 @@ DEVI void degrade_plane8(float (&v)[8][8], const QuantP& qp) {
         for (int r = 0; r < 8; ++r) t[r] = v[r][c];
         dct8_fwd(t);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v[r][c] = quantise_t<0>(t[r], qp);
+        for (int r = 0; r < 8; ++r) v[r][c] = quantise_t<0, false>(t[r], qp);
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {

@@ -60,3 +60,26 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+
+
+def test_packed_fp32_is_not_contracted(lib):
+    """ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the rounding modifiers (seen with 12.9), which breaks the
+    bit-exact DCT.  The K4 ring kernel is written so that no packed product feeds a packed addition; its SASS must hold exactly
+    the packed operations of the algorithm: 2 x 16 FFMA2 in the DCT butterflies + 2 x 16 in the quotient, 56 FMUL2, 160 FADD2."""
+    import shutil
+    import subprocess
+    from dynamic_video_compression_surveillance_b200 import build
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", build.LIB], capture_output=True, text=True).stdout
+    counts, fn = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        for op in ("FFMA2", "FMUL2", "FADD2"):
+            if fn and "k_degrade4s" in fn and (" " + op + " ") in line:
+                counts.setdefault(fn, {}).setdefault(op, 0)
+                counts[fn][op] += 1
+    assert counts, "k_degrade4s not found in the library"
+    for fn, c in counts.items():
+        assert (c.get("FFMA2"), c.get("FMUL2"), c.get("FADD2")) == (64, 56, 160), (fn, c)

@@ -252,7 +252,7 @@ def test_degrade_fd(P, shape, bs):
     assert c[3] == 3 * (shape[0] // bs) * (shape[1] // bs) and c[4] == n_static
 
 
-@pytest.mark.parametrize("q", [100, 100.0, 33.3, 8, 7.5, 1, 250, 0.25])
+@pytest.mark.parametrize("q", [100, 100.0, 33.3, 8, 7.5, 1, 250, 0.25, 0.3, 7.3, 0.05, 1000.5])
 def test_degrade_fd_quantiser_ties_and_levels(P, q):
     """Blocks built to sit exactly on quantiser ties (d/q = n + 1/2) and a sweep of quantisation levels,
     including levels small enough to disable the fast rounding path."""
@@ -314,6 +314,23 @@ def test_degrade_fd_ring_wraps_many_tiles_per_cta(P):
     assert c[2] == int((acc > 127).sum())
     nz_blocks = (acc.reshape(n, h // 4, 4, w // 4, 4) != 0).any(axis=(2, 4))
     assert c[4] == int((~nz_blocks).sum())
+
+
+@pytest.mark.parametrize("q", [0.011, 0.05, 0.3, 33.3, 100.0])
+def test_degrade_fd_exact_on_many_dense_blocks(P, q):
+    """19 200 random blocks per level, exact equality: small q keeps every coefficient alive, which is where a one-bit
+    difference in the arithmetic (e.g. a compiler-contracted multiply-add) shows up as a flipped truncation."""
+    if not so.cv2_dct4_matches_closed_form():
+        pytest.skip("host cv2 does not follow the recovered float32 DCT sequence; covered by tolerance tests")
+    r = rng(5)
+    t, h, w = 2, 240, 640
+    frames = r.integers(0, 256, (t, h, w, 3), dtype=np.uint8)
+    acc = np.zeros((t, h, w), np.uint8)
+    comp = host(P.degrade_blend(dev(frames), dev(acc), 4, q, "fd", False)[0])
+    for i in range(t):
+        ref = so.degrade_fd(frames[i], acc[i], 4, q)
+        bad = (comp[i] != ref).any(axis=2).reshape(h // 4, 4, w // 4, 4).any(axis=(1, 3)).sum()
+        assert bad == 0, (q, i, int(bad))
 
 
 def test_degrade_mco(P):
