@@ -198,6 +198,26 @@ def test_resize_linear(P, shape):
     assert np.array_equal(got[0], cv2.resize(g[0], (w // 2, h // 2)))
 
 
+def test_bgr2gray_all_colours(P):
+    """Every one of the 2^24 BGR triples through the IDP.2A gray conversion (K1 / blur kernels share it)."""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([v & 0xff, (v >> 8) & 0xff, v >> 16], axis=-1).astype(np.uint8).reshape(1, 4096, 4096, 3)
+    got = host(P.bgr2gray(dev(img)))[0]
+    assert np.array_equal(got, so.bgr2gray(img[0]))
+
+
+def test_mask_rectangles_max_runs_per_word(P):
+    """Isolated pixels on a 2-pixel grid: 16 runs in every word (all overflow slots of the run graph in use), one component
+    per pixel; and a one-pixel checkerboard, which is a single 8-connected component."""
+    grid = np.zeros((64, 160), np.uint8)
+    grid[::2, ::2] = 255
+    chk = ((np.add.outer(np.arange(48), np.arange(100)) & 1) * 255).astype(np.uint8)
+    for m in (grid, np.ascontiguousarray(grid[:, 1:]), chk):
+        got = host(P.mask_rectangles(dev(m[None])))[0]
+        assert np.array_equal(got, so.mask_rectangles_cv2(m))
+        assert np.array_equal(host(P.contour_filter(dev(m[None]), 0))[0], so.contour_filter_cv2(m, 0))
+
+
 def test_contour_filter_1080p_blobs(P):
     r = rng(10)
     m = np.zeros((1080, 1920), np.uint8)
