@@ -4,6 +4,8 @@ Bar (BASELINE.json north_star): masks bit-exact; frames bit-exact where the refe
 ops; DCT-degraded blocks bit-exact when this host's cv2 follows the recovered float32 sequence, otherwise
 within 1 grey level away from exact quantiser ties.
 """
+import os
+
 import cv2
 import numpy as np
 import pytest
@@ -667,3 +669,15 @@ def test_config5_farneback_masks_to_mco_degrade_1080p(P):
         assert np.mean(d <= 2) > 0.97 and d.max() <= 110       # a flipped tie moves a block by one quantiser step
         psnr = 10 * np.log10(255.0 ** 2 / max(1e-9, np.mean((comp[i].astype(float) - ref.astype(float)) ** 2)))
         assert psnr > 40, psnr
+
+
+def test_random_loop_configurations_against_oracle():
+    """tools/loop_fuzz.py: random sizes, batch sizes and parameters of both loop flavours (window sizes 1..31, alpha 0..1,
+    rect / ellipse elements, even kernel sizes, thresholds up to 200, release factors 0.05..0.9, several quantisation levels),
+    state carried over several host calls; masks, overlays and compressed frames must equal the oracle loops."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "loop_fuzz.py"), "14", "11"], capture_output=True, text=True,
+                       timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().splitlines()[-1].startswith("all cases equal"), r.stdout[-3000:]
