@@ -345,13 +345,13 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
             static PerDeviceOnce attr_p;
             if (attr_p.need()) {
                 CU(cudaFuncSetAttribute(k_degrade4p<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                CU(cudaFuncSetAttribute(k_degrade4r, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                CU(cudaFuncSetAttribute(k_degrade4r, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             }
-            static const bool rowspan_env = [] { const char* e = getenv("DVC_K4_ROWSPAN"); return e ? atoi(e) != 0 : true; }();
+            // DVC_K4_PERSIST=0 selects the CTA-per-256-groups kernel (k_degrade4p) for A/B; it is also the fallback for pointers
+            // that are not 16-byte aligned and for W > 2048 with W % 16 != 0 (bulk copies need 16-byte pieces)
+            static const bool ring_env = [] { const char* e = getenv("DVC_K4_PERSIST"); return e ? atoi(e) != 0 : true; }();
             const int gpr = W / 8, nbr = H / 4;
             const bool ptr16 = ((((uintptr_t)frames) | ((uintptr_t)compressed) | ((uintptr_t)overlay)) & 15u) == 0;
-            if (rowspan_env && ptr16 && (gpr <= 256 || W % 16 == 0)) {
+            if (ring_env && ptr16 && (gpr <= 256 || W % 16 == 0)) {
                 K4Geom g;
                 if (gpr <= 256) {
                     g.parts = 1; g.gp = gpr; g.nb = std::max(1, std::min(nbr, std::min(256 / gpr, 256 / wpr))); g.sp = W * 3;
@@ -364,11 +364,8 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                 }
                 g.mask_bytes = 4 * g.nb * wpr * 4;
                 static const int dbg = [] { const char* e = getenv("DVC_K4_DEBUG"); return e ? atoi(e) : 0; }();
-                static const int pad = [] { const char* e = getenv("DVC_K4_SMEM_PAD"); return e ? atoi(e) : 0; }();
                 g.debug = dbg;
-                const size_t smem_r = (size_t)2 * g.span_bytes + 2 * g.mask_bytes + 16 + pad;
-                static const int persist = [] { const char* e = getenv("DVC_K4_PERSIST"); return e ? atoi(e) : 1; }();
-                if (persist) {
+                {
                     static const int env_stages = [] { const char* e = getenv("DVC_K4_STAGES"); return e ? atoi(e) : 6; }();
                     static const int env_groups = [] { const char* e = getenv("DVC_K4_GROUPS"); return e ? atoi(e) : 2; }();
                     static const int env_piece = [] { const char* e = getenv("DVC_K4_PIECE"); return e ? atoi(e) : 0; }();
@@ -407,9 +404,6 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                     if (G == 1) k_degrade4s<1, 1><<<ctas, 32 + 256, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
                     else if (G == 3) k_degrade4s<3, 1><<<ctas, 32 + 768, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
                     else k_degrade4s<2, 1><<<ctas, 32 + 512, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
-                } else {
-                dim3 grid_r(g.parts == 1 ? cdiv(nbr, g.nb) : (unsigned)(nbr * g.parts), n);
-                k_degrade4r<<<grid_r, 256, smem_r, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, g);
                 }
             } else
             if (tma) k_degrade4p<true><<<grid, 256, smem, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);

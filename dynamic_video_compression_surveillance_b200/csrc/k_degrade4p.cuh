@@ -539,13 +539,9 @@ k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
 }
 
 // ------------------------------------------------------------------------------------------------
-// Row-span version (default when the geometry allows): a CTA owns whole 4-pixel-high block rows (or an exact
-// part of one for W > 2048), i.e. one contiguous span of the frame.  HBM only ever sees large bulk operations:
-//   * the span (<= 24 KB) and its two mask-plane row groups arrive by cp.async.bulk (TMA) on one mbarrier;
-//   * threads read their 8 px x 4 rows with conflict-free LDS.64 (lane stride 24 B);
-//   * the overlay is the input span painted in place (only where acc > 127), the compressed span is written to
-//     a second buffer; both leave by cp.async.bulk stores issued by one thread.
-// Shared memory: 2 spans + 2 mask groups (~53 KB) -> 4 CTAs per SM.
+// Tile geometry of the ring kernel below: a tile is a span of whole 4-pixel-high block rows (contiguous in the frame), or
+// an exact part of one block row for W > 2048.  (A one-shot CTA-per-span kernel built on the same geometry was measured
+// and dropped: profiles/r1l_k4_experiments.txt section 2.)
 // ------------------------------------------------------------------------------------------------
 struct K4Geom {
     int gp;          // pixel groups (8 px) per CTA row piece
@@ -556,123 +552,6 @@ struct K4Geom {
     int mask_bytes;  // bytes of one mask-plane row group buffer (4 * nb rows of wpr words)
     int debug;       // measurement switches (DVC_K4_DEBUG): 1 = no stores, 2 = no block arithmetic; 0 in production
 };
-
-__global__ void __launch_bounds__(256, 4)
-k_degrade4r(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127,
-            const uint32_t* __restrict__ nonzero, uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay,
-            int H, int W, int wpr, QuantP qp, Counters* __restrict__ counters, K4Geom g) {
-    extern __shared__ __align__(128) uint8_t k4_smem[];
-    const uint32_t sX = (uint32_t)__cvta_generic_to_shared(k4_smem);       // input span, becomes the overlay span
-    const uint32_t sY = sX + g.span_bytes;                                  // compressed span
-    const uint32_t sMh = sY + g.span_bytes;                                 // over127 rows
-    const uint32_t sMn = sMh + g.mask_bytes;                                // nonzero rows
-    const uint32_t bar = sMn + g.mask_bytes;
-    const int gpr = W >> 3, nbr = H >> 2;
-    const int tid = threadIdx.x;
-    const size_t pitch = (size_t)W * 3;
-    const size_t frame_off = (size_t)blockIdx.y * H * W * 3;
-    const size_t plane_off = (size_t)blockIdx.y * H * wpr;
-    // CTA geometry
-    int br0, nb, g0, ng;
-    if (g.parts == 1) { br0 = blockIdx.x * g.nb; nb = min(g.nb, nbr - br0); g0 = 0; ng = gpr; }
-    else { br0 = blockIdx.x / g.parts; nb = 1; g0 = (blockIdx.x - br0 * g.parts) * g.gp; ng = min(g.gp, gpr - g0); }
-    const size_t span_off = frame_off + (size_t)(br0 * 4) * pitch + (size_t)g0 * 24;
-    const uint32_t mrow_bytes = (uint32_t)wpr * 4u;
-
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t mbytes = (uint32_t)(4 * nb) * mrow_bytes;
-        const uint32_t fbytes = g.parts == 1 ? (uint32_t)(4 * nb) * (uint32_t)pitch : 4u * (uint32_t)ng * 24u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(fbytes + 2u * mbytes) : "memory");
-        if (g.parts == 1) bulk_load(sX, frames + span_off, fbytes, bar);
-        else
-            for (int r = 0; r < 4; ++r) bulk_load(sX + r * g.sp, frames + span_off + r * pitch, (uint32_t)ng * 24u, bar);
-        bulk_load(sMh, over127 + plane_off + (size_t)(br0 * 4) * wpr, mbytes, bar);
-        bulk_load(sMn, nonzero + plane_off + (size_t)(br0 * 4) * wpr, mbytes, bar);
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
-                         : "=r"(done) : "r"(bar) : "memory");
-        }
-    }
-    __syncthreads();          // the waiter's observation of the completed phase orders the async writes before everybody's reads
-
-    unsigned n_motion = 0, n_static = 0;
-    const int brl = tid / ng, gxl = tid - brl * ng;
-    if (brl < nb) {
-        const uint32_t toff = (uint32_t)(brl * 4) * (uint32_t)g.sp + (uint32_t)gxl * 24u;
-        const uint32_t moff = (uint32_t)(brl * 4) * mrow_bytes + (uint32_t)(g0 + gxl);
-        uint32_t w[4][6];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) lds64(sX + toff + r * g.sp + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
-        uint32_t hi[4], nz = 0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            hi[r] = lds_u8(sMh + moff + r * mrow_bytes);
-            nz |= lds_u8(sMn + moff + r * mrow_bytes);
-        }
-        // ---- overlay: paint (B,G,R) = (0,0,255) where acc > 127, in place in the input span ----
-        if (overlay) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (hi[r] == 0u) continue;
-                uint32_t o[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) o[i] = w[r][i];
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const uint32_t m = hi[r] >> (4 * b);
-                    if (m & 1u) { o[3 * b] = (o[3 * b] & 0xff000000u) | 0x00ff0000u; }
-                    if (m & 2u) { o[3 * b] &= 0x00ffffffu; o[3 * b + 1] = (o[3 * b + 1] & 0xffff0000u) | 0x0000ff00u; }
-                    if (m & 4u) { o[3 * b + 1] &= 0x0000ffffu; o[3 * b + 2] = (o[3 * b + 2] & 0xffffff00u) | 0x000000ffu; }
-                    if (m & 8u) { o[3 * b + 2] = (o[3 * b + 2] & 0x000000ffu) | 0xff000000u; }
-                }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) sts64(sX + toff + r * g.sp + 8 * i, o[2 * i], o[2 * i + 1]);
-            }
-        }
-        n_motion = __popc(hi[0]) + __popc(hi[1]) + __popc(hi[2]) + __popc(hi[3]);
-        const bool st_a = (nz & 0xfu) == 0u, st_b = (nz >> 4) == 0u;
-        n_static = (st_a ? 1u : 0u) + (st_b ? 1u : 0u);
-        if (compressed) {
-            if (!(g.debug & 2)) k4_blocks(w, st_a, st_b, qp);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int i = 0; i < 3; ++i) sts64(sY + toff + r * g.sp + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
-        }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0 && !(g.debug & 1)) {
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-            uint8_t* dst = o == 0 ? overlay : compressed;
-            if (!dst) continue;
-            const uint32_t src = o == 0 ? sX : sY;
-            if (g.parts == 1) bulk_store(dst + span_off, src, (uint32_t)(4 * nb) * (uint32_t)pitch);
-            else
-                for (int r = 0; r < 4; ++r) bulk_store(dst + span_off + r * pitch, src + r * g.sp, (uint32_t)ng * 24u);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
-    }
-    if (counters) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            n_motion += __shfl_xor_sync(0xffffffffu, n_motion, o);
-            n_static += __shfl_xor_sync(0xffffffffu, n_static, o);
-        }
-        if ((tid & 31) == 0) {
-            if (n_motion) atomicAdd(&counters->motion_pixels, (unsigned long long)n_motion);
-            if (n_static) atomicAdd(&counters->static_blocks, (unsigned long long)n_static);
-        }
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // Persistent, warp-specialised version (the default): one CTA per SM walks tiles t = blockIdx.x, blockIdx.x +

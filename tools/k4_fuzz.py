@@ -1,5 +1,5 @@
 """Fuzz the block_size-4 degrade kernel over random geometries: prints one checksum line per case.  Run it twice with different
-kernel selections (e.g. default and DVC_K4_PERSIST=0 DVC_K4_ROWSPAN=0 DVC_K4_PACKED=0) and diff the outputs."""
+kernel selections (e.g. default and DVC_K4_PERSIST=0, or DVC_K4_PACKED=0) and diff the outputs."""
 import os, sys, hashlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
