@@ -186,6 +186,7 @@ struct CclScratch {
     // union-find storage per frame (k_ccl.cuh): dense slot-0 arrays [plane_words + 1] and overflow arrays
     // [plane_words * 15], for the phase A parents, the phase B parents and the phase B areas
     int *pa0 = nullptr, *paov = nullptr, *pb0 = nullptr, *pbov = nullptr, *ar0 = nullptr, *arov = nullptr;
+    uint8_t* rowflag = nullptr;   // [frames][H]: the row holds foreground (written by the first kernel, read by the other six)
     uint32_t* filled = nullptr;  // [frames] planes
     int frames = 0;
 };
@@ -201,13 +202,15 @@ static int launch_contour_filter(char* ERRBUF, const uint32_t* raw, uint32_t* ou
         dim3 grid(cdiv(pw, 256), m);
         dim3 grow((H + 7) / 8, m);
         const uint32_t* r = raw + (size_t)i0 * pw;
-        k_ccl_rowlink<true, true><<<grow, 256, 0, st>>>(r, sc.pa0, sc.paov, nullptr, nullptr, H, W, wpr);
-        k_ccl_union<true, 4><<<grid, 256, 0, st>>>(r, sc.pa0, sc.paov, H, W, wpr);
-        k_ccl_fill<<<grid, 256, 0, st>>>(r, sc.pa0, sc.paov, sc.filled, H, W, wpr);
-        k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, H, W, wpr);
-        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, H, W, wpr);
-        k_ccl_area<<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, H, W, wpr);
-        k_ccl_select<<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, out + (size_t)i0 * pw, H, W, wpr, thr);
+        static const bool row_skip = [] { const char* e = getenv("DVC_CCL_ROWSKIP"); return e ? atoi(e) != 0 : true; }();
+        uint8_t* rf = row_skip ? sc.rowflag : nullptr;
+        k_ccl_rowlink<true, true><<<grow, 256, 0, st>>>(r, sc.pa0, sc.paov, nullptr, nullptr, H, W, wpr, rf);
+        k_ccl_union<true, 4><<<grid, 256, 0, st>>>(r, sc.pa0, sc.paov, H, W, wpr, rf);
+        k_ccl_fill<<<grid, 256, 0, st>>>(r, sc.pa0, sc.paov, sc.filled, H, W, wpr, rf);
+        k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, H, W, wpr, rf);
+        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, H, W, wpr, rf);
+        k_ccl_area<<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, H, W, wpr, rf);
+        k_ccl_select<<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, out + (size_t)i0 * pw, H, W, wpr, thr, rf);
         CHECK_LAUNCH();
     }
     return DVC_OK;
@@ -226,11 +229,12 @@ static int ccl_scratch_alloc(char* ERRBUF, CclScratch& sc, int frames, int H, in
     CU(cudaMalloc(&sc.pb0, d + o)); sc.pbov = sc.pb0 + d / sizeof(int);
     CU(cudaMalloc(&sc.ar0, d + o)); sc.arov = sc.ar0 + d / sizeof(int);
     CU(cudaMalloc(&sc.filled, pw * 4 * frames));
+    CU(cudaMalloc(&sc.rowflag, (size_t)frames * H));
     return DVC_OK;
 }
 static void ccl_scratch_free(CclScratch& sc) {
     cudaFree(sc.pa0); cudaFree(sc.pb0); cudaFree(sc.ar0);
-    cudaFree(sc.filled);
+    cudaFree(sc.filled); cudaFree(sc.rowflag);
     sc = CclScratch();
 }
 
@@ -1156,12 +1160,14 @@ extern "C" int dvc_contour_filter_u8(const uint8_t* src, uint8_t* dst, int32_t n
     const size_t pw = (size_t)H * words_per_row(W);
     const int fr = std::min(n, 8);
     const size_t d = ccl_dense_ints(H, W) * sizeof(int) * fr, o = ccl_overflow_ints(H, W) * sizeof(int) * fr;
-    ScopedAsyncBuf a(st), b(st), pa(st), pb(st), ar(st), fl(st);
+    ScopedAsyncBuf a(st), b(st), pa(st), pb(st), ar(st), fl(st), rfl(st);
     CU(a.alloc(pw * 4 * n));
     CU(b.alloc(pw * 4 * n));
     CU(pa.alloc(d + o)); CU(pb.alloc(d + o)); CU(ar.alloc(d + o));      // dense + overflow pairs, one allocation each
     CU(fl.alloc(pw * 4 * fr));
+    CU(rfl.alloc((size_t)fr * H));
     CclScratch sc;
+    sc.rowflag = (uint8_t*)rfl.p;
     sc.pa0 = (int*)pa.p; sc.paov = sc.pa0 + d / sizeof(int); sc.pb0 = (int*)pb.p; sc.pbov = sc.pb0 + d / sizeof(int);
     sc.ar0 = (int*)ar.p; sc.arov = sc.ar0 + d / sizeof(int); sc.filled = (uint32_t*)fl.p; sc.frames = fr;
     rc = pack_to_bits(src, (uint32_t*)a.p, n, H, W, st);
@@ -1218,8 +1224,8 @@ extern "C" int dvc_mask_rectangles_u8(const uint8_t* src, uint8_t* dst, int32_t 
         const uint32_t* r = (const uint32_t*)a.p + (size_t)i0 * pw;
         CU(cudaMemsetAsync(bd.p, 0x7f, 3 * d, st));           // 0x7f7f7f7f: larger than any coordinate or negated coordinate
         CU(cudaMemsetAsync(bo.p, 0x7f, 3 * o, st));
-        k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, nullptr, nullptr, H, W, wpr);
-        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, H, W, wpr);
+        k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, nullptr, nullptr, H, W, wpr, nullptr);
+        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, H, W, wpr, nullptr);
         k_ccl_bbox<<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, bb, H, W, wpr);
         k_ccl_paint_rects<<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, bb, (uint32_t*)b.p + (size_t)i0 * pw, H, W, wpr);
         CHECK_LAUNCH();

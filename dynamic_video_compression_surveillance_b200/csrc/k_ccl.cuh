@@ -91,10 +91,13 @@ DEVI uint32_t plane_word(const uint32_t* plane, int y, int j, int H, int W, int 
 template <bool INVERT, bool BORDER>
 __global__ void __launch_bounds__(256)
 k_ccl_rowlink(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov,
-              int* __restrict__ a0, int* __restrict__ aov, int H, int W, int wpr) {
+              int* __restrict__ a0, int* __restrict__ aov, int H, int W, int wpr, uint8_t* __restrict__ rowflag) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * 8 + warp;
     if (y >= H) return;
+    // rowflag[frame][y] = the row holds foreground.  Phase A (INVERT) computes it; every later kernel skips rows without
+    // foreground: their background is rooted at 'outside' by this kernel, nothing of them is filled, labelled or selected.
+    if (!INVERT && rowflag && rowflag[(size_t)blockIdx.y * H + y] == 0) return;
     const size_t plane_words = (size_t)H * wpr;
     const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
@@ -103,9 +106,11 @@ k_ccl_rowlink(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __
     const bool edge_row = BORDER && (y == 0 || y == H - 1);
     const int last_word = (W - 1) >> 5, last_bit = (W - 1) & 31;
     int carry_root = -1;                      // root of the run leaving the previous chunk through bit 31 (-1: none)
+    bool any_fg = false;
     for (int j0 = 0; j0 < wpr; j0 += 32) {
         const int j = j0 + lane;
         const uint32_t w = j < wpr ? plane_word<INVERT>(plane, y, j, H, W, wpr) : 0u;
+        if (INVERT && rowflag) any_fg |= __any_sync(0xffffffffu, j < wpr && (~w & valid_mask(j, W)) != 0u);
         const int word = y * wpr + j;
         const int nruns = __popc(run_starts(w));
         const bool full = w == 0xffffffffu;
@@ -147,26 +152,20 @@ k_ccl_rowlink(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __
         }
         carry_root = __shfl_sync(0xffffffffu, out_root, 31);
     }
+    if (INVERT && rowflag && lane == 0) rowflag[(size_t)blockIdx.y * H + y] = any_fg ? 1 : 0;
 }
 
 // ---- unions with the row above (4- or 8-connected); horizontal links already exist ----------------------
+// All vertical links of one word (y, j) with row y - 1.
 template <bool INVERT, int CONN>
-__global__ void __launch_bounds__(256)
-k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov, int H, int W, int wpr) {
-    const size_t plane_words = (size_t)H * wpr;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
-    if (idx >= (uint32_t)plane_words) return;
-    const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
-    if (y == 0) return;
-    const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
-    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
+DEVI void ccl_union_word(const uint32_t* __restrict__ plane, const UF& P, int y, int j, int H, int W, int wpr) {
     const uint32_t cur = plane_word<INVERT>(plane, y, j, H, W, wpr);
     if (!cur) return;
     const uint32_t up = plane_word<INVERT>(plane, y - 1, j, H, W, wpr);
     const uint32_t upl = CONN == 8 ? plane_word<INVERT>(plane, y - 1, j - 1, H, W, wpr) : 0u;
     const uint32_t upr = CONN == 8 ? plane_word<INVERT>(plane, y - 1, j + 1, H, W, wpr) : 0u;
     if (!(up | (upl >> 31) | (upr & 1u))) return;
-    const int word = (int)idx, word_up = word - wpr;
+    const int word = y * wpr + j, word_up = word - wpr;
     // The run through bit 0 of this word and the run through bit 0 of the word above both continue from the words to
     // the left: the thread of word j-1 already links those two horizontal runs, so this pair is skipped.  Inside wide
     // regions only the left-most word of every row does a union.
@@ -205,14 +204,38 @@ k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __re
     }
 }
 
-// ---- phase A result: F = complement of the background reachable from outside ---------------------
+template <bool INVERT, int CONN>
 __global__ void __launch_bounds__(256)
-k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov,
-           uint32_t* __restrict__ filled, int H, int W, int wpr) {
+k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov, int H, int W, int wpr,
+            const uint8_t* __restrict__ rowflag) {
     const size_t plane_words = (size_t)H * wpr;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
     if (idx >= (uint32_t)plane_words) return;
     const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
+    if (y == 0) return;
+    if (rowflag) {
+        const uint8_t* f = rowflag + (size_t)blockIdx.y * H;
+        // background flood (INVERT): two foreground-free rows are both rooted at 'outside' already; foreground labelling: a row
+        // without foreground has no nodes
+        if (INVERT ? (f[y] == 0 && f[y - 1] == 0) : (f[y] == 0)) return;
+    }
+    const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
+    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
+    ccl_union_word<INVERT, CONN>(plane, P, y, j, H, W, wpr);
+}
+
+// ---- phase A result: F = complement of the background reachable from outside ---------------------
+__global__ void __launch_bounds__(256)
+k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov,
+           uint32_t* __restrict__ filled, int H, int W, int wpr, const uint8_t* __restrict__ rowflag) {
+    const size_t plane_words = (size_t)H * wpr;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
+    if (idx >= (uint32_t)plane_words) return;
+    const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
+    if (rowflag && rowflag[(size_t)blockIdx.y * H + y] == 0) {             // no foreground in the row: all of it is outside
+        filled[(size_t)blockIdx.y * plane_words + idx] = 0u;
+        return;
+    }
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     uint32_t m = plane_word<true>(planes + (size_t)blockIdx.y * plane_words, y, j, H, W, wpr);
     uint32_t outside = 0;
@@ -229,11 +252,15 @@ k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __res
 // ---- phase B: 2*area = 2*Q4 + Q3 per label --------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __restrict__ pov, int* __restrict__ a0,
-           int* __restrict__ aov, int H, int W, int wpr) {
+           int* __restrict__ aov, int H, int W, int wpr, const uint8_t* __restrict__ rowflag) {
     const size_t plane_words = (size_t)H * wpr;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
     if (idx >= (uint32_t)plane_words) return;
     const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
+    if (rowflag) {
+        const uint8_t* f = rowflag + (size_t)blockIdx.y * H;
+        if (f[y] == 0 && (y + 1 >= H || f[y + 1] == 0)) return;           // both rows of the 2x2 windows are empty
+    }
     const uint32_t* F = filled + (size_t)blockIdx.y * plane_words;
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
@@ -269,10 +296,15 @@ k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __res
 
 __global__ void __launch_bounds__(256)
 k_ccl_select(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __restrict__ pov, int* __restrict__ a0,
-             int* __restrict__ aov, uint32_t* __restrict__ out, int H, int W, int wpr, int twice_min_area_floor) {
+             int* __restrict__ aov, uint32_t* __restrict__ out, int H, int W, int wpr, int twice_min_area_floor,
+             const uint8_t* __restrict__ rowflag) {
     const size_t plane_words = (size_t)H * wpr;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint32_t)plane_words) return;
+    if (rowflag && rowflag[(size_t)blockIdx.y * H + idx / (uint32_t)wpr] == 0) {
+        out[(size_t)blockIdx.y * plane_words + idx] = 0u;
+        return;
+    }
     const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
     const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
     uint32_t m = filled[(size_t)blockIdx.y * plane_words + idx];
