@@ -48,6 +48,19 @@ DEVI int uf_find(const UF& u, int x) {
         x = gp;
     }
 }
+// After the unions of a phase are complete (a later kernel), roots no longer change: a parent read from the SM's L1 may be
+// stale, but it is still an ancestor, and a root still reads as its own parent.  The 60 threads of a row share their row
+// head and its chain, so most steps hit L1 instead of making an L2 round trip.
+DEVI int uf_find_settled(const UF& u, int x) {
+    while (true) {
+        const int p = *uf_addr(u, x);
+        if (p == x) return x;
+        const int gp = *uf_addr(u, p);
+        if (gp == p) return p;
+        __stcg(uf_addr(u, x), gp);
+        x = gp;
+    }
+}
 DEVI void uf_union(const UF& u, int a, int b) {
     while (true) {
         a = uf_find(u, a);
@@ -244,7 +257,7 @@ k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __res
         int lo;
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
-        if (uf_find(P, node_id((int)idx, slot++)) == 0) outside |= run;
+        if (uf_find_settled(P, node_id((int)idx, slot++)) == 0) outside |= run;
     }
     filled[(size_t)blockIdx.y * plane_words + idx] = ~outside & valid_mask(j, W);
 }
@@ -279,7 +292,7 @@ k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __res
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
         const int c = 2 * __popc(q4 & run) + __popc(q3a & run);
-        if (c) atomicAdd(uf_addr(A, uf_find(P, node_id((int)idx, slot))), c);
+        if (c) atomicAdd(uf_addr(A, uf_find_settled(P, node_id((int)idx, slot))), c);
         ++slot;
     }
     m = q3b ? b : 0u;
@@ -289,7 +302,7 @@ k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __res
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
         const int c = __popc(q3b & run);
-        if (c) atomicAdd(uf_addr(A, uf_find(P, node_id((int)idx + wpr, slot))), c);
+        if (c) atomicAdd(uf_addr(A, uf_find_settled(P, node_id((int)idx + wpr, slot))), c);
         ++slot;
     }
 }
@@ -314,7 +327,7 @@ k_ccl_select(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __r
         int lo;
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
-        if (__ldcg(uf_addr(A, uf_find(P, node_id((int)idx, slot++)))) > twice_min_area_floor) keep |= run;
+        if (__ldcg(uf_addr(A, uf_find_settled(P, node_id((int)idx, slot++)))) > twice_min_area_floor) keep |= run;
     }
     out[(size_t)blockIdx.y * plane_words + idx] = keep;
 }
@@ -345,7 +358,7 @@ k_ccl_bbox(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __res
         const uint32_t run = lowest_run(m, lo);
         m &= ~run;
         const int hi = 31 - __clz(run);
-        const int root = uf_find(P, node_id((int)idx, slot++));
+        const int root = uf_find_settled(P, node_id((int)idx, slot++));
         atomicMin(uf_addr(MINX, root), j * 32 + lo);
         atomicMin(uf_addr(NMAXX, root), -(j * 32 + hi));
         atomicMin(uf_addr(NMAXY, root), -y);
