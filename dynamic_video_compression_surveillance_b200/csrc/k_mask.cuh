@@ -65,13 +65,34 @@ k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int
     int s_old = s_new - K;                                  // slot of the plane leaving the window
     if (s_old < 0) s_old += ring_cap;
     int L = nh;                                             // masks in the window before adding frame t
-    for (int t = t0; t < t1; ++t) {
-        if (L == K) { if (t > t0) bs_sub(c, ring[(size_t)s_old * plane_words + idx]); }
-        else ++L;
-        bs_add(c, ring[(size_t)s_new * plane_words + idx]);
-        voted[(size_t)t * plane_words + idx] = bs_ge(c, s_mc[L - 1]) & vm;
-        s_new = s_new + 1 == ring_cap ? 0 : s_new + 1;
-        s_old = s_old + 1 == ring_cap ? 0 : s_old + 1;
+    // The counter chain is serial in t, the plane loads are not: the entering and leaving words of eight frames are fetched
+    // together (sixteen L2 loads in flight), then the counters are walked.
+    constexpr int PF = 8;
+    for (int tb = t0; tb < t1; tb += PF) {
+        uint32_t w_new[PF], w_old[PF];
+        int sn = s_new, so = s_old;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const bool live = tb + u < t1;
+            w_new[u] = live ? ring[(size_t)sn * plane_words + idx] : 0u;
+            // frame t evicts a plane once the window is full and t is not the first frame of the segment (whose history was
+            // added above without the evicted plane)
+            const bool evict = live && (L + u >= K) && (tb + u > t0);
+            w_old[u] = evict ? ring[(size_t)so * plane_words + idx] : 0u;
+            sn = sn + 1 == ring_cap ? 0 : sn + 1;
+            so = so + 1 == ring_cap ? 0 : so + 1;
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int t = tb + u;
+            if (t < t1) {
+                if (L == K) { if (t > t0) bs_sub(c, w_old[u]); }
+                else ++L;
+                bs_add(c, w_new[u]);
+                voted[(size_t)t * plane_words + idx] = bs_ge(c, s_mc[L - 1]) & vm;
+            }
+        }
+        s_new = sn; s_old = so;
     }
 }
 
