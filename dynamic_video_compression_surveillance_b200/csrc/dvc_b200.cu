@@ -305,6 +305,35 @@ static int ensure_dct8(char* ERRBUF) {
     return DVC_OK;
 }
 
+static PerDeviceOnce g_dctn_once;
+static int ensure_dctn(char* ERRBUF) {
+    if (!g_dctn_once.need()) return DVC_OK;
+    static float t[8][8][8];
+    const double pi = 3.14159265358979323846;
+    for (int N = 1; N <= 8; ++N)
+        for (int k = 0; k < 8; ++k)
+            for (int n = 0; n < 8; ++n)
+                t[N - 1][k][n] = (k < N && n < N) ? (float)((k == 0 ? std::sqrt(1.0 / N) : std::sqrt(2.0 / N)) * std::cos(pi * (2 * n + 1) * k / (2.0 * N))) : 0.0f;
+    CU(cudaMemcpyToSymbol(c_dctn, t, sizeof(t)));
+    return DVC_OK;
+}
+
+// partial blocks at the right / bottom edge of frames whose size is not a multiple of the block size
+static int launch_degrade_edges(char* ERRBUF, const uint8_t* frames, const uint32_t* over127, const uint32_t* nonzero,
+                                uint8_t* compressed, uint8_t* overlay, int n, int H, int W, int bs, float q, int flavour,
+                                Counters* counters, cudaStream_t st) {
+    if (H % bs == 0 && W % bs == 0) return DVC_OK;
+    int rc = ensure_dctn(ERRBUF);
+    if (rc) return rc;
+    const int n_edge = (W % bs ? (H + bs - 1) / bs : 0) + (H % bs ? W / bs : 0);
+    dim3 grid(cdiv(n_edge, 64), n);
+    const int wpr = words_per_row(W);
+    if (flavour == DVC_DEGRADE_FD) k_degrade_edges<0><<<grid, 64, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, bs, q, counters);
+    else k_degrade_edges<1><<<grid, 64, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, bs, q, counters);
+    CHECK_LAUNCH();
+    return DVC_OK;
+}
+
 static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* over127, const uint32_t* nonzero,
                           uint8_t* compressed, uint8_t* overlay, int n, int H, int W, int bs, float q, int flavour,
                           Counters* counters, cudaStream_t st) {
@@ -312,9 +341,13 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
     if (bs != 4 && bs != 8) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "block_size %d: the GPU path implements 4 and 8", bs);
     if (flavour == DVC_DEGRADE_MCO && bs != 8) return set_err(ERRBUF, DVC_ERR_INVALID, "MCO flavour uses 8x8 blocks");
     if (!(q > 0.0f)) return set_err(ERRBUF, DVC_ERR_INVALID, "quantization_level must be > 0");
-    if (flavour == DVC_DEGRADE_FD && (H % bs || W % bs))
-        return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "frame %dx%d is not a multiple of block_size %d (clipped edge blocks are not implemented)", W, H, bs);
     if (n <= 0) return DVC_OK;
+    if (H % bs || W % bs) {
+        // full blocks by the kernels below (they floor H and W to whole blocks), partial edge blocks by a small second launch
+        int rc = launch_degrade_edges(ERRBUF, frames, over127, nonzero, compressed, overlay, n, H, W, bs, q, flavour, counters, st);
+        if (rc) return rc;
+        if (H < bs || W < bs) return DVC_OK;
+    }
     if (flavour == DVC_DEGRADE_FD && bs == 4 && W % 8 == 0) {
         QuantConsts qc;
         const float iq = 1.0f / q;
@@ -354,7 +387,8 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
             // that are not 16-byte aligned and for W > 2048 with W % 16 != 0 (bulk copies need 16-byte pieces)
             static const bool ring_env = [] { const char* e = getenv("DVC_K4_PERSIST"); return e ? atoi(e) != 0 : true; }();
             const int gpr = W / 8, nbr = H / 4;
-            const bool ptr16 = ((((uintptr_t)frames) | ((uintptr_t)compressed) | ((uintptr_t)overlay)) & 15u) == 0;
+            const bool ptr16 = ((((uintptr_t)frames) | ((uintptr_t)compressed) | ((uintptr_t)overlay)) & 15u) == 0 &&
+                               ((size_t)H * W * 3) % 16 == 0;          // every frame of the batch starts 16-byte aligned
             if (ring_env && ptr16 && (gpr <= 256 || W % 16 == 0)) {
                 K4Geom g;
                 if (gpr <= 256) {
@@ -420,16 +454,10 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
     } else {
         int rc = ensure_dct8(ERRBUF);
         if (rc) return rc;
-        if (flavour == DVC_DEGRADE_MCO && (H % 8 || W % 8)) {
-            // clipped edge blocks are skipped by the reference (motion_compression_opt.py:159): they only
-            // see the colour round trip.  The kernel covers full blocks; edges handled by a second launch
-            // would go here.
-            return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "MCO flavour needs W, H multiples of 8");
-        }
         dim3 grid(cdiv((size_t)(W / bs) * (H / bs), 128), n);
         static const bool k8_env = [] { const char* e = getenv("DVC_K4_BLOCK8_FAST"); return e ? atoi(e) != 0 : true; }();
         const bool ptr8 = ((((uintptr_t)frames) | ((uintptr_t)compressed) | ((uintptr_t)overlay)) & 7u) == 0;
-        if (bs == 8 && k8_env && ptr8 && q >= 0.01f && q <= 1.0e6f) {
+        if (bs == 8 && W % 8 == 0 && k8_env && ptr8 && q >= 0.01f && q <= 1.0e6f) {
             QuantP qp;
             for (int ne = 0; ne < 3; ++ne) { qp.rcp[ne] = 1.0f / q; qp.nqs[ne] = -q; qp.o[ne] = q; }     // no folded scalings in the 8-point path
             if (flavour == DVC_DEGRADE_FD) k_degrade8<0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
@@ -893,7 +921,7 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
     h->n_masks += T;
     h->counters_host.frames += T;
     h->counters_host.pixels += (uint64_t)T * H * W;
-    h->counters_host.blocks += (uint64_t)T * (H / h->cfg.block_size) * (W / h->cfg.block_size);
+    h->counters_host.blocks += (uint64_t)T * ((H + h->cfg.block_size - 1) / h->cfg.block_size) * ((W + h->cfg.block_size - 1) / h->cfg.block_size);   // clipped edge blocks count (frame_differencing.py:117-118)
     return DVC_OK;
 }
 
@@ -1258,7 +1286,7 @@ extern "C" int dvc_degrade_blend_u8(const uint8_t* bgr, const uint8_t* mask, uin
     if (rc) return rc;
     if (counters) {
         k_counters_add<<<1, 1, 0, st>>>((Counters*)counters, (unsigned long long)n, (unsigned long long)n * H * W,
-                                         (unsigned long long)n * (H / block_size) * (W / block_size));
+                                         (unsigned long long)n * ((H + block_size - 1) / block_size) * ((W + block_size - 1) / block_size));
         CHECK_LAUNCH();
     }
     return DVC_OK;

@@ -601,4 +601,87 @@ k_degrade_generic(const uint8_t* __restrict__ frames, const uint32_t* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Clipped edge blocks: frames whose size is not a multiple of block_size (frame_differencing.py:117-121 slices the last
+// block of a row / column shorter; motion_compression_opt.py:159 skips partial blocks).  One thread per edge block: the right
+// column of partial blocks (all block rows) and the bottom row (all full block columns).  The N-point DCTs (N = 1..8) are
+// plain float32 matrix products; cv2's odd-size routines are not reproduced bit for bit (tolerance bar, like the 8-point path).
+// A frame has at most W / bs + H / bs + 1 such blocks, so this launch costs microseconds.
+// ------------------------------------------------------------------------------------------------
+__constant__ float c_dctn[8][8][8];    // c_dctn[N-1][k][n] = s_N(k) cos(pi (2n+1) k / (2N))
+
+template <int FLAVOUR>
+__global__ void __launch_bounds__(64)
+k_degrade_edges(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127, const uint32_t* __restrict__ nonzero,
+                uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay, int H, int W, int wpr, int bs, float q,
+                Counters* __restrict__ counters) {
+    const int nbx = W / bs, nby = H / bs, nbx_c = (W + bs - 1) / bs, nby_c = (H + bs - 1) / bs;
+    const int n_right = W % bs ? nby_c : 0, n_bottom = H % bs ? nbx : 0;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_right + n_bottom) return;
+    const int bx = e < n_right ? nbx_c - 1 : e - n_right, by = e < n_right ? e : nby_c - 1;
+    const int x0 = bx * bs, y0 = by * bs, bw = min(bs, W - x0), bh = min(bs, H - y0);
+    const uint8_t* fr = frames + (size_t)blockIdx.y * H * W * 3;
+    const size_t plane_off = (size_t)blockIdx.y * H * wpr;
+    unsigned n_motion = 0;
+    bool any_nz = false;
+    for (int r = 0; r < bh; ++r) {
+        const size_t wo = plane_off + (size_t)(y0 + r) * wpr;
+        for (int c = 0; c < bw; ++c) {
+            const int x = x0 + c;
+            const bool hi = (over127[wo + (x >> 5)] >> (x & 31)) & 1u;
+            any_nz |= ((nonzero[wo + (x >> 5)] >> (x & 31)) & 1u) != 0;
+            n_motion += hi ? 1u : 0u;
+            if (overlay) {
+                const size_t o = (size_t)blockIdx.y * H * W * 3 + ((size_t)(y0 + r) * W + x) * 3;
+                overlay[o] = hi ? 0 : frames[o]; overlay[o + 1] = hi ? 0 : frames[o + 1]; overlay[o + 2] = hi ? 255 : frames[o + 2];
+            }
+        }
+    }
+    const bool is_static = FLAVOUR == 0 && !any_nz;
+    if (compressed) {
+        uint8_t* out = compressed + (size_t)blockIdx.y * H * W * 3;
+        if (!is_static) {
+            for (int r = 0; r < bh; ++r)
+                for (int c = 0; c < bw; ++c) {
+                    const size_t o = ((size_t)(y0 + r) * W + x0 + c) * 3;
+                    int b = fr[o], g = fr[o + 1], rr = fr[o + 2];
+                    ycc_roundtrip(b, g, rr);
+                    out[o] = (uint8_t)b; out[o + 1] = (uint8_t)g; out[o + 2] = (uint8_t)rr;
+                }
+        } else {
+            float v[8][8], t[8][8];
+            for (int r = 0; r < bh; ++r)
+                for (int c = 0; c < bw; ++c) {
+                    const size_t o = ((size_t)(y0 + r) * W + x0 + c) * 3;
+                    v[r][c] = (float)(luma_of(fr[o], fr[o + 1], fr[o + 2]) - 128);
+                }
+            const float (*cw)[8] = c_dctn[bw - 1];
+            const float (*ch)[8] = c_dctn[bh - 1];
+            for (int r = 0; r < bh; ++r)                  // rows, then columns (cv2.dct)
+                for (int k = 0; k < bw; ++k) { float a = 0.0f; for (int n = 0; n < bw; ++n) a = fmaf(cw[k][n], v[r][n], a); t[r][k] = a; }
+            for (int c = 0; c < bw; ++c)
+                for (int k = 0; k < bh; ++k) {
+                    float a = 0.0f;
+                    for (int n = 0; n < bh; ++n) a = fmaf(ch[k][n], t[n][c], a);
+                    v[k][c] = __fmul_rn(rintf(__fdiv_rn(a, q)), q);
+                }
+            for (int c = 0; c < bw; ++c)                  // inverse: columns, then rows
+                for (int n = 0; n < bh; ++n) { float a = 0.0f; for (int k = 0; k < bh; ++k) a = fmaf(ch[k][n], v[k][c], a); t[n][c] = a; }
+            for (int r = 0; r < bh; ++r)
+                for (int n = 0; n < bw; ++n) {
+                    float a = 0.0f;
+                    for (int k = 0; k < bw; ++k) a = fmaf(cw[k][n], t[r][k], a);
+                    const uint8_t y = (uint8_t)clip_trunc_u8(__fadd_rn(a, 128.0f));
+                    const size_t o = ((size_t)(y0 + r) * W + x0 + n) * 3;
+                    out[o] = y; out[o + 1] = y; out[o + 2] = y;
+                }
+        }
+    }
+    if (counters) {
+        if (n_motion) atomicAdd(&counters->motion_pixels, (unsigned long long)n_motion);
+        if (is_static) atomicAdd(&counters->static_blocks, 1ull);
+    }
+}
+
 }  // namespace dvc

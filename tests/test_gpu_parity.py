@@ -374,11 +374,95 @@ def test_degrade_mco(P):
         assert np.mean(d <= 2) > 0.97, np.mean(d <= 2)
 
 
+@pytest.mark.parametrize("shape,bs", [((30, 50), 4), ((480, 854), 4), ((37, 41), 4), ((6, 2), 4), ((3, 3), 4), ((90, 122), 8),
+                                      ((1082, 1920), 4), ((20, 36), 8)])
+def test_degrade_fd_clipped_edge_blocks(P, shape, bs):
+    """Frame sizes that are not multiples of the block size: the reference slices the last blocks shorter
+    (frame_differencing.py:117-121).  Full blocks keep their bar (exact for 4x4 when cv2 follows the closed form); the
+    partial blocks run plain float32 N-point DCTs and are held to 1 grey level away from quantiser ties; overlay, the
+    colour round trip of non-static blocks and the counters are exact everywhere."""
+    r = rng(33)
+    h, w = shape
+    exact = bs == 4 and so.cv2_dct4_matches_closed_form()
+    n = 2
+    frames = r.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    frames[1] = (frames[1] // 32) * 32
+    acc = (r.random((n, h, w)) < 0.004).astype(np.uint8) * r.integers(1, 256, (n, h, w), dtype=np.uint8)
+    cnt = torch.zeros(5, dtype=torch.int64, device="cuda")
+    comp, ov = P.degrade_blend(dev(frames), dev(acc), bs, 100, "fd", True, counters=cnt)
+    comp, ov = host(comp), host(ov)
+    hf, wf = (h // bs) * bs, (w // bs) * bs
+    n_static = 0
+    for i in range(n):
+        ref = so.degrade_fd(frames[i], acc[i], bs, 100)
+        assert np.array_equal(ov[i], so.overlay_paint(frames[i], acc[i]))
+        if hf and wf:
+            _check_degraded(comp[i][:hf, :wf], ref[:hf, :wf], frames[i][:hf, :wf], acc[i][:hf, :wf], bs, 100, exact)
+        edge = np.ones((h, w), bool)
+        edge[:hf, :wf] = False
+        static = so.block_all_zero(acc[i], bs)
+        n_static += int(static.sum())
+        st_px = np.repeat(np.repeat(static, bs, 0), bs, 1)[:h, :w]
+        assert np.array_equal(comp[i][edge & ~st_px], ref[edge & ~st_px])          # colour round trip: integer, exact
+        d = np.abs(comp[i].astype(int) - ref.astype(int)).max(axis=2)[edge & st_px]
+        if d.size:
+            assert np.mean(d <= 1) >= 0.9, (shape, i, float(np.mean(d <= 1)))
+    c = cnt.cpu().numpy()
+    assert c[2] == int((acc > 127).sum())
+    assert c[3] == n * (-(-h // bs)) * (-(-w // bs)) and c[4] == n_static
+
+
+def test_degrade_mco_partial_blocks_only_get_the_colour_round_trip(P):
+    r = rng(34)
+    h, w = 70, 100                                      # 8 full block rows + 6 rows, 12 full block columns + 4 columns
+    frames = r.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    masks = np.zeros((2, h, w), np.uint8)
+    masks[0, 10:30, 20:60] = 255
+    comp = host(P.degrade_blend(dev(frames), dev(masks), 8, 100, "mco", False)[0])
+    for i in range(2):
+        ref = so.degrade_mco(frames[i], masks[i])
+        assert np.array_equal(comp[i][64:, :], ref[64:, :]) and np.array_equal(comp[i][:, 96:], ref[:, 96:])
+        d = np.abs(comp[i][:64, :96].astype(int) - ref[:64, :96].astype(int))
+        assert np.mean(d <= 2) > 0.97
+
+
+@pytest.mark.parametrize("mode", ["window", "fd"])
+def test_loops_on_frame_sizes_not_multiple_of_block(P, mode):
+    """854 x 480-like geometry (W % 4 == 2): every kernel of both loops on a size with clipped edge blocks."""
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n = 62, 110, 16
+    frames = make_clip((h, w), n, seed=12).frames()
+    exact = so.cv2_dct4_matches_closed_form()
+    if mode == "window":
+        kw = dict(window_size=5, alpha_fraction=0.2, morph_kernel=2, kernel_size=7)
+        ref = loops.window_loop(list(frames), **kw)
+        seed, mref = so.bgr2gray(frames[0]), np.stack(ref["mask"])
+    else:
+        kw = dict(min_area=50)
+        ref = loops.fd_loop(list(frames), **kw)
+        seed, mref = loops.first_frame_gray_fd(frames[0]), np.stack(ref["acc"])
+    pipe = P.FramePipeline(w, h, mode, max_batch=8, **kw)
+    pipe.begin_stream(seed)
+    ov = np.empty((n - 1, h, w, 3), np.uint8); cp = np.empty_like(ov); mk = np.empty((n - 1, h, w), np.uint8)
+    pipe.process_host(np.ascontiguousarray(frames[1:]), ov, cp, mk)
+    c = pipe.counters()
+    pipe.close()
+    assert np.array_equal(mk, mref)
+    assert np.array_equal(ov, np.stack(ref["overlay"]))
+    rc = np.stack(ref["compressed"])
+    hf, wf = (h // 4) * 4, (w // 4) * 4
+    d = np.abs(cp.astype(int) - rc.astype(int))
+    if exact:
+        assert d[:, :hf, :wf].max() == 0
+    assert np.mean(d[:, hf:, :] <= 1) > 0.9 and np.mean(d[:, :, wf:] <= 1) > 0.9
+    assert c["blocks"] == (n - 1) * (-(-h // 4)) * (-(-w // 4))
+
+
 def test_unsupported_is_loud(P):
     from dynamic_video_compression_surveillance_b200._lib import DvcUnsupported
-    frames = torch.zeros((1, 30, 50, 3), dtype=torch.uint8, device="cuda")
+    frames = torch.zeros((1, 32, 48, 3), dtype=torch.uint8, device="cuda")
     with pytest.raises(DvcUnsupported):
-        P.degrade_blend(frames, torch.zeros((1, 30, 50), dtype=torch.uint8, device="cuda"), 4, 100, "fd")
+        P.degrade_blend(frames, torch.zeros((1, 32, 48), dtype=torch.uint8, device="cuda"), 6, 100, "fd")
     with pytest.raises(NotImplementedError):
         P.FramePipeline(64, 64, "fd", block_size=6)
 
