@@ -120,6 +120,24 @@ def test_fd_scale_factor_resizes_on_gpu(tmp_path, dropin_modules):
     assert stats["motion_pixels"] == int(sum((a > 127).sum() for a in ref["acc"]))
 
 
+def test_fd_video_size_not_multiple_of_block(tmp_path, dropin_modules):
+    """A 130 x 98 clip (W % 4 == 2, H % 4 == 2): the reference slices the edge blocks (frame_differencing.py:117-121) and
+    so does the GPU path; nothing is rejected."""
+    fd, _ = dropin_modules
+    h, w, n = 98, 130, 24
+    src = str(tmp_path / "odd.mp4")
+    _write_clip(src, _smooth_clip(h, w, n, 9))
+    decoded = _read_all(src)
+    stats = {}
+    fd.filter_and_dilate_movements(src, str(tmp_path / "out"), stats_out=stats, max_batch=8)
+    vdir = os.path.join(str(tmp_path / "out"), "odd")
+    assert len(_read_all(os.path.join(vdir, "compressed_final_video.mp4"))) == n - 1
+    ref = loops.fd_loop(decoded, degrade=False)
+    assert stats["frames"] == n - 1
+    assert stats["motion_pixels"] == int(sum((a > 127).sum() for a in ref["acc"]))
+    assert stats["blocks"] == (n - 1) * 25 * 33
+
+
 def test_fd_error_convention(tmp_path, dropin_modules):
     fd, _ = dropin_modules
     assert fd.process_single_video_fd(str(tmp_path / "missing.mp4"), str(tmp_path / "o")) is None     # logs, never raises
