@@ -66,6 +66,8 @@ def filter_and_dilate_movements(video_path, output_dir, block_size=4, search_are
             s.release()
     if stats_out is not None:
         stats_out.update(run.counters)
+    if run.counters:
+        _hl.write_gpu_statistics(out_dir, run.counters)
 
     total = time.time() - t_start
     avg = sum(run.per_frame_s) / len(run.per_frame_s) if run.per_frame_s else 0

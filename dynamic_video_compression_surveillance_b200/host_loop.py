@@ -232,6 +232,21 @@ def _rectangles_from_mask_cv2(mask: np.ndarray) -> np.ndarray:
     return out
 
 
+def write_gpu_statistics(out_dir: str, counters: dict) -> str:
+    """The in-loop statistics north_star asks for, next to execution_times.txt (an extra file: the reference's
+    performance_analysis.py ignores it; its own compression percentage is derived from file sizes, perf:195-204).
+    motion_pixel_percent = share of pixels painted in the overlay (acc > 127), static_block_percent = share of blocks degraded."""
+    import json
+    c = dict(counters)
+    px, bl = max(1, int(c.get("pixels", 0))), max(1, int(c.get("blocks", 0)))
+    c["motion_pixel_percent"] = 100.0 * int(c.get("motion_pixels", 0)) / px
+    c["static_block_percent"] = 100.0 * int(c.get("static_blocks", 0)) / bl
+    path = os.path.join(out_dir, "gpu_statistics.json")
+    with open(path, "w") as f:
+        json.dump(c, f, indent=1)
+    return path
+
+
 def attach_file_log(output_dir: str) -> str:
     """Add a processing.log FileHandler to the root logger unless one for that file is already attached
     (motion_compression_opt.py:8-27 behaviour)."""

@@ -79,6 +79,9 @@ def test_process_single_video_fd(tmp_path, dropin_modules):
     for name in ("processing.log", "dilated_motion_mask_video.mp4", "compressed_final_video.mp4", "execution_times.txt"):
         assert os.path.exists(os.path.join(vdir, name)), name
     assert calls == [50, 100]                                            # frame_differencing.py:137-138
+    import json
+    gs = json.load(open(os.path.join(vdir, "gpu_statistics.json")))
+    assert gs["frames"] == n - 1 and 0.0 <= gs["motion_pixel_percent"] <= 100.0 and 0.0 <= gs["static_block_percent"] <= 100.0
     assert len(_read_all(os.path.join(vdir, "dilated_motion_mask_video.mp4"))) == n - 1
     assert len(_read_all(os.path.join(vdir, "compressed_final_video.mp4"))) == n - 1
     txt = open(os.path.join(vdir, "execution_times.txt")).read().splitlines()
