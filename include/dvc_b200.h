@@ -60,7 +60,8 @@ enum { DVC_SHAPE_RECT = 0, DVC_SHAPE_ELLIPSE = 1 };
 enum { DVC_DEGRADE_FD = 0, DVC_DEGRADE_MCO = 1 };
 
 typedef struct dvc_config {
-    int32_t width, height;        /* frame size after the reference's resize (scale_factor 1.0) */
+    int32_t width, height;        /* frame size after the reference's resize (frame_differencing.py:59-60); any size >= 1:
+                                   * blocks clipped by the frame edge are handled as the reference slices them (:117-121) */
     int32_t mode;                 /* DVC_MODE_* */
     int32_t block_size;           /* frame_differencing.py:22 (4); 4 or 8 */
     float   motion_threshold;     /* frame_differencing.py:24 (0.5); cv2.threshold floors it */
@@ -126,7 +127,9 @@ int dvc_process_batch(dvc_handle* h, const uint8_t* frames_dev, int32_t n_frames
 int dvc_set_overlap(dvc_handle* h, int32_t on);
 int dvc_flush(dvc_handle* h, void* stream);     /* make `stream` wait for every batch issued so far */
 /* Same loop with HOST buffers (pinned for full speed): frames are uploaded, processed and the results
- * downloaded in chunks of cfg.max_batch, double-buffered on the handle's own copy/compute streams.
+ * downloaded in chunks of min(cfg.max_batch, 8) frames, double-buffered on the handle's own copy/compute
+ * streams.  With cfg.src_width / src_height set, frames_host holds frames of that size and the library does the
+ * reference's cv2.resize (frame_differencing.py:91) after the upload; the outputs are width x height.
  * Returns after everything has landed in the host buffers.  Any n_frames >= 0. */
 int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64_t n_frames, uint8_t* overlay_host,
                      uint8_t* compressed_host, uint8_t* mask_host);
