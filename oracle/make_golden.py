@@ -31,6 +31,8 @@ FD_CASES = {
     "fd_default_96x128": (96, 128, 26, 11, False, {}),
     "fd_main_cfg_64x96": (64, 96, 20, 12, False, dict(block_size=8, kernel_size=10, release_factor=0.3)),
     "fd_minarea50_noise_72x112": (72, 112, 18, 13, True, dict(min_area=50, motion_threshold=6.0, kernel_size=3)),
+    # frame size that is not a multiple of the block size: the reference slices the edge blocks (frame_differencing.py:117-121)
+    "fd_clipped_126x218": (126, 218, 16, 14, False, dict(min_area=50)),
 }
 
 
@@ -98,10 +100,14 @@ def make_window(name="window_vote_48x80"):
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    only = sys.argv[1:]                       # optional fixture names: regenerate just those
     for name, spec in FD_CASES.items():
-        make_fd(name, spec)
-    make_mco()
-    make_window()
+        if not only or name in only:
+            make_fd(name, spec)
+    if not only or "mco_compress_64x96" in only:
+        make_mco()
+    if not only or "window_vote_48x80" in only:
+        make_window()
 
 
 if __name__ == "__main__":

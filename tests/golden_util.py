@@ -9,6 +9,8 @@ from dynamic_video_compression_surveillance_b200.synth import make_clip
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FD_FIXTURES = ["fd_default_96x128", "fd_main_cfg_64x96", "fd_minarea50_noise_72x112"]
+# frame size not a multiple of the block size: edge blocks clipped by the reference (frame_differencing.py:117-121)
+FD_CLIPPED_FIXTURE = "fd_clipped_126x218"
 
 
 def sha(a):

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import loops, stage_ops as so
-from tests.golden_util import FD_FIXTURES, load_fd, sha, unpack
+from tests.golden_util import FD_CLIPPED_FIXTURE, FD_FIXTURES, load_fd, sha, unpack
 
 pytestmark = pytest.mark.gpu
 
@@ -456,6 +456,29 @@ def test_loops_on_frame_sizes_not_multiple_of_block(P, mode):
         assert d[:, :hf, :wf].max() == 0
     assert np.mean(d[:, hf:, :] <= 1) > 0.9 and np.mean(d[:, :, wf:] <= 1) > 0.9
     assert c["blocks"] == (n - 1) * (-(-h // 4)) * (-(-w // 4))
+
+
+def test_fd_loop_against_reference_fixture_with_clipped_blocks(P):
+    """126 x 218 frames through the UNMODIFIED reference (tests/golden/fd_clipped_126x218.npz): masks and overlays are
+    exact; compressed frames are exact on whole blocks and within a grey level on the clipped edge blocks."""
+    z, frames, kw, (h, w, n) = load_fd(FD_CLIPPED_FIXTURE)
+    exact = so.cv2_dct4_matches_closed_form()
+    pipe = P.FramePipeline(w, h, "fd", max_batch=8, **kw)
+    pipe.begin_stream(loops.first_frame_gray_fd(frames[0]))
+    ov = np.empty((n - 1, h, w, 3), np.uint8); cp = np.empty_like(ov); mk = np.empty((n - 1, h, w), np.uint8)
+    pipe.process_host(np.ascontiguousarray(frames[1:]), ov, cp, mk)
+    pipe.close()
+    assert np.array_equal(mk, z["acc"])
+    assert [sha(x) for x in ov] == list(z["overlay_sha"])
+    hf, wf = (h // 4) * 4, (w // 4) * 4
+    tail = z["compressed_tail"]
+    d = np.abs(cp[-2:].astype(int) - tail.astype(int))
+    if exact:
+        assert d[:, :hf, :wf].max() == 0
+    else:
+        assert np.mean(d[:, :hf, :wf] > 1) < 1e-3
+    assert np.mean(d[:, hf:, :] <= 1) > 0.9 and np.mean(d[:, :, wf:] <= 1) > 0.9
+    assert (z["acc"][-1][hf:, :] == 0).any() or (z["acc"][-1][:, wf:] == 0).any()      # the fixture does have static edge pixels
 
 
 def test_unsupported_is_loud(P):

@@ -5,10 +5,10 @@ import numpy as np
 import pytest
 
 from oracle import loops, stage_ops as so
-from tests.golden_util import FD_FIXTURES, GOLDEN, load_fd, sha, unpack
+from tests.golden_util import FD_CLIPPED_FIXTURE, FD_FIXTURES, GOLDEN, load_fd, sha, unpack
 
 
-@pytest.mark.parametrize("name", FD_FIXTURES)
+@pytest.mark.parametrize("name", FD_FIXTURES + [FD_CLIPPED_FIXTURE])
 def test_fd_loop_matches_reference_fixture(name):
     z, frames, kw, (h, w, n) = load_fd(name)
     got = loops.fd_loop(list(frames), **kw)
