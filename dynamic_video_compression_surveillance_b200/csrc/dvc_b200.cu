@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/dvc_b200.h"
@@ -136,8 +137,24 @@ static void window_min_counts(double alpha, int K, MinCounts& mc) {
 // Function attributes and __constant__ uploads are per device: one-time set-up is tracked per CUDA device ordinal so that
 // handles on several GPUs in one process all get it.
 struct PerDeviceOnce {
+    std::mutex mu;
     bool done[64] = {};
-    bool need() { int d = 0; cudaGetDevice(&d); d &= 63; if (done[d]) return false; done[d] = true; return true; }
+    struct Guard {
+        PerDeviceOnce* o; int d;
+        explicit operator bool() const { return o != nullptr; }
+        void commit() { o->done[d] = true; }              // not reached when the set-up bails out: it is retried next time
+        ~Guard() { if (o) o->mu.unlock(); }
+    };
+    // `if (auto g = once.begin()) { set-up; g.commit(); }`: the lock is held while the first caller sets up, so a second thread
+    // cannot launch before the attributes / tables are in place
+    Guard begin() {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        mu.lock();
+        if (done[d]) { mu.unlock(); return Guard{nullptr, d}; }
+        return Guard{this, d};
+    }
 };
 
 static int g_morph_smem_limit = 0;
@@ -150,12 +167,13 @@ static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, 
         if (src != dst) CU(cudaMemcpyAsync(dst, src, (size_t)n * H * wpr * 4, cudaMemcpyDeviceToDevice, st));
         return DVC_OK;
     }
-    if (g_morph_once.need()) {
+    if (auto once = g_morph_once.begin()) {
         int dev = 0, lim = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         CU(cudaFuncSetAttribute(k_morph_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         g_morph_smem_limit = lim;
+        once.commit();
     }
     const int halo = ch.halo_top + ch.halo_bot;
     for (int i = 0; i < ch.n; ++i)
@@ -295,19 +313,22 @@ static int launch_resize(char* ERRBUF, const uint8_t* src, uint8_t* dst, int n, 
 
 static PerDeviceOnce g_dct8_once;
 static int ensure_dct8(char* ERRBUF) {
-    if (!g_dct8_once.need()) return DVC_OK;
+    auto once = g_dct8_once.begin();
+    if (!once) return DVC_OK;
     float t[8][4];
     const double pi = 3.14159265358979323846;
     for (int k = 0; k < 8; ++k)
         for (int n = 0; n < 4; ++n)
             t[k][n] = (float)((k == 0 ? std::sqrt(1.0 / 8.0) : 0.5) * std::cos(pi * (2 * n + 1) * k / 16.0));
     CU(cudaMemcpyToSymbol(c_dct8, t, sizeof(t)));
+    once.commit();
     return DVC_OK;
 }
 
 static PerDeviceOnce g_dctn_once;
 static int ensure_dctn(char* ERRBUF) {
-    if (!g_dctn_once.need()) return DVC_OK;
+    auto once = g_dctn_once.begin();
+    if (!once) return DVC_OK;
     static float t[8][8][8];
     const double pi = 3.14159265358979323846;
     for (int N = 1; N <= 8; ++N)
@@ -315,6 +336,7 @@ static int ensure_dctn(char* ERRBUF) {
             for (int n = 0; n < 8; ++n)
                 t[N - 1][k][n] = (k < N && n < N) ? (float)((k == 0 ? std::sqrt(1.0 / N) : std::sqrt(2.0 / N)) * std::cos(pi * (2 * n + 1) * k / (2.0 * N))) : 0.0f;
     CU(cudaMemcpyToSymbol(c_dctn, t, sizeof(t)));
+    once.commit();
     return DVC_OK;
 }
 
@@ -365,9 +387,10 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         const bool tma = tma_env && W % 16 == 0;
         const size_t smem = tma ? (size_t)K4_STAGE_BYTES : 0;
         static PerDeviceOnce attr_set;
-        if (attr_set.need()) {
+        if (auto once = attr_set.begin()) {
             CU(cudaFuncSetAttribute(k_degrade4<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CU(cudaFuncSetAttribute(k_degrade4<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            once.commit();
         }
         static const bool packed_env = [] { const char* e = getenv("DVC_K4_PACKED"); return e ? atoi(e) != 0 : true; }();
         if (packed_env && q >= 0.01f && q <= 1.0e6f) {
@@ -380,8 +403,9 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                 qp.o[ne] = q / (float)(1 << ne);
             }
             static PerDeviceOnce attr_p;
-            if (attr_p.need()) {
+            if (auto once = attr_p.begin()) {
                 CU(cudaFuncSetAttribute(k_degrade4p<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                once.commit();
             }
             // DVC_K4_PERSIST=0 selects the CTA-per-256-groups kernel (k_degrade4p) for A/B; it is also the fallback for pointers
             // that are not 16-byte aligned and for W > 2048 with W % 16 != 0 (bulk copies need 16-byte pieces)
@@ -434,10 +458,11 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                     const size_t smem_s = smem_need(S);
                     const unsigned ctas = (unsigned)std::min(sg.n_tiles, env_ctas > 0 ? env_ctas : sms);
                     static PerDeviceOnce attr_s;
-                    if (attr_s.need()) {
+                    if (auto once = attr_s.begin()) {
                         CU(cudaFuncSetAttribute(k_degrade4s<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                         CU(cudaFuncSetAttribute(k_degrade4s<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                         CU(cudaFuncSetAttribute(k_degrade4s<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                        once.commit();
                     }
                     if (G == 1) k_degrade4s<1, 1><<<ctas, 32 + 256, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
                     else if (G == 3) k_degrade4s<3, 1><<<ctas, 32 + 768, smem_s, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters, sg);
