@@ -621,6 +621,46 @@ def test_handles_on_two_devices_in_one_process(P):
     torch.cuda.set_device(0)
 
 
+def test_handles_driven_from_several_host_threads(P):
+    """Four host threads, each with its own handle (the GUI runs the entry points from worker threads, windows.py:94-101):
+    creation, one-time kernel set-up and the loops race each other; every stream must still equal the oracle."""
+    import threading
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w, n = 64, 96, 24
+    kw = dict(window_size=5, alpha_fraction=0.2, morph_kernel=2, kernel_size=7)
+    clips = [make_clip((h, w), n, seed=40 + i).frames() for i in range(4)]
+    refs = [loops.window_loop(list(c), **kw) if i % 2 == 0 else loops.fd_loop(list(c)) for i, c in enumerate(clips)]
+    results, errors = [None] * 4, []
+
+    def work(i):
+        try:
+            mode = "window" if i % 2 == 0 else "fd"
+            pipe = P.FramePipeline(w, h, mode, max_batch=8, **(kw if mode == "window" else {}))
+            pipe.begin_stream(so.bgr2gray(clips[i][0]) if mode == "window" else loops.first_frame_gray_fd(clips[i][0]))
+            ov = np.empty((n - 1, h, w, 3), np.uint8); cp = np.empty_like(ov); mk = np.empty((n - 1, h, w), np.uint8)
+            for a in range(0, n - 1, 8):
+                b = min(n - 1, a + 8)
+                pipe.process_host(np.ascontiguousarray(clips[i][1 + a:1 + b]), ov[a:b], cp[a:b], mk[a:b])
+            pipe.close()
+            results[i] = (ov, cp, mk)
+        except Exception as e:          # surfaced below
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    exact = so.cv2_dct4_matches_closed_form()
+    for i in range(4):
+        ov, cp, mk = results[i]
+        assert np.array_equal(mk, np.stack(refs[i]["mask" if i % 2 == 0 else "acc"])), i
+        assert np.array_equal(ov, np.stack(refs[i]["overlay"])), i
+        if exact:
+            assert np.array_equal(cp, np.stack(refs[i]["compressed"])), i
+
+
 def test_state_handoff_between_handles(P):
     """Frame-chunk sharding: a second handle continues a stream from a state blob."""
     from dynamic_video_compression_surveillance_b200.synth import make_clip
