@@ -48,6 +48,12 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-overlap", action="store_true", help="strict per-batch stream order instead of the two-stream pipeline")
+    # overrides of the loop parameters for the other BASELINE configs (e.g. config 3: --resolution 4k --frames 900
+    # --kernel-size 15 --morph-kernel 15 --morph-shape rect); the default line is config 2
+    p.add_argument("--kernel-size", type=int, default=None)
+    p.add_argument("--morph-kernel", type=int, default=None)
+    p.add_argument("--morph-shape", default=None, choices=["ellipse", "rect"])
+    p.add_argument("--window-size", type=int, default=None)
     return p.parse_args()
 
 
@@ -193,13 +199,16 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, h, w):
-    name = {"window": "north_star loop: gray/absdiff/threshold -> K=5 window vote -> ellipse-2 close/open -> 7x7 dilate -> "
+    name = {"window": f"north_star loop: gray/absdiff/threshold -> K={LOOP['window_size']} window vote -> {LOOP['morph_shape']}-"
+                      f"{LOOP['morph_kernel']} close/open -> {LOOP['kernel_size']}x{LOOP['kernel_size']} dilate -> "
                       "overlay + 4x4 block-DCT degrade",
             "fd": "frame_differencing.py loop: gray/blur5/absdiff/threshold -> contour filter -> 7x7 dilate -> EMA -> overlay + "
                   "4x4 block-DCT degrade"}[args.mode]
-    return {"workload": f"BASELINE configs[1]: single {args.resolution} ({w}x{h}) synthetic stream per GPU, {args.frames} frames, "
+    cfg_name = "BASELINE configs[1]" if (args.resolution, args.frames) == ("1080p", 1800) else "BASELINE-style config"
+    return {"workload": f"{cfg_name}: single {args.resolution} ({w}x{h}) synthetic stream per GPU, {args.frames} frames, "
                         f"{name}", "mode": args.mode, "frames_per_step": args.frames, "max_batch": args.max_batch, "two_stream_overlap": not args.no_overlap,
-            "l2_policy": "inputs (clip 11.2 GB) and outputs (22.4 GB) per step are far larger than the 126 MB L2"}
+            "l2_policy": f"inputs (clip {args.frames * h * w * 3 / 1e9:.1f} GB) and outputs ({2 * args.frames * h * w * 3 / 1e9:.1f} GB) per step "
+                         "are far larger than the 126 MB L2"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -383,6 +392,10 @@ def run_b200(args, rank, world, local_rank):
 
 def main():
     args = parse_args()
+    for key, val in (("kernel_size", args.kernel_size), ("morph_kernel", args.morph_kernel), ("morph_shape", args.morph_shape),
+                     ("window_size", args.window_size)):
+        if val is not None:
+            LOOP[key] = val
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
