@@ -263,17 +263,30 @@ DEVI void rect_pass(uint32_t* A, uint32_t* B, const BandCtx& c, uint32_t flip) {
         }
     }
     __syncthreads();
-    for (int r = c.ra; r < c.rb; ++r) {
-        uint32_t acc = 0;
-        if (r - R >= c.r_lo && r + R < c.r_hi) {
-            const uint32_t* q = B + (r - R) * c.wpr + c.j;
+    // vertical: the thread walks its rows with the last K row words in registers (slot = row offset mod K, all indices
+    // compile-time after unrolling by K): one shared-memory load per output instead of K
+    {
+        uint32_t w[K];
 #pragma unroll
-            for (int d = 0; d < K; ++d) acc |= q[d * c.wpr];
-        } else {
-            const int a0 = max(r - R, c.r_lo), a1 = min(r + R, c.r_hi - 1);
-            for (int rr = a0; rr <= a1; ++rr) acc |= B[rr * c.wpr + c.j];
+        for (int d = 0; d < K - 1; ++d) {                      // rows ra-R .. ra+R-1 -> slots 0 .. K-2
+            const int rr = c.ra - R + d;
+            w[d] = (rr >= c.r_lo && rr < c.r_hi) ? B[rr * c.wpr + c.j] : 0u;
         }
-        A[r * c.wpr + c.j] = (acc ^ flip) & c.vm;
+        w[K - 1] = 0u;
+        for (int r0 = c.ra; r0 < c.rb; r0 += K) {
+#pragma unroll
+            for (int u = 0; u < K; ++u) {
+                const int r = r0 + u;
+                if (r < c.rb) {
+                    const int rn = r + R;                      // the row entering the window: slot (u + K - 1) % K
+                    w[(u + K - 1) % K] = (rn >= c.r_lo && rn < c.r_hi) ? B[rn * c.wpr + c.j] : 0u;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int d = 0; d < K; ++d) acc |= w[d];
+                    A[r * c.wpr + c.j] = (acc ^ flip) & c.vm;
+                }
+            }
+        }
     }
     __syncthreads();
 }
