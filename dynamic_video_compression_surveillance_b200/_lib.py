@@ -69,6 +69,7 @@ SYMBOLS = {
     "dvc_mask_rectangles_u8": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "dvc_resize_linear_u8": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "dvc_degrade_blend_u8": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
+    "dvc_dct_blocks_f32": (C.c_int, [_P, _P, _L, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -311,42 +311,11 @@ static int launch_resize(char* ERRBUF, const uint8_t* src, uint8_t* dst, int n, 
     return DVC_OK;
 }
 
-static PerDeviceOnce g_dct8_once;
-static int ensure_dct8(char* ERRBUF) {
-    auto once = g_dct8_once.begin();
-    if (!once) return DVC_OK;
-    float t[8][4];
-    const double pi = 3.14159265358979323846;
-    for (int k = 0; k < 8; ++k)
-        for (int n = 0; n < 4; ++n)
-            t[k][n] = (float)((k == 0 ? std::sqrt(1.0 / 8.0) : 0.5) * std::cos(pi * (2 * n + 1) * k / 16.0));
-    CU(cudaMemcpyToSymbol(c_dct8, t, sizeof(t)));
-    once.commit();
-    return DVC_OK;
-}
-
-static PerDeviceOnce g_dctn_once;
-static int ensure_dctn(char* ERRBUF) {
-    auto once = g_dctn_once.begin();
-    if (!once) return DVC_OK;
-    static float t[8][8][8];
-    const double pi = 3.14159265358979323846;
-    for (int N = 1; N <= 8; ++N)
-        for (int k = 0; k < 8; ++k)
-            for (int n = 0; n < 8; ++n)
-                t[N - 1][k][n] = (k < N && n < N) ? (float)((k == 0 ? std::sqrt(1.0 / N) : std::sqrt(2.0 / N)) * std::cos(pi * (2 * n + 1) * k / (2.0 * N))) : 0.0f;
-    CU(cudaMemcpyToSymbol(c_dctn, t, sizeof(t)));
-    once.commit();
-    return DVC_OK;
-}
-
 // partial blocks at the right / bottom edge of frames whose size is not a multiple of the block size
 static int launch_degrade_edges(char* ERRBUF, const uint8_t* frames, const uint32_t* over127, const uint32_t* nonzero,
                                 uint8_t* compressed, uint8_t* overlay, int n, int H, int W, int bs, float q, int flavour,
                                 Counters* counters, cudaStream_t st) {
     if (H % bs == 0 && W % bs == 0) return DVC_OK;
-    int rc = ensure_dctn(ERRBUF);
-    if (rc) return rc;
     const int n_edge = (W % bs ? (H + bs - 1) / bs : 0) + (H % bs ? W / bs : 0);
     dim3 grid(cdiv(n_edge, 64), n);
     const int wpr = words_per_row(W);
@@ -477,8 +446,6 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         else if (tma) k_degrade4<false, true><<<grid, 256, smem, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
         else k_degrade4<false, false><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
     } else {
-        int rc = ensure_dct8(ERRBUF);
-        if (rc) return rc;
         dim3 grid(cdiv((size_t)(W / bs) * (H / bs), 128), n);
         static const bool k8_env = [] { const char* e = getenv("DVC_K4_BLOCK8_FAST"); return e ? atoi(e) != 0 : true; }();
         const bool ptr8 = ((((uintptr_t)frames) | ((uintptr_t)compressed) | ((uintptr_t)overlay)) & 7u) == 0;
@@ -1314,5 +1281,15 @@ extern "C" int dvc_degrade_blend_u8(const uint8_t* bgr, const uint8_t* mask, uin
                                          (unsigned long long)n * ((H + block_size - 1) / block_size) * ((W + block_size - 1) / block_size));
         CHECK_LAUNCH();
     }
+    return DVC_OK;
+}
+
+extern "C" int dvc_dct_blocks_f32(const float* src, float* dst, int64_t n, int32_t bh, int32_t bw, int32_t inverse, void* stream) {
+    char* ERRBUF = nullptr;
+    if (n < 0 || bh < 1 || bh > 8 || bw < 1 || bw > 8) return set_err(nullptr, DVC_ERR_INVALID, "dvc_dct_blocks_f32: n >= 0, block sides 1..8");
+    if (n == 0) return DVC_OK;
+    if (!src || !dst) return set_err(nullptr, DVC_ERR_INVALID, "dvc_dct_blocks_f32: null pointer");
+    k_dct_blocks<<<(unsigned)cdiv((size_t)n, 128), 128, 0, (cudaStream_t)stream>>>(src, dst, (long long)n, bh, bw, inverse);
+    CHECK_LAUNCH();
     return DVC_OK;
 }

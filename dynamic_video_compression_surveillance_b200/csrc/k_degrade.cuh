@@ -15,31 +15,9 @@
 // The 4-point DCT below reproduces cv2.dct / cv2.idct (IPP build, float32) bit for bit: the operation
 // order and the two FMAs were recovered by search against cv2 on 200 000 random vectors.
 #pragma once
-#include "common.cuh"
+#include "k_dct8.cuh"
 
 namespace dvc {
-
-// 0.5*cos(pi/8)*sqrt(2) ... : orthonormal 4-point DCT-II coefficients, correctly rounded to float32
-#define DVC_C1 0x1.4e7aeap-1f   /* cos(pi/8)  / sqrt(2) = 0.6532815 */
-#define DVC_C3 0x1.1517a8p-2f   /* cos(3pi/8) / sqrt(2) = 0.2705981 */
-
-DEVI void dct4_fwd(float& x0, float& x1, float& x2, float& x3) {
-    const float s0 = __fadd_rn(x0, x3), s1 = __fadd_rn(x1, x2);
-    const float d0 = __fsub_rn(x0, x3), d1 = __fsub_rn(x1, x2);
-    x0 = __fmul_rn(__fadd_rn(s0, s1), 0.5f);
-    x2 = __fmul_rn(__fsub_rn(s0, s1), 0.5f);
-    x1 = __fmaf_rn(DVC_C3, d1, __fmul_rn(DVC_C1, d0));
-    x3 = __fmaf_rn(DVC_C3, d0, -__fmul_rn(DVC_C1, d1));
-}
-DEVI void dct4_inv(float& x0, float& x1, float& x2, float& x3) {
-    const float e0 = __fmul_rn(__fadd_rn(x0, x2), 0.5f), e1 = __fmul_rn(__fsub_rn(x0, x2), 0.5f);
-    const float o0 = __fmaf_rn(DVC_C3, x3, __fmul_rn(DVC_C1, x1));
-    const float o1 = __fmaf_rn(DVC_C3, x1, -__fmul_rn(DVC_C1, x3));
-    x0 = __fadd_rn(e0, o0);
-    x3 = __fsub_rn(e0, o0);
-    x1 = __fadd_rn(e1, o1);
-    x2 = __fsub_rn(e1, o1);
-}
 
 // np.round(d / q) * q in float32: IEEE division, round half to even, exact product
 DEVI float quantise(float d, float q) { return __fmul_rn(rintf(__fdiv_rn(d, q)), q); }
@@ -413,80 +391,12 @@ k_degrade4(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
 // General path: block_size 4 or 8, any W, H that are multiples of block_size, both flavours.
 // One thread per block, bytewise access.  Used for block_size 8 (frame_differencing.py:203 main
 // config), for the MCO flavour (motion_compression_opt.py:152-183) and for widths the fast path
-// cannot take.  The 8-point DCT is the orthonormal DCT-II in even/odd matrix form in float32; cv2's
-// 8x8 routine (IPP) is not reproduced bit for bit -- results agree within 1 grey level away from
-// exact quantiser ties.
+// cannot take.  8x8 blocks use the exact restatement of cv2's 2-D routine in k_dct8.cuh.
 // ------------------------------------------------------------------------------------------------
-__constant__ float c_dct8[8][4];   // c_dct8[k][n] = s(k) cos(pi (2n+1) k / 16), n < 4
-
-DEVI void dct8_fwd(float (&x)[8]) {
-    float a[4], b[4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) { a[n] = x[n] + x[7 - n]; b[n] = x[n] - x[7 - n]; }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float (&s)[4] = (k & 1) ? b : a;
-        float acc = 0.0f;
-#pragma unroll
-        for (int n = 0; n < 4; ++n) acc = fmaf(c_dct8[k][n], s[n], acc);
-        x[k] = acc;
-    }
-}
-DEVI void dct8_inv(float (&x)[8]) {
-    float e[4], o[4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-        float ae = 0.0f, ao = 0.0f;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            ae = fmaf(c_dct8[2 * m][n], x[2 * m], ae);
-            ao = fmaf(c_dct8[2 * m + 1][n], x[2 * m + 1], ao);
-        }
-        e[n] = ae; o[n] = ao;
-    }
-#pragma unroll
-    for (int n = 0; n < 4; ++n) { x[n] = e[n] + o[n]; x[7 - n] = e[n] - o[n]; }
-}
-
 template <int BS>
 DEVI void degrade_plane(float (&v)[BS][BS], float q) {
-    if constexpr (BS == 4) {
-        degrade_block4(v, q);
-    } else {
-        float t[8];
-#pragma unroll
-        for (int r = 0; r < BS; ++r) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) t[c] = v[r][c];
-            dct8_fwd(t);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) v[r][c] = t[c];
-        }
-#pragma unroll
-        for (int c = 0; c < BS; ++c) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) t[r] = v[r][c];
-            dct8_fwd(t);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) v[r][c] = quantise(t[r], q);
-        }
-#pragma unroll
-        for (int r = 0; r < BS; ++r) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) t[c] = v[r][c];
-            dct8_inv(t);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) v[r][c] = t[c];
-        }
-#pragma unroll
-        for (int c = 0; c < BS; ++c) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) t[r] = v[r][c];
-            dct8_inv(t);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) v[r][c] = t[r];
-        }
-    }
+    if constexpr (BS == 4) degrade_block4(v, q);
+    else degrade_block8_exact(v, [q](float d) { return quantise(d, q); });
 }
 
 template <int BS, int FLAVOUR>   // FLAVOUR 0 = FD, 1 = MCO
@@ -604,12 +514,10 @@ k_degrade_generic(const uint8_t* __restrict__ frames, const uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------
 // Clipped edge blocks: frames whose size is not a multiple of block_size (frame_differencing.py:117-121 slices the last
 // block of a row / column shorter; motion_compression_opt.py:159 skips partial blocks).  One thread per edge block: the right
-// column of partial blocks (all block rows) and the bottom row (all full block columns).  The N-point DCTs (N = 1..8) are
-// plain float32 matrix products; cv2's odd-size routines are not reproduced bit for bit (tolerance bar, like the 8-point path).
+// column of partial blocks (all block rows) and the bottom row (all full block columns).  Clipped blocks are bit-exact
+// through the 1-D routines of k_dct8.cuh (every length 1..8).
 // A frame has at most W / bs + H / bs + 1 such blocks, so this launch costs microseconds.
 // ------------------------------------------------------------------------------------------------
-__constant__ float c_dctn[8][8][8];    // c_dctn[N-1][k][n] = s_N(k) cos(pi (2n+1) k / (2N))
-
 template <int FLAVOUR>
 __global__ void __launch_bounds__(64)
 k_degrade_edges(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127, const uint32_t* __restrict__ nonzero,
@@ -650,29 +558,23 @@ k_degrade_edges(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
                     out[o] = (uint8_t)b; out[o + 1] = (uint8_t)g; out[o + 2] = (uint8_t)rr;
                 }
         } else {
-            float v[8][8], t[8][8];
+            float v[8][8];
             for (int r = 0; r < bh; ++r)
                 for (int c = 0; c < bw; ++c) {
                     const size_t o = ((size_t)(y0 + r) * W + x0 + c) * 3;
                     v[r][c] = (float)(luma_of(fr[o], fr[o + 1], fr[o + 2]) - 128);
                 }
-            const float (*cw)[8] = c_dctn[bw - 1];
-            const float (*ch)[8] = c_dctn[bh - 1];
-            for (int r = 0; r < bh; ++r)                  // rows, then columns (cv2.dct)
-                for (int k = 0; k < bw; ++k) { float a = 0.0f; for (int n = 0; n < bw; ++n) a = fmaf(cw[k][n], v[r][n], a); t[r][k] = a; }
-            for (int c = 0; c < bw; ++c)
-                for (int k = 0; k < bh; ++k) {
-                    float a = 0.0f;
-                    for (int n = 0; n < bh; ++n) a = fmaf(ch[k][n], t[n][c], a);
-                    v[k][c] = __fmul_rn(rintf(__fdiv_rn(a, q)), q);
-                }
-            for (int c = 0; c < bw; ++c)                  // inverse: columns, then rows
-                for (int n = 0; n < bh; ++n) { float a = 0.0f; for (int k = 0; k < bh; ++k) a = fmaf(ch[k][n], v[k][c], a); t[n][c] = a; }
+            // cv2.dct on a clipped block: rows, then columns, forward and inverse alike, each through the 1-D routine of
+            // its length (k_dct8.cuh, exact for every length 1..8).
+            for (int r = 0; r < bh; ++r) dct1d(&v[r][0], bw, 1, false);
+            for (int c = 0; c < bw; ++c) dct1d(&v[0][c], bh, 8, false);
+            for (int r = 0; r < bh; ++r)
+                for (int c = 0; c < bw; ++c) v[r][c] = quantise(v[r][c], q);
+            for (int r = 0; r < bh; ++r) dct1d(&v[r][0], bw, 1, true);
+            for (int c = 0; c < bw; ++c) dct1d(&v[0][c], bh, 8, true);
             for (int r = 0; r < bh; ++r)
                 for (int n = 0; n < bw; ++n) {
-                    float a = 0.0f;
-                    for (int k = 0; k < bw; ++k) a = fmaf(cw[k][n], t[r][k], a);
-                    const uint8_t y = (uint8_t)clip_trunc_u8(__fadd_rn(a, 128.0f));
+                    const uint8_t y = (uint8_t)clip_trunc_u8(__fadd_rn(v[r][n], 128.0f));
                     const size_t o = ((size_t)(y0 + r) * W + x0 + n) * 3;
                     out[o] = y; out[o + 1] = y; out[o + 2] = y;
                 }
@@ -682,6 +584,35 @@ k_degrade_edges(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
         if (n_motion) atomicAdd(&counters->motion_pixels, (unsigned long long)n_motion);
         if (is_static) atomicAdd(&counters->static_blocks, 1ull);
     }
+}
+
+// cv2.dct / cv2.idct on a stack of float32 blocks (dvc_dct_blocks_f32): one thread per block.
+__global__ void __launch_bounds__(128)
+k_dct_blocks(const float* __restrict__ src, float* __restrict__ dst, long long n, int bh, int bw, int inverse) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const float* s = src + b * bh * bw;
+    float* d = dst + b * bh * bw;
+    float v[8][8];
+    for (int r = 0; r < bh; ++r)
+        for (int c = 0; c < bw; ++c) v[r][c] = s[r * bw + c];
+    if (bh == 8 && bw == 8) {
+        if (!inverse) {
+            for (int r = 0; r < 8; ++r) dct8x8_row_fwd(v[r]);
+            for (int c = 0; c < 8; ++c) dct8x8_col_fwd(v[0][c], v[1][c], v[2][c], v[3][c], v[4][c], v[5][c], v[6][c], v[7][c]);
+        } else {
+            for (int r = 0; r < 8; ++r) {
+                for (int c = 0; c < 8; ++c) v[r][c] = __fmul_rn(v[r][c], dct8_rowscale(r));
+                dct8x8_row_inv(v[r]);
+            }
+            for (int c = 0; c < 8; ++c) dct8x8_col_inv(v[0][c], v[1][c], v[2][c], v[3][c], v[4][c], v[5][c], v[6][c], v[7][c]);
+        }
+    } else {
+        for (int r = 0; r < bh; ++r) dct1d(&v[r][0], bw, 1, inverse != 0);
+        for (int c = 0; c < bw; ++c) dct1d(&v[0][c], bh, 8, inverse != 0);
+    }
+    for (int r = 0; r < bh; ++r)
+        for (int c = 0; c < bw; ++c) d[r * bw + c] = v[r][c];
 }
 
 }  // namespace dvc

@@ -332,43 +332,11 @@ DEVI void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t ba
 // block_size 8 (frame_differencing.py:203 main config; motion_compression_opt.py:152-183): one thread per 8x8 block,
 // 8 rows x 24 bytes moved with 8-byte vector loads / stores (a warp covers 768 contiguous bytes per row), the pixels
 // stay packed in registers.  FLAVOUR 0 = FD (luma quantised, chroma 128), 1 = MCO (Y, Cr and Cb quantised, then
-// YCrCb -> BGR -> gray, replicated).  The quotient d / q is the exact IEEE one (quantise_t, Markstein step); the
-// 8-point DCT itself is a plain float32 DCT-II (cv2's 8x8 routine is not reproduced bit for bit).
+// YCrCb -> BGR -> gray, replicated).  The quotient d / q is the exact IEEE one (quantise_t, Markstein step); the 8x8
+// transform pair is the exact restatement of cv2's 2-D routine (k_dct8.cuh).
 // ------------------------------------------------------------------------------------------------
 DEVI void degrade_plane8(float (&v)[8][8], const QuantP& qp) {
-    float t[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) t[c] = v[r][c];
-        dct8_fwd(t);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[r][c] = t[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) t[r] = v[r][c];
-        dct8_fwd(t);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v[r][c] = quantise_t<0, false>(t[r], qp);
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) t[c] = v[r][c];
-        dct8_inv(t);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[r][c] = t[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) t[r] = v[r][c];
-        dct8_inv(t);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v[r][c] = t[r];
-    }
+    degrade_block8_exact(v, [&qp](float d) { return quantise_t<0, false>(d, qp); });
 }
 
 // MCO keeps the thread's 8 x 24 input bytes and two quantised channel planes in shared memory ([row][thread], lane stride

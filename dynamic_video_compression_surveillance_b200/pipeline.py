@@ -295,3 +295,14 @@ def degrade_blend(bgr: torch.Tensor, mask: torch.Tensor, block_size: int = 4, qu
               n, h, w, int(block_size), float(quantization_level), DVC_DEGRADE_FD if flavour == "fd" else DVC_DEGRADE_MCO,
               None if counters is None else counters.data_ptr(), _stream_ptr(None))
     return comp, ov
+
+
+def dct_blocks(blocks: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    """cv2.dct / cv2.idct (frame_differencing.py:122,124; motion_compression_opt.py:165,167) of a float32 CUDA stack
+    [N, bh, bw] with bh, bw in 1..8, bit for bit."""
+    if not (blocks.is_cuda and blocks.dtype == torch.float32 and blocks.dim() == 3 and blocks.is_contiguous()):
+        raise ValueError("blocks: contiguous float32 CUDA tensor [N, bh, bw]")
+    out = torch.empty_like(blocks)
+    _lib_call("dvc_dct_blocks_f32", blocks.data_ptr(), out.data_ptr(), blocks.shape[0], blocks.shape[1], blocks.shape[2],
+              1 if inverse else 0, _stream_ptr(None))
+    return out

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DVC_ABI_VERSION 2
+#define DVC_ABI_VERSION 3
 
 enum {
     DVC_OK = 0,
@@ -196,6 +196,12 @@ int dvc_mask_rectangles_u8(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n, 
 int dvc_degrade_blend_u8(const uint8_t* bgr_dev, const uint8_t* mask_dev, uint8_t* compressed_dev,
                          uint8_t* overlay_dev, int32_t n, int32_t H, int32_t W, int32_t block_size,
                          float quantization_level, int32_t flavour, uint64_t* counters_dev, void* stream);
+
+/* cv2.dct / cv2.idct on n float32 blocks [n][bh][bw] (bh, bw in 1..8), frame_differencing.py:122,124 and
+ * motion_compression_opt.py:165,167: the transform pair the degrade kernels apply, bit for bit (8 x 8 is cv2's
+ * dedicated 2-D routine, every other shape rows-then-columns through the 1-D routine of each length). */
+int dvc_dct_blocks_f32(const float* src_dev, float* dst_dev, int64_t n, int32_t bh, int32_t bw, int32_t inverse,
+                       void* stream);
 
 #ifdef __cplusplus
 }

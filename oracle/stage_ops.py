@@ -527,3 +527,221 @@ def cv2_dct4_matches_closed_form(n: int = 20000) -> bool:
         ok &= np.array_equal(cv2.dct(arr, flags=cv2.DCT_ROWS), dct4_rows_closed_form(arr))
         ok &= np.array_equal(cv2.dct(arr, flags=cv2.DCT_ROWS | cv2.DCT_INVERSE), dct4_rows_closed_form(arr, True))
     return bool(ok)
+
+
+# ----------------------------------------------------------------------------
+# closed forms of cv2's other float32 DCT routines (recovered by search in round 2):
+# the dedicated 2-D 8x8 routine and the 1-D routines of length 2, 6 and 8 that every other (clipped) block shape
+# goes through, rows first, then columns, forward and inverse alike.  csrc/k_dct8.cuh is the same sequences in CUDA.
+# ----------------------------------------------------------------------------
+def _fma_any(a, b, c):
+    """float32 fma for arrays or scalars (float32 products are exact in float64)."""
+    return (np.asarray(a, np.float64) * np.float64(b) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+_A8 = np.array([[(np.sqrt(1 / 8) if k == 0 else 0.5) * np.cos(np.pi * (2 * n + 1) * k / 16) for n in range(8)]
+                for k in range(8)]).astype(np.float32)                       # orthonormal 8-point DCT-II matrix
+_C8 = [None] + [np.float32(0.5 * np.cos(j * np.pi / 16)) for j in range(1, 8)]   # 0.5 cos(j pi / 16)
+_TG = [None] + [np.float32(np.tan(j * np.pi / 16)) for j in range(1, 4)]
+_R2 = np.float32(np.sqrt(0.5))
+_B8 = [None] + [np.float32(np.cos(j * np.pi / 16) / np.sqrt(2.0)) for j in range(1, 8)]
+_ROWSCALE8 = np.array([_C8[4], _C8[1], _C8[2], _C8[3], _C8[4], _C8[3], _C8[2], _C8[1]], np.float32)
+
+
+def _dct8x8_rows_fwd(x):
+    v = [x[..., i] for i in range(8)]
+    s = [v[i] + v[7 - i] for i in range(4)]
+    d = [v[i] - v[7 - i] for i in range(4)]
+    out = []
+    for l in range(8):
+        if l % 2 == 0:
+            acc = _A8[l, 0] * s[0]
+            for i in (1, 2, 3):
+                acc = _fma_any(s[i], _A8[l, i], acc)
+        else:
+            acc = _A8[l, 3] * d[3]
+            for i in (2, 1, 0):
+                acc = _fma_any(d[i], _A8[l, i], acc)
+        out.append(acc)
+    return np.stack(out, -1)
+
+
+def _dct8x8_cols_fwd(x):
+    v = [x[..., i, :] for i in range(8)]
+    t = [v[i] + v[7 - i] for i in range(4)]
+    m = [v[i] - v[7 - i] for i in range(4)]
+    tp03, tm03, tp12, tm12 = t[0] + t[3], t[0] - t[3], t[1] + t[2], t[1] - t[2]
+    y = [None] * 8
+    y[0] = _C8[4] * (tp03 + tp12)
+    y[4] = _C8[4] * (tp03 - tp12)
+    y[2] = _C8[2] * _fma_any(tm12, _TG[2], tm03)
+    y[6] = _C8[2] * _fma_any(tm03, _TG[2], -tm12)
+    tp65, tm65 = (m[1] + m[2]) * _R2, (m[1] - m[2]) * _R2
+    tp765, tm765, tp465, tm465 = m[0] + tp65, m[0] - tp65, m[3] + tm65, m[3] - tm65
+    y[1] = _C8[1] * _fma_any(tp465, _TG[1], tp765)
+    y[7] = _C8[1] * _fma_any(tp765, _TG[1], -tp465)
+    y[5] = _C8[3] * _fma_any(tm765, _TG[3], tm465)
+    y[3] = _C8[3] * _fma_any(tm465, -_TG[3], tm765)
+    return np.stack(y, -2)
+
+
+def _dct8x8_rows_inv(w):
+    u = [w[..., i] for i in range(8)]
+    out = [None] * 8
+    for c in range(4):
+        e = _A8[0, c] * u[0]
+        o = _A8[1, c] * u[1]
+        for l in (2, 4, 6):
+            e = _fma_any(u[l], _A8[l, c], e)
+            o = _fma_any(u[l + 1], _A8[l + 1, c], o)
+        out[c], out[7 - c] = e + o, e - o
+    return np.stack(out, -1)
+
+
+def _dct8x8_cols_inv(z):
+    x = [z[..., k, :] for k in range(8)]
+    tp765, tp465 = _fma_any(x[7], _TG[1], x[1]), _fma_any(x[1], _TG[1], -x[7])
+    tm765, tm465 = _fma_any(x[5], _TG[3], x[3]), _fma_any(x[3], -_TG[3], x[5])
+    tm03, tm12 = _fma_any(x[6], _TG[2], x[2]), _fma_any(x[2], _TG[2], -x[6])
+    t7, tp65, t4, tm65 = tp765 + tm765, tp765 - tm765, tp465 + tm465, tp465 - tm465
+    p65, m65 = tp65 * _R2, tm65 * _R2
+    t6, t5 = p65 + m65, p65 - m65
+    tp03, tp12 = x[0] + x[4], x[0] - x[4]
+    t0, t3, t1, t2 = tp03 + tm03, tp03 - tm03, tp12 + tm12, tp12 - tm12
+    return np.stack([t0 + t7, t1 + t6, t2 + t5, t3 + t4, t3 - t4, t2 - t5, t1 - t6, t0 - t7], -2)
+
+
+def dct8x8_closed_form(blocks: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """cv2.dct / cv2.idct of float32 [..., 8, 8] blocks as an explicit float32 operation sequence: forward = rows as
+    even/odd FMA chains, then columns through a tangent-rotation butterfly scaled last; inverse = row k scaled by
+    0.5 cos(k pi / 16), rows as FMA chains, then the column butterfly."""
+    b = np.asarray(blocks, np.float32)
+    if not inverse:
+        return _dct8x8_cols_fwd(_dct8x8_rows_fwd(b))
+    return _dct8x8_cols_inv(_dct8x8_rows_inv(b * _ROWSCALE8[:, None]))
+
+
+def _dct1d_generic(v, n: int, inverse: bool):
+    """Lengths 3, 5, 6, 7: fold about the middle; even / odd outputs as FMA chains over the unnormalised cosines
+    float32(cos(pi (2 i + 1) k / (2 n))) (odd lengths start the even chains with the middle sample); the scale
+    sqrt(2/n) (sqrt(1/n) for k = 0) is applied last (forward) or first (inverse)."""
+    m = np.array([[np.cos(np.pi * (2 * i + 1) * k / (2 * n)) for i in range(n)] for k in range(n)]).astype(np.float32)
+    k1, k0 = np.float32(np.sqrt(2 / n)), np.float32(np.sqrt(1 / n))
+    h, odd = n // 2, n % 2
+    if not inverse:
+        s = [v[i] + v[n - 1 - i] for i in range(h)]
+        d = [v[i] - v[n - 1 - i] for i in range(h)]
+        out = []
+        for k in range(n):
+            if k % 2:
+                terms = [(d[i], m[k, i]) for i in range(h)]
+            else:
+                terms = ([(v[h], m[k, h])] if odd else []) + [(s[i], m[k, i]) for i in range(h)]
+            acc = terms[0][1] * terms[0][0]
+            for u, c in terms[1:]:
+                acc = _fma_any(u, c, acc)
+            out.append(acc * (k0 if k == 0 else k1))
+        return np.stack(out, -1)
+    w = [v[k] * (k0 if k == 0 else k1) for k in range(n)]
+    out = [None] * n
+    for i in range(h):
+        e = m[0, i] * w[0]
+        for k in range(2, n, 2):
+            e = _fma_any(w[k], m[k, i], e)
+        o = m[1, i] * w[1]
+        for k in range(3, n, 2):
+            o = _fma_any(w[k], m[k, i], o)
+        out[i], out[n - 1 - i] = e + o, e - o
+    if odd:
+        p, q = w[0], w[2]
+        if n > 4:
+            p = p + w[4]
+        if n > 6:
+            q = q + w[6]
+        out[h] = p - q
+    return np.stack(out, -1)
+
+
+def dct1d_closed_form(x: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """The 1-D transform cv2.dct(..., DCT_ROWS) applies along the last axis (length 1..8)."""
+    x = np.asarray(x, np.float32)
+    n = x.shape[-1]
+    v = [x[..., i] for i in range(n)]
+    h = np.float32(0.5)
+    if n == 1:
+        return x.copy()
+    if n == 2:
+        a, b = v[0] * _R2, v[1] * _R2
+        return np.stack([a + b, a - b], -1)
+    if n == 4:
+        return dct4_rows_closed_form(x.reshape(-1, 4), inverse).reshape(x.shape)
+    if n in (3, 5, 6, 7):
+        return _dct1d_generic(v, n, inverse)
+    if n == 8:
+        c0, c2, c6 = _C8[4], _C8[2], _C8[6]
+        if not inverse:
+            s = [v[i] + v[7 - i] for i in range(4)]
+            d = [v[i] - v[7 - i] for i in range(4)]
+            e0, e1, f0, f1 = s[0] + s[3], s[1] + s[2], s[0] - s[3], s[1] - s[2]
+            u0, u3 = d[0] * _R2, d[3] * _R2
+            p65, m65 = (d[1] + d[2]) * h, (d[1] - d[2]) * h
+            tp765, tm765, tp465, tm465 = u0 + p65, u0 - p65, u3 + m65, u3 - m65
+            y = [None] * 8
+            y[0], y[4] = c0 * (e0 + e1), c0 * (e0 - e1)
+            y[2] = _fma_any(f0, c2, c6 * f1)
+            y[6] = _fma_any(f0, c6, -(c2 * f1))
+            y[1] = _fma_any(tp465, _B8[7], _B8[1] * tp765)
+            y[7] = _fma_any(tp765, _B8[7], -(_B8[1] * tp465))
+            y[5] = _fma_any(tm465, _B8[3], _B8[5] * tm765)
+            y[3] = _fma_any(tm765, _B8[3], -(_B8[5] * tm465))
+            return np.stack(y, -1)
+        a0, a4 = c0 * v[0], c0 * v[4]
+        ap, am = a0 + a4, a0 - a4
+        b0 = _fma_any(v[6], c6, c2 * v[2])
+        b1 = _fma_any(v[2], c6, -(c2 * v[6]))
+        e = [ap + b0, am + b1, am - b1, ap - b0]
+        tp765 = _fma_any(v[7], _B8[7], _B8[1] * v[1])
+        tp465 = _fma_any(v[1], _B8[7], -(_B8[1] * v[7]))
+        tm765 = _fma_any(v[3], _B8[3], _B8[5] * v[5])
+        tm465 = _fma_any(v[5], _B8[3], -(_B8[5] * v[3]))
+        p65, m65 = (tp765 - tm765) * h, (tp465 - tm465) * h
+        o = [_R2 * (tp765 + tm765), p65 + m65, p65 - m65, _R2 * (tp465 + tm465)]
+        out = [None] * 8
+        for i in range(4):
+            out[i], out[7 - i] = e[i] + o[i], e[i] - o[i]
+        return np.stack(out, -1)
+    raise ValueError(f"no closed form for length {n}")
+
+
+def dct_block_closed_form(x: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """cv2.dct / cv2.idct of float32 [..., h, w] blocks (h, w in 1..8) as explicit float32 sequences."""
+    x = np.asarray(x, np.float32)
+    h, w = x.shape[-2:]
+    if (h, w) == (8, 8):
+        return dct8x8_closed_form(x, inverse)
+    r = dct1d_closed_form(x, inverse)
+    c = dct1d_closed_form(np.swapaxes(r, -1, -2), inverse)
+    return np.ascontiguousarray(np.swapaxes(c, -1, -2))
+
+
+_CF_OK: dict = {}
+
+
+def cv2_dct_matches_closed_form(h: int = 8, w: int = 8, n: int = 4000) -> bool:
+    """Does this host's cv2 (its IPP code path depends on the CPU) agree bit for bit with the closed forms for
+    h x w blocks, forward and inverse, on integer, quantised and generic inputs?"""
+    import cv2
+    key = (h, w)
+    if key not in _CF_OK:
+        rng = np.random.default_rng(4242 + 16 * h + w)
+        xi = rng.integers(-128, 128, (n, h, w)).astype(np.float32)
+        xg = (rng.standard_normal((n, h, w)) * 80).astype(np.float32)
+        ok = True
+        for arr in (xi, xg):
+            f = np.stack([cv2.dct(b) for b in arr])
+            ok &= np.array_equal(f, dct_block_closed_form(arr))
+            for q in (100.0, 3.0):
+                qd = (np.round(f / np.float32(q)) * np.float32(q)).astype(np.float32)
+                ok &= np.array_equal(np.stack([cv2.idct(b) for b in qd]), dct_block_closed_form(qd, True))
+        _CF_OK[key] = bool(ok)
+    return _CF_OK[key]

@@ -28,7 +28,7 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 def test_abi_version_and_defaults(lib):
     from dynamic_video_compression_surveillance_b200._lib import DvcConfig
-    assert lib.dvc_abi_version() == 2
+    assert lib.dvc_abi_version() == 3
     cfg = DvcConfig()
     lib.dvc_default_config(ctypes.byref(cfg))
     # the reference's defaults (frame_differencing.py:21-30; motion_compression_opt.py:29-31)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from dynamic_video_compression_surveillance_b200.synth import make_clip
-from oracle import loops
+from oracle import loops, stage_ops as so
 
 pytestmark = pytest.mark.gpu
 
@@ -171,7 +171,10 @@ def test_process_single_video_of(tmp_path, dropin_modules):
     got = host_loop.degrade_mco_gpu(frames[:4], [cv2.cvtColor(m, cv2.COLOR_BGR2GRAY) for m in masks[:4]])
     ref = loops.mco_compress(frames[:4], masks[:4])
     d = np.abs(got.astype(int) - np.stack(ref).astype(int))
-    assert np.mean(d <= 2) > 0.97
+    if so.cv2_dct_matches_closed_form(8, 8):
+        assert d.max() == 0, int(d.max())
+    else:
+        assert np.mean(d <= 2) > 0.97
 
 
 def test_of_window_vote_chunking_matches_reference_statements(dropin_modules):

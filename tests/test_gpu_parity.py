@@ -1,8 +1,9 @@
 """GPU parity: every kernel behind the C ABI against the CPU oracle (run on the B200 box, `-m gpu`).
 
 Bar (BASELINE.json north_star): masks bit-exact; frames bit-exact where the reference uses integer OpenCV
-ops; DCT-degraded blocks bit-exact when this host's cv2 follows the recovered float32 sequence, otherwise
-within 1 grey level away from exact quantiser ties.
+ops; DCT-degraded blocks bit-exact when this host's cv2 follows the recovered float32 sequences (4x4, 8x8 and every
+clipped shape: oracle/stage_ops.py closed forms, checked per shape on this host), otherwise within 1 quantised-channel
+level away from exact quantiser ties, with tie-block count, flipped-block count and PSNR reported.
 """
 import os
 
@@ -233,27 +234,108 @@ def test_contour_filter_1080p_blobs(P):
     assert np.array_equal(got, so.contour_filter_cv2(m, 500))
 
 
+def _exact(bs, h=None, w=None):
+    """Does this host's cv2 follow the recovered float32 sequences for every block shape a (h, w) frame cut into
+    bs x bs blocks produces?  (True on the AVX-512 IPP build of the image; when False the tests fall back to the
+    tie-classified tolerance bar and print the report.)"""
+    ok = so.cv2_dct4_matches_closed_form() if bs == 4 else so.cv2_dct_matches_closed_form(bs, bs)
+    if h is not None:
+        rh, rw = h % bs, w % bs
+        for sh in {(rh, bs), (bs, rw), (rh, rw)}:
+            if sh[0] and sh[1] and sh != (bs, bs) and (h >= sh[0]) and (w >= sh[1]):
+                ok = ok and so.cv2_dct_matches_closed_form(min(sh[0], h), min(sh[1], w))
+    return ok
+
+
+def _degrade_report(got, ref, planes, static, bs, q, max_off_tie, label=""):
+    """Tolerance bar for hosts whose cv2 does not follow the closed forms: integer pixels exact, static blocks within
+    `max_off_tie` away from blocks holding an exact quantiser tie in any quantised plane; prints tie-block count,
+    flipped-block count and PSNR."""
+    h, w = static.shape[0] * bs, static.shape[1] * bs
+    got, ref = got[:h, :w], ref[:h, :w]
+    st_px = np.repeat(np.repeat(static, bs, 0), bs, 1)
+    assert np.array_equal(got[~st_px], ref[~st_px])
+    tie = np.zeros_like(static)
+    for pl in planes:
+        tie |= so.tie_blocks(pl[:h, :w], static, bs, q)
+    tie_px = np.repeat(np.repeat(tie, bs, 0), bs, 1)
+    d = np.abs(got.astype(int) - ref.astype(int))
+    d = d.max(axis=2) if d.ndim == 3 else d
+    flipped = (d.reshape(static.shape[0], bs, static.shape[1], bs).max(axis=(1, 3)) > max_off_tie) & static
+    mse = np.mean((got.astype(float) - ref.astype(float)) ** 2)
+    psnr = float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+    print(f"[degrade report{label}] static blocks {int(static.sum())}, tie blocks {int(tie.sum())}, "
+          f"flipped blocks {int(flipped.sum())}, max off-tie diff {int(d[st_px & ~tie_px].max(initial=0))}, PSNR {psnr:.2f} dB")
+    assert d[st_px & ~tie_px].max(initial=0) <= max_off_tie
+    assert not (flipped & ~tie).any()
+    assert psnr > 40
+
+
 def _check_degraded(got, ref, frame, acc, bs, q, exact):
     """Integer pixels must match; DCT blocks exactly (exact=True) or within 1 LSB away from ties."""
     if exact:
         assert np.array_equal(got, ref)
         return
-    static = so.block_all_zero(acc, bs)
-    h, w = acc.shape
-    st_px = np.repeat(np.repeat(static, bs, 0), bs, 1)[:h, :w]
-    assert np.array_equal(got[~st_px], ref[~st_px])
+    h, w = (acc.shape[0] // bs) * bs, (acc.shape[1] // bs) * bs
+    static = so.block_all_zero(acc[:h, :w], bs)
+    _degrade_report(got, ref, [so.bgr2ycrcb(frame)[..., 0]], static, bs, q, 1)
+
+
+def _check_degraded_mco(got, ref, frame, mask, q=100):
+    """MCO flavour (three quantised planes, then YCrCb -> BGR -> gray): exact when cv2 follows the 8x8 closed form, else
+    within 2 grey levels (one level in each quantised plane) away from tie blocks, reported."""
+    if so.cv2_dct_matches_closed_form(8, 8):
+        assert np.array_equal(got, ref)
+        return
+    static = so.block_all_zero(mask, 8, full_blocks_only=True)[:mask.shape[0] // 8, :mask.shape[1] // 8]
     ycc = so.bgr2ycrcb(frame)
-    tie = so.tie_blocks(ycc[..., 0], static, bs, q)
-    tie_px = np.repeat(np.repeat(tie, bs, 0), bs, 1)[:h, :w]
-    d = np.abs(got.astype(int) - ref.astype(int))
-    assert d[st_px & ~tie_px].max(initial=0) <= 1
-    assert (d[st_px & ~tie_px] > 0).mean() < 0.02
+    _degrade_report(got, ref, [ycc[..., c] for c in range(3)], static, 8, q, 2, " mco")
+
+
+@pytest.mark.parametrize("bh", range(1, 9))
+@pytest.mark.parametrize("bw", range(1, 9))
+def test_dct_blocks_match_cv2(P, bh, bw):
+    """The float32 transform pair itself (dvc_dct_blocks_f32) against cv2.dct / cv2.idct on random blocks of every shape
+    a clipped block can take: pixel-like integers, generic floats and quantised coefficients; equality of every bit."""
+    if (bh, bw) == (1, 1):
+        pytest.skip("1 x 1 is the identity")
+    if not so.cv2_dct_matches_closed_form(bh, bw):
+        pytest.skip("host cv2 does not follow the recovered float32 sequence for this shape")
+    r = rng(100 * bh + bw)
+    n = 3000
+    xi = r.integers(-128, 128, (n, bh, bw)).astype(np.float32)
+    xg = (r.standard_normal((n, bh, bw)) * 70).astype(np.float32)
+    for x in (xi, xg):
+        f = np.stack([cv2.dct(b) for b in x])
+        assert np.array_equal(host(P.dct_blocks(dev(x))), f), ("forward", bh, bw)
+        for q in (100.0, 7.5):
+            qd = (np.round(f / np.float32(q)) * np.float32(q)).astype(np.float32)
+            assert np.array_equal(host(P.dct_blocks(dev(qd), inverse=True)), np.stack([cv2.idct(b) for b in qd])), ("inverse", bh, bw, q)
+
+
+@pytest.mark.parametrize("q", [100.0, 33.3, 8, 1, 0.3, 0.05])
+@pytest.mark.parametrize("flavour", ["fd", "mco"])
+def test_degrade_8x8_exact_on_many_dense_blocks(P, q, flavour):
+    """block_size 8 (frame_differencing.py:203 / motion_compression_opt.py:156-183), 4 800 random blocks per level, all static:
+    exact equality with the reference arithmetic, small q keeping every coefficient alive."""
+    if not so.cv2_dct_matches_closed_form(8, 8):
+        pytest.skip("host cv2 does not follow the recovered float32 8x8 sequence; covered by the tolerance bar")
+    r = rng(6)
+    t, h, w = 2, 240, 640
+    frames = r.integers(0, 256, (t, h, w, 3), dtype=np.uint8)
+    frames[1] = (frames[1] // 8) * 8
+    acc = np.zeros((t, h, w), np.uint8)
+    comp = host(P.degrade_blend(dev(frames), dev(acc), 8, q, flavour, False)[0])
+    for i in range(t):
+        ref = so.degrade_fd(frames[i], acc[i], 8, q) if flavour == "fd" else so.degrade_mco(frames[i], acc[i], q)
+        bad = (comp[i] != ref).any(axis=2).reshape(h // 8, 8, w // 8, 8).any(axis=(1, 3)).sum()
+        assert bad == 0, (q, flavour, i, int(bad))
 
 
 @pytest.mark.parametrize("shape,bs", [((48, 64), 4), ((96, 128), 4), ((44, 60), 4), ((48, 64), 8), ((40, 72), 8)])
 def test_degrade_fd(P, shape, bs):
     r = rng(11)
-    exact = bs == 4 and so.cv2_dct4_matches_closed_form()
+    exact = _exact(bs)
     frames = r.integers(0, 256, (3,) + shape + (3,), dtype=np.uint8)
     frames[1] = (frames[1] // 16) * 16                                    # flatter content: DC-dominated blocks
     frames[2, :, :, :] = np.linspace(0, 255, shape[1], dtype=np.uint8)[None, :, None]
@@ -365,25 +447,19 @@ def test_degrade_mco(P):
     comp, _ = P.degrade_blend(dev(frames), dev(masks), 8, 100, "mco", False)
     comp = host(comp)
     for i in range(2):
-        ref = so.degrade_mco(frames[i], masks[i])
-        static = so.block_all_zero(masks[i], 8, full_blocks_only=True)
-        st_px = np.repeat(np.repeat(static, 8, 0), 8, 1)
-        assert np.array_equal(comp[i][~st_px], ref[~st_px])
-        d = np.abs(comp[i].astype(int) - ref.astype(int))[st_px]
-        # three quantised channels feed one grey value: allow 2 LSB off ties, report the rest
-        assert np.mean(d <= 2) > 0.97, np.mean(d <= 2)
+        _check_degraded_mco(comp[i], so.degrade_mco(frames[i], masks[i]), frames[i], masks[i])
 
 
 @pytest.mark.parametrize("shape,bs", [((30, 50), 4), ((480, 854), 4), ((37, 41), 4), ((6, 2), 4), ((3, 3), 4), ((90, 122), 8),
-                                      ((1082, 1920), 4), ((20, 36), 8)])
+                                      ((1082, 1920), 4), ((20, 36), 8), ((35, 47), 4), ((41, 67), 8), ((43, 69), 8), ((45, 71), 8),
+                                      ((46, 70), 8), ((540, 960), 8), ((7, 5), 8)])
 def test_degrade_fd_clipped_edge_blocks(P, shape, bs):
     """Frame sizes that are not multiples of the block size: the reference slices the last blocks shorter
-    (frame_differencing.py:117-121).  Full blocks keep their bar (exact for 4x4 when cv2 follows the closed form); the
-    partial blocks run plain float32 N-point DCTs and are held to 1 grey level away from quantiser ties; overlay, the
-    colour round trip of non-static blocks and the counters are exact everywhere."""
+    (frame_differencing.py:117-121) and cv2.dct takes them rows-then-columns through its 1-D routine of each length
+    (1..8, all restated exactly in csrc/k_dct8.cuh).  Everything is exact when cv2 follows the closed forms."""
     r = rng(33)
     h, w = shape
-    exact = bs == 4 and so.cv2_dct4_matches_closed_form()
+    exact = _exact(bs, h, w)
     n = 2
     frames = r.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
     frames[1] = (frames[1] // 32) * 32
@@ -406,7 +482,10 @@ def test_degrade_fd_clipped_edge_blocks(P, shape, bs):
         assert np.array_equal(comp[i][edge & ~st_px], ref[edge & ~st_px])          # colour round trip: integer, exact
         d = np.abs(comp[i].astype(int) - ref.astype(int)).max(axis=2)[edge & st_px]
         if d.size:
-            assert np.mean(d <= 1) >= 0.9, (shape, i, float(np.mean(d <= 1)))
+            if exact:
+                assert d.max() == 0, (shape, i, int(d.max()), int((d > 0).sum()))
+            else:
+                assert np.mean(d <= 1) >= 0.9, (shape, i, float(np.mean(d <= 1)))
     c = cnt.cpu().numpy()
     assert c[2] == int((acc > 127).sum())
     assert c[3] == n * (-(-h // bs)) * (-(-w // bs)) and c[4] == n_static
@@ -422,8 +501,7 @@ def test_degrade_mco_partial_blocks_only_get_the_colour_round_trip(P):
     for i in range(2):
         ref = so.degrade_mco(frames[i], masks[i])
         assert np.array_equal(comp[i][64:, :], ref[64:, :]) and np.array_equal(comp[i][:, 96:], ref[:, 96:])
-        d = np.abs(comp[i][:64, :96].astype(int) - ref[:64, :96].astype(int))
-        assert np.mean(d <= 2) > 0.97
+        _check_degraded_mco(comp[i][:64, :96], ref[:64, :96], frames[i][:64, :96], masks[i][:64, :96])
 
 
 @pytest.mark.parametrize("mode", ["window", "fd"])
@@ -432,7 +510,7 @@ def test_loops_on_frame_sizes_not_multiple_of_block(P, mode):
     from dynamic_video_compression_surveillance_b200.synth import make_clip
     h, w, n = 62, 110, 16
     frames = make_clip((h, w), n, seed=12).frames()
-    exact = so.cv2_dct4_matches_closed_form()
+    exact = _exact(4, h, w)
     if mode == "window":
         kw = dict(window_size=5, alpha_fraction=0.2, morph_kernel=2, kernel_size=7)
         ref = loops.window_loop(list(frames), **kw)
@@ -453,16 +531,17 @@ def test_loops_on_frame_sizes_not_multiple_of_block(P, mode):
     hf, wf = (h // 4) * 4, (w // 4) * 4
     d = np.abs(cp.astype(int) - rc.astype(int))
     if exact:
-        assert d[:, :hf, :wf].max() == 0
-    assert np.mean(d[:, hf:, :] <= 1) > 0.9 and np.mean(d[:, :, wf:] <= 1) > 0.9
+        assert d.max() == 0
+    else:
+        assert np.mean(d[:, hf:, :] <= 1) > 0.9 and np.mean(d[:, :, wf:] <= 1) > 0.9
     assert c["blocks"] == (n - 1) * (-(-h // 4)) * (-(-w // 4))
 
 
 def test_fd_loop_against_reference_fixture_with_clipped_blocks(P):
     """126 x 218 frames through the UNMODIFIED reference (tests/golden/fd_clipped_126x218.npz): masks and overlays are
-    exact; compressed frames are exact on whole blocks and within a grey level on the clipped edge blocks."""
+    exact; so are the compressed frames, clipped 4x2 / 2x4 / 2x2 edge blocks included."""
     z, frames, kw, (h, w, n) = load_fd(FD_CLIPPED_FIXTURE)
-    exact = so.cv2_dct4_matches_closed_form()
+    exact = _exact(4, h, w)
     pipe = P.FramePipeline(w, h, "fd", max_batch=8, **kw)
     pipe.begin_stream(loops.first_frame_gray_fd(frames[0]))
     ov = np.empty((n - 1, h, w, 3), np.uint8); cp = np.empty_like(ov); mk = np.empty((n - 1, h, w), np.uint8)
@@ -474,10 +553,10 @@ def test_fd_loop_against_reference_fixture_with_clipped_blocks(P):
     tail = z["compressed_tail"]
     d = np.abs(cp[-2:].astype(int) - tail.astype(int))
     if exact:
-        assert d[:, :hf, :wf].max() == 0
+        assert d.max() == 0
     else:
         assert np.mean(d[:, :hf, :wf] > 1) < 1e-3
-    assert np.mean(d[:, hf:, :] <= 1) > 0.9 and np.mean(d[:, :, wf:] <= 1) > 0.9
+        assert np.mean(d[:, hf:, :] <= 1) > 0.9 and np.mean(d[:, :, wf:] <= 1) > 0.9
     assert (z["acc"][-1][hf:, :] == 0).any() or (z["acc"][-1][:, wf:] == 0).any()      # the fixture does have static edge pixels
 
 
@@ -499,7 +578,7 @@ def test_fd_loop_against_reference_fixture(P, name, max_batch):
     """The fd-exact loop against outputs of the UNMODIFIED reference (tests/golden/*.npz)."""
     z, frames, kw, (h, w, n) = load_fd(name)
     bs = kw.get("block_size", 4)
-    exact = bs == 4 and so.cv2_dct4_matches_closed_form()
+    exact = _exact(bs, h, w)
     pipe = P.FramePipeline(w, h, "fd", max_batch=max_batch, **kw)
     pipe.begin_stream(loops.first_frame_gray_fd(frames[0]))
     ov = np.empty((n - 1, h, w, 3), np.uint8)
@@ -808,14 +887,7 @@ def test_config5_farneback_masks_to_mco_degrade_1080p(P):
     comp, _ = P.degrade_blend(dev(frames[1:]), dev(masks), 8, 100, "mco", False)
     comp = host(comp)
     for i in (0, n - 2):
-        ref = so.degrade_mco(frames[i + 1], masks[i])
-        static = so.block_all_zero(masks[i], 8, full_blocks_only=True)
-        st_px = np.repeat(np.repeat(static, 8, 0), 8, 1)
-        assert np.array_equal(comp[i][~st_px], ref[~st_px])
-        d = np.abs(comp[i].astype(int) - ref.astype(int))[st_px]
-        assert np.mean(d <= 2) > 0.97 and d.max() <= 110       # a flipped tie moves a block by one quantiser step
-        psnr = 10 * np.log10(255.0 ** 2 / max(1e-9, np.mean((comp[i].astype(float) - ref.astype(float)) ** 2)))
-        assert psnr > 40, psnr
+        _check_degraded_mco(comp[i], so.degrade_mco(frames[i + 1], masks[i]), frames[i + 1], masks[i])
 
 
 def test_random_loop_configurations_against_oracle():

@@ -229,3 +229,40 @@ def test_resize_linear(shape):
         assert np.array_equal(so.resize_linear(img, (dw, dh)), cv2.resize(img, (dw, dh))), (shape, sf)
     g = img[..., 0].copy()
     assert np.array_equal(so.resize_linear(g, (w // 2, h // 2)), cv2.resize(g, (w // 2, h // 2)))
+
+
+def _ipp_is_avx512():
+    import cv2
+    try:
+        return cv2.ipp.useIPP() and "(k0)" in cv2.ipp.getIppVersion()
+    except Exception:
+        return False
+
+
+@pytest.mark.parametrize("bh", range(1, 9))
+@pytest.mark.parametrize("bw", range(1, 9))
+def test_dct_closed_forms_against_cv2(bh, bw):
+    """frame_differencing.py:122,124 / motion_compression_opt.py:165,167: the recovered float32 operation sequences
+    (8x8 2-D routine; 1-D routines of length 2..8 for every clipped shape) reproduce this host's cv2.dct / cv2.idct bit
+    for bit.  IPP dispatches on the CPU: the sequences were recovered on the AVX-512 (k0) build, other dispatches are
+    reported as a skip, and the GPU tests then fall back to the tie-classified tolerance bar."""
+    if (bh, bw) == (1, 1):
+        pytest.skip("identity")
+    ok = so.cv2_dct_matches_closed_form(bh, bw, 1500)
+    if not ok and not _ipp_is_avx512():
+        pytest.skip("cv2's IPP dispatch on this CPU is not the AVX-512 one the sequences were recovered from")
+    assert ok, (bh, bw)
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (8, 4), (2, 8), (6, 8), (3, 5), (7, 7), (4, 4), (1, 6)])
+def test_dct_closed_forms_are_the_orthonormal_dct(shape):
+    """Independent of cv2: the closed forms are the orthonormal DCT-II / DCT-III pair to float32 accuracy."""
+    from scipy.fft import dctn, idctn
+    rng = _rng(91)
+    x = rng.integers(-128, 128, (500,) + shape).astype(np.float32)
+    f = so.dct_block_closed_form(x)
+    ref = dctn(x.astype(np.float64), axes=(1, 2), norm="ortho")
+    assert np.abs(f - ref).max() < 2e-4
+    y = (rng.standard_normal((500,) + shape) * 100).astype(np.float32)
+    assert np.abs(so.dct_block_closed_form(y, True) - idctn(y.astype(np.float64), axes=(1, 2), norm="ortho")).max() < 2e-4
+    assert np.abs(so.dct_block_closed_form(f, True) - x).max() < 2e-3
