@@ -499,6 +499,8 @@ struct dvc_handle {
     cudaStream_t s_mask, s_k4;
     cudaEvent_t ev_in, ev_mask[2], ev_k4[2];
     bool ev_used[2];
+    cudaEvent_t ev_user;          // end of the last batch issued on a caller's stream (strict-order mode)
+    bool ev_user_used;
     // host pipeline
     cudaStream_t s_h2d, s_d2h;
     cudaEvent_t ev_h2d[2], ev_d2h[2];
@@ -532,6 +534,29 @@ static int alloc_staging(dvc_handle* h) {
     CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
     h->staging = true;
     return DVC_OK;
+}
+
+// Wait for everything this handle has in flight -- its own streams and the last batch issued on a caller's stream --
+// without a device-wide synchronisation: handles of other streams on the same GPU keep running.
+static cudaError_t handle_join(dvc_handle* h) {
+    cudaError_t e;
+    if (h->ev_user_used && (e = cudaEventSynchronize(h->ev_user)) != cudaSuccess) return e;
+    if (h->s_mask && (e = cudaStreamSynchronize(h->s_mask)) != cudaSuccess) return e;
+    if (h->s_k4 && (e = cudaStreamSynchronize(h->s_k4)) != cudaSuccess) return e;
+    if (h->staging) {
+        if ((e = cudaStreamSynchronize(h->s_h2d)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(h->s_d2h)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+// synchronous copies / fills on the handle's own stream (the legacy default stream would serialise all handles)
+static cudaError_t h_copy(dvc_handle* h, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, h->s_mask);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(h->s_mask);
+}
+static cudaError_t h_fill0(dvc_handle* h, void* dst, size_t bytes) {
+    cudaError_t e = cudaMemsetAsync(dst, 0, bytes, h->s_mask);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(h->s_mask);
 }
 
 extern "C" int dvc_abi_version(void) { return DVC_ABI_VERSION; }
@@ -590,6 +615,7 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     CU(cudaStreamCreateWithFlags(&h->s_mask, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->s_k4, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
     for (int s = 0; s < 2; ++s) {
         CU(cudaEventCreateWithFlags(&h->ev_mask[s], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_k4[s], cudaEventDisableTiming));
@@ -626,13 +652,14 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
 extern "C" int dvc_destroy(dvc_handle* h) {
     if (!h) return DVC_OK;
     cudaSetDevice(h->cfg.device);
-    cudaDeviceSynchronize();
+    handle_join(h);
     cudaFree(h->prev_gray[0]); cudaFree(h->prev_gray[1]); cudaFree(h->acc); cudaFree(h->ring);
     for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(h->bits[s][k]);
     cudaFree(h->blurred); cudaFree(h->counters_dev); cudaFree(h->resize_tables);
     if (h->s_mask) cudaStreamDestroy(h->s_mask);
     if (h->s_k4) cudaStreamDestroy(h->s_k4);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_user) cudaEventDestroy(h->ev_user);
     for (int s = 0; s < 2; ++s) { if (h->ev_mask[s]) cudaEventDestroy(h->ev_mask[s]); if (h->ev_k4[s]) cudaEventDestroy(h->ev_k4[s]); }
     ccl_scratch_free(h->ccl);
     if (h->staging) {
@@ -680,10 +707,10 @@ extern "C" int dvc_begin_stream(dvc_handle* h, const uint8_t* prev_gray_host) {
     char* ERRBUF = h ? h->err : nullptr;
     if (!h || !prev_gray_host) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_begin_stream: null argument");
     CU(cudaSetDevice(h->cfg.device));
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(h->prev_gray[h->cur], prev_gray_host, h->plane_bytes, cudaMemcpyHostToDevice));
-    if (h->acc) CU(cudaMemset(h->acc, 0, h->plane_bytes));
-    if (h->ring) CU(cudaMemset(h->ring, 0, h->plane_words * 4 * h->ring_cap));
+    CU(handle_join(h));
+    CU(h_copy(h, h->prev_gray[h->cur], prev_gray_host, h->plane_bytes, cudaMemcpyHostToDevice));
+    if (h->acc) CU(h_fill0(h, h->acc, h->plane_bytes));
+    if (h->ring) CU(h_fill0(h, h->ring, h->plane_words * 4 * h->ring_cap));
     h->n_masks = 0;
     return DVC_OK;
 }
@@ -703,18 +730,18 @@ extern "C" int dvc_get_state(dvc_handle* h, void* buf, size_t bytes) {
     char* ERRBUF = h ? h->err : nullptr;
     if (!h || !buf || bytes < dvc_state_bytes(h)) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_get_state: buffer too small");
     CU(cudaSetDevice(h->cfg.device));
-    CU(cudaDeviceSynchronize());
+    CU(handle_join(h));
     StateHeader hd = {STATE_MAGIC, (uint32_t)h->cfg.mode, (uint32_t)h->W, (uint32_t)h->H, (uint32_t)h->cfg.window_size, 0, h->n_masks};
     uint8_t* p = (uint8_t*)buf;
     memcpy(p, &hd, sizeof(hd)); p += sizeof(hd);
-    CU(cudaMemcpy(p, h->prev_gray[h->cur], h->plane_bytes, cudaMemcpyDeviceToHost)); p += h->plane_bytes;
+    CU(h_copy(h, p, h->prev_gray[h->cur], h->plane_bytes, cudaMemcpyDeviceToHost)); p += h->plane_bytes;
     if (h->cfg.mode == DVC_MODE_FD) {
-        CU(cudaMemcpy(p, h->acc, h->plane_bytes, cudaMemcpyDeviceToHost));
+        CU(h_copy(h, p, h->acc, h->plane_bytes, cudaMemcpyDeviceToHost));
     } else {
         const int K = h->cfg.window_size;
         for (int i = 0; i < K; ++i) {       // slot i holds mask n_masks-K+i (zeros if before the stream start)
             const long long f = h->n_masks - K + i;
-            if (f >= 0) CU(cudaMemcpy(p, h->ring + (size_t)(f % h->ring_cap) * h->plane_words, h->plane_words * 4, cudaMemcpyDeviceToHost));
+            if (f >= 0) CU(h_copy(h, p, h->ring + (size_t)(f % h->ring_cap) * h->plane_words, h->plane_words * 4, cudaMemcpyDeviceToHost));
             else memset(p, 0, h->plane_words * 4);
             p += h->plane_words * 4;
         }
@@ -732,16 +759,16 @@ extern "C" int dvc_set_state(dvc_handle* h, const void* buf, size_t bytes) {
         (h->cfg.mode == DVC_MODE_WINDOW && hd.K != (uint32_t)h->cfg.window_size))
         return set_err(h->err, DVC_ERR_INVALID, "dvc_set_state: blob does not match this handle's configuration");
     CU(cudaSetDevice(h->cfg.device));
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(h->prev_gray[h->cur], p, h->plane_bytes, cudaMemcpyHostToDevice)); p += h->plane_bytes;
+    CU(handle_join(h));
+    CU(h_copy(h, h->prev_gray[h->cur], p, h->plane_bytes, cudaMemcpyHostToDevice)); p += h->plane_bytes;
     h->n_masks = hd.n_masks;
     if (h->cfg.mode == DVC_MODE_FD) {
-        CU(cudaMemcpy(h->acc, p, h->plane_bytes, cudaMemcpyHostToDevice));
+        CU(h_copy(h, h->acc, p, h->plane_bytes, cudaMemcpyHostToDevice));
     } else {
         const int K = h->cfg.window_size;
         for (int i = 0; i < K; ++i) {
             const long long f = h->n_masks - K + i;
-            if (f >= 0) CU(cudaMemcpy(h->ring + (size_t)(f % h->ring_cap) * h->plane_words, p, h->plane_words * 4, cudaMemcpyHostToDevice));
+            if (f >= 0) CU(h_copy(h, h->ring + (size_t)(f % h->ring_cap) * h->plane_words, p, h->plane_words * 4, cudaMemcpyHostToDevice));
             p += h->plane_words * 4;
         }
     }
@@ -752,9 +779,9 @@ extern "C" int dvc_get_counters(dvc_handle* h, dvc_counters* out) {
     char* ERRBUF = h ? h->err : nullptr;
     if (!h || !out) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_get_counters: null argument");
     CU(cudaSetDevice(h->cfg.device));
-    CU(cudaDeviceSynchronize());
+    CU(handle_join(h));
     Counters c;
-    CU(cudaMemcpy(&c, h->counters_dev, sizeof(c), cudaMemcpyDeviceToHost));
+    CU(h_copy(h, &c, h->counters_dev, sizeof(c), cudaMemcpyDeviceToHost));
     *out = h->counters_host;
     out->motion_pixels = c.motion_pixels;
     out->static_blocks = c.static_blocks;
@@ -765,8 +792,8 @@ extern "C" int dvc_reset_counters(dvc_handle* h) {
     char* ERRBUF = h ? h->err : nullptr;
     if (!h) return set_err(nullptr, DVC_ERR_INVALID, "dvc_reset_counters: null handle");
     CU(cudaSetDevice(h->cfg.device));
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemset(h->counters_dev, 0, sizeof(Counters)));
+    CU(handle_join(h));
+    CU(h_fill0(h, h->counters_dev, sizeof(Counters)));
     memset(&h->counters_host, 0, sizeof(h->counters_host));
     return DVC_OK;
 }
@@ -799,7 +826,7 @@ extern "C" int dvc_profile_read(dvc_handle* h, double* ms_by_kernel, int64_t* la
     if (!h || !ms_by_kernel || !launches_by_kernel || n_kernels < DVC_PROF_KERNELS)
         return set_err(ERRBUF, DVC_ERR_INVALID, "dvc_profile_read: need arrays of %d entries", DVC_PROF_KERNELS);
     CU(cudaSetDevice(h->cfg.device));
-    CU(cudaDeviceSynchronize());
+    CU(handle_join(h));
     for (int i = 0; i < n_kernels; ++i) { ms_by_kernel[i] = 0.0; launches_by_kernel[i] = 0; }
     for (ProfRec& r : *h->prof_recs) {
         float ms = 0.f;
@@ -926,7 +953,11 @@ extern "C" int dvc_process_batch(dvc_handle* h, const uint8_t* frames_dev, int32
     if (!frames_dev) return set_err(h->err, DVC_ERR_INVALID, "dvc_process_batch: null frames");
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (!h->overlap) return process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, st, st, 0);
+    if (!h->overlap) {
+        int rc = process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, st, st, 0);
+        if (rc == DVC_OK) { CU(cudaEventRecord(h->ev_user, st)); h->ev_user_used = true; }
+        return rc;
+    }
     // pipelined: the batch is ordered after the work already in `stream`, but `stream` is only re-joined by dvc_flush
     const int set = h->pp;
     h->pp ^= 1;
@@ -940,7 +971,7 @@ extern "C" int dvc_set_overlap(dvc_handle* h, int32_t on) {
     char* ERRBUF = h ? h->err : nullptr;
     if (!h) return set_err(nullptr, DVC_ERR_INVALID, "dvc_set_overlap: null handle");
     CU(cudaSetDevice(h->cfg.device));
-    CU(cudaDeviceSynchronize());
+    CU(handle_join(h));
     h->overlap = on != 0;
     return DVC_OK;
 }
@@ -972,7 +1003,7 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
     static const int host_chunk = [] { const char* e = getenv("DVC_HOST_CHUNK"); return e ? std::max(1, atoi(e)) : 8; }();
     const int Tc = std::min(h->cfg.max_batch, host_chunk);
     const int64_t nchunks = (n_frames + Tc - 1) / Tc;
-    CU(cudaDeviceSynchronize());          // join whatever dvc_process_batch left in flight
+    CU(handle_join(h));                   // join whatever dvc_process_batch left in flight (this handle only)
     for (int64_t c = 0; c < nchunks; ++c) {
         const int b = (int)(c & 1);       // staging buffers, scratch set and events all alternate with the chunk
         const int64_t f0 = c * Tc;
@@ -984,7 +1015,7 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
             CU(cudaMemcpyAsync(h->st_src[b], frames_host + (size_t)f0 * h->src_frame_bytes, (size_t)T * h->src_frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
             rc = launch_resize(h->err, h->st_src[b], h->st_in[b], T, h->cfg.src_height, h->cfg.src_width, h->H, h->W, 3,
                                resize_tables_view(h->resize_tables, h->H, h->W), h->s_h2d);
-            if (rc) { cudaDeviceSynchronize(); return rc; }
+            if (rc) { handle_join(h); return rc; }
             h->launches += 1;
         } else
         CU(cudaMemcpyAsync(h->st_in[b], frames_host + (size_t)f0 * h->frame_bytes, (size_t)T * h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
@@ -999,7 +1030,7 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
         if (no_kernels) { CU(cudaEventRecord(h->ev_k4[b], h->s_k4)); h->ev_used[b] = true; rc = DVC_OK; } else
         rc = process_batch_impl(h, h->st_in[b], T, overlay_host ? h->st_ov[b] : nullptr, compressed_host ? h->st_cp[b] : nullptr,
                                 mask_host ? h->st_mask[b] : nullptr, h->s_mask, h->s_k4, b);
-        if (rc) { cudaDeviceSynchronize(); return rc; }
+        if (rc) { handle_join(h); return rc; }
         CU(cudaStreamWaitEvent(h->s_d2h, h->ev_k4[b], 0));
         if (overlay_host) CU(cudaMemcpyAsync(overlay_host + (size_t)f0 * h->frame_bytes, h->st_ov[b], (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
         if (compressed_host) CU(cudaMemcpyAsync(compressed_host + (size_t)f0 * h->frame_bytes, h->st_cp[b], (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
