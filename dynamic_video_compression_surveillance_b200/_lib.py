@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdvc_b200.so")
+# tools/ that A/B kernel variants set DVC_LIB_FLAVOUR=measure to load the -DDVC_MEASURE build (build.py --measure);
+# that file does not exist unless such a tool built it
+LIB_PATH = os.path.join(HERE, "libdvc_b200_measure.so" if os.environ.get("DVC_LIB_FLAVOUR") == "measure" else "libdvc_b200.so")
 
 DVC_MODE_FD, DVC_MODE_WINDOW = 0, 1
 DVC_MORPH_ERODE, DVC_MORPH_DILATE, DVC_MORPH_OPEN, DVC_MORPH_CLOSE = 0, 1, 2, 3
@@ -43,6 +45,7 @@ class DvcUnsupported(DvcError, NotImplementedError):
 _P, _I, _F, _D, _L = C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_int64
 SYMBOLS = {
     "dvc_abi_version": (C.c_int, []),
+    "dvc_measure_build": (C.c_int, []),
     "dvc_last_error": (C.c_char_p, [_P]),
     "dvc_default_config": (None, [C.POINTER(DvcConfig)]),
     "dvc_create": (C.c_int, [C.POINTER(DvcConfig), C.POINTER(_P)]),

@@ -30,7 +30,16 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+LIB_MEASURE = os.path.join(HERE, "libdvc_b200_measure.so")
+
+
+def build(force: bool = False, verbose: bool = False, measure: bool = False) -> str:
+    """measure=True builds the -DDVC_MEASURE flavour (environment switches for A/B runs, tools/ only) next to the product."""
+    if measure:
+        r = subprocess.run([find_nvcc()] + NVCC_FLAGS + ["-DDVC_MEASURE", "-o", LIB_MEASURE, SRC], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        return LIB_MEASURE
     if not force and not is_stale():
         return LIB
     cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
@@ -43,4 +52,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, measure="--measure" in sys.argv))

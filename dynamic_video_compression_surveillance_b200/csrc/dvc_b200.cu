@@ -136,6 +136,15 @@ static void window_min_counts(double alpha, int K, MinCounts& mc) {
 // ------------------------------------------------------------------------------------------------
 // Function attributes and __constant__ uploads are per device: one-time set-up is tracked per CUDA device ordinal so that
 // handles on several GPUs in one process all get it.
+// Measurement switches (kernel generations, ring geometry, copy-only probes: DESIGN.md section 6a) exist only in the
+// -DDVC_MEASURE flavour of the library that tools/ build for A/B runs.  The product build ignores the environment, so a
+// stray variable can never change what the loop computes.
+#ifdef DVC_MEASURE
+static int measure_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+static constexpr int measure_env(const char*, int dflt) { return dflt; }
+#endif
+
 struct PerDeviceOnce {
     std::mutex mu;
     bool done[64] = {};
@@ -185,7 +194,7 @@ static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, 
     // large halo get bands at least twice the halo so the redundant rows stay under a third.
     const size_t row_bytes = 2 * (size_t)wpr * 4;
     const size_t limit = (size_t)g_morph_smem_limit - 64;
-    static const int target_kb = [] { const char* e = getenv("DVC_MORPH_SMEM_KB"); return e ? std::max(4, atoi(e)) : 36; }();
+    static const int target_kb = std::max(4, measure_env("DVC_MORPH_SMEM_KB", 36));
     int band = (int)((size_t)target_kb * 1024 / row_bytes) - halo;
     band = std::max(band, std::max(16, 2 * halo));
     band = std::min<int>(band, (int)(limit / row_bytes) - halo);
@@ -220,7 +229,7 @@ static int launch_contour_filter(char* ERRBUF, const uint32_t* raw, uint32_t* ou
         dim3 grid(cdiv(pw, 256), m);
         dim3 grow((H + 7) / 8, m);
         const uint32_t* r = raw + (size_t)i0 * pw;
-        static const bool row_skip = [] { const char* e = getenv("DVC_CCL_ROWSKIP"); return e ? atoi(e) != 0 : true; }();
+        static const bool row_skip = measure_env("DVC_CCL_ROWSKIP", 1) != 0;
         uint8_t* rf = row_skip ? sc.rowflag : nullptr;
         k_ccl_rowlink<true, true><<<grow, 256, 0, st>>>(r, sc.pa0, sc.paov, nullptr, nullptr, H, W, wpr, rf);
         k_ccl_union<true, 4><<<grid, 256, 0, st>>>(r, sc.pa0, sc.paov, H, W, wpr, rf);
@@ -351,8 +360,8 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         qc.tie_lo = 0.5f - band;
         qc.fast = band <= 0.01f && q <= 1.0e6f;
         dim3 grid(cdiv((size_t)(W / 8) * (H / 4), 256), n);
-        static const bool luma_dp4a = [] { const char* e = getenv("DVC_LUMA_DP4A"); return e ? atoi(e) != 0 : true; }();
-        static const bool tma_env = [] { const char* e = getenv("DVC_K4_TMA_STORE"); return e ? atoi(e) != 0 : true; }();
+        static const bool luma_dp4a = measure_env("DVC_LUMA_DP4A", 1) != 0;
+        static const bool tma_env = measure_env("DVC_K4_TMA_STORE", 1) != 0;
         const bool tma = tma_env && W % 16 == 0;
         const size_t smem = tma ? (size_t)K4_STAGE_BYTES : 0;
         static PerDeviceOnce attr_set;
@@ -361,7 +370,7 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
             CU(cudaFuncSetAttribute(k_degrade4<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             once.commit();
         }
-        static const bool packed_env = [] { const char* e = getenv("DVC_K4_PACKED"); return e ? atoi(e) != 0 : true; }();
+        static const bool packed_env = measure_env("DVC_K4_PACKED", 1) != 0;
         if (packed_env && q >= 0.01f && q <= 1.0e6f) {
             // packed-pair kernel: quotient by Markstein correction (exact for normal-range q), magic rounding needs |d/q| < 2^22
             QuantP qp;
@@ -378,7 +387,7 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
             }
             // DVC_K4_PERSIST=0 selects the CTA-per-256-groups kernel (k_degrade4p) for A/B; it is also the fallback for pointers
             // that are not 16-byte aligned and for W > 2048 with W % 16 != 0 (bulk copies need 16-byte pieces)
-            static const bool ring_env = [] { const char* e = getenv("DVC_K4_PERSIST"); return e ? atoi(e) != 0 : true; }();
+            static const bool ring_env = measure_env("DVC_K4_PERSIST", 1) != 0;
             const int gpr = W / 8, nbr = H / 4;
             const bool ptr16 = ((((uintptr_t)frames) | ((uintptr_t)compressed) | ((uintptr_t)overlay)) & 15u) == 0 &&
                                ((size_t)H * W * 3) % 16 == 0;          // every frame of the batch starts 16-byte aligned
@@ -394,13 +403,13 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                     g.nb = 1; g.sp = g.gp * 24; g.span_bytes = 4 * g.sp;
                 }
                 g.mask_bytes = 4 * g.nb * wpr * 4;
-                static const int dbg = [] { const char* e = getenv("DVC_K4_DEBUG"); return e ? atoi(e) : 0; }();
+                static const int dbg = measure_env("DVC_K4_DEBUG", 0);
                 g.debug = dbg;
                 {
-                    static const int env_stages = [] { const char* e = getenv("DVC_K4_STAGES"); return e ? atoi(e) : 6; }();
-                    static const int env_groups = [] { const char* e = getenv("DVC_K4_GROUPS"); return e ? atoi(e) : 2; }();
-                    static const int env_piece = [] { const char* e = getenv("DVC_K4_PIECE"); return e ? atoi(e) : 0; }();
-                    static const int env_ctas = [] { const char* e = getenv("DVC_K4_CTAS"); return e ? atoi(e) : 0; }();
+                    static const int env_stages = measure_env("DVC_K4_STAGES", 6);
+                    static const int env_groups = measure_env("DVC_K4_GROUPS", 2);
+                    static const int env_piece = measure_env("DVC_K4_PIECE", 0);
+                    static const int env_ctas = measure_env("DVC_K4_CTAS", 0);
                     int dev = 0, sms = 0;
                     CU(cudaGetDevice(&dev));
                     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -447,7 +456,7 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         else k_degrade4<false, false><<<grid, 256, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qc, counters);
     } else {
         dim3 grid(cdiv((size_t)(W / bs) * (H / bs), 128), n);
-        static const bool k8_env = [] { const char* e = getenv("DVC_K4_BLOCK8_FAST"); return e ? atoi(e) != 0 : true; }();
+        static const bool k8_env = measure_env("DVC_K4_BLOCK8_FAST", 1) != 0;
         const bool ptr8 = ((((uintptr_t)frames) | ((uintptr_t)compressed) | ((uintptr_t)overlay)) & 7u) == 0;
         if (bs == 8 && W % 8 == 0 && k8_env && ptr8 && q >= 0.01f && q <= 1.0e6f) {
             QuantP qp;
@@ -560,6 +569,13 @@ static cudaError_t h_fill0(dvc_handle* h, void* dst, size_t bytes) {
 }
 
 extern "C" int dvc_abi_version(void) { return DVC_ABI_VERSION; }
+extern "C" int dvc_measure_build(void) {
+#ifdef DVC_MEASURE
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 extern "C" const char* dvc_last_error(const dvc_handle* h) { return h ? h->err : g_err; }
 
@@ -590,10 +606,8 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     h->frame_bytes = h->plane_bytes * 3;
     h->aligned = (h->W % 16) == 0;
     const int T = cfg->max_batch;
-    const char* sl = getenv("DVC_SEG_LEN");
-    h->seg_len = sl ? std::max(1, atoi(sl)) : 8;
-    const char* gd = getenv("DVC_GRAY_IMPL");
-    h->gray_impl = gd ? atoi(gd) : 2;
+    h->seg_len = std::max(1, measure_env("DVC_SEG_LEN", 8));
+    h->gray_impl = measure_env("DVC_GRAY_IMPL", 2);
     CU(cudaSetDevice(cfg->device));
     h->resizing = cfg->src_width > 0 && cfg->src_height > 0 && (cfg->src_width != cfg->width || cfg->src_height != cfg->height);
     h->src_frame_bytes = h->resizing ? (size_t)cfg->src_width * cfg->src_height * 3 : h->frame_bytes;
@@ -1000,7 +1014,7 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
     if (rc) return rc;
     // chunk size of the copy pipeline: small enough that the first upload and the last download (the only copies
     // nothing overlaps) are short against the PCIe-bound steady state, large enough for full-size kernels
-    static const int host_chunk = [] { const char* e = getenv("DVC_HOST_CHUNK"); return e ? std::max(1, atoi(e)) : 8; }();
+    static const int host_chunk = std::max(1, measure_env("DVC_HOST_CHUNK", 8));
     const int Tc = std::min(h->cfg.max_batch, host_chunk);
     const int64_t nchunks = (n_frames + Tc - 1) / Tc;
     CU(handle_join(h));                   // join whatever dvc_process_batch left in flight (this handle only)
@@ -1026,7 +1040,7 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
             CU(cudaStreamWaitEvent(h->s_mask, h->ev_d2h[b], 0));     // output staging of chunk c-2 downloaded
             CU(cudaStreamWaitEvent(h->s_k4, h->ev_d2h[b], 0));
         }
-        static const bool no_kernels = [] { const char* e = getenv("DVC_HOST_NOKERNEL"); return e && atoi(e) != 0; }();   // copy-pipeline probe
+        static const bool no_kernels = measure_env("DVC_HOST_NOKERNEL", 0) != 0;   // copy-pipeline probe
         if (no_kernels) { CU(cudaEventRecord(h->ev_k4[b], h->s_k4)); h->ev_used[b] = true; rc = DVC_OK; } else
         rc = process_batch_impl(h, h->st_in[b], T, overlay_host ? h->st_ov[b] : nullptr, compressed_host ? h->st_cp[b] : nullptr,
                                 mask_host ? h->st_mask[b] : nullptr, h->s_mask, h->s_k4, b);

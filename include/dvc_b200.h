@@ -93,6 +93,9 @@ typedef struct dvc_counters {
 } dvc_counters;
 
 int         dvc_abi_version(void);
+/* 1 for the -DDVC_MEASURE flavour (tools/: environment switches select kernel generations and copy-only probes, outputs may
+ * be wrong), 0 for the product library, which reads no environment variable at all. */
+int         dvc_measure_build(void);
 const char* dvc_last_error(const dvc_handle* h);   /* h may be NULL: error of the last failed create / stage call */
 void        dvc_default_config(dvc_config* cfg);   /* the reference's defaults, mode FD */
 

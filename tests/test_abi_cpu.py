@@ -83,3 +83,21 @@ def test_packed_fp32_is_not_contracted(lib):
     assert counts, "k_degrade4s not found in the library"
     for fn, c in counts.items():
         assert (c.get("FFMA2"), c.get("FMUL2"), c.get("FADD2")) == (64, 56, 160), (fn, c)
+
+
+def test_product_library_reads_no_environment(lib):
+    """Measurement switches (kernel generations, copy-only probes) are compiled out of the product build: it reports so and
+    its sources call getenv only under #ifdef DVC_MEASURE (a stray variable must never change what the loop computes)."""
+    import glob
+    from dynamic_video_compression_surveillance_b200 import _lib
+    assert lib.dvc_measure_build() == 0
+    assert _lib.LIB_PATH.endswith("libdvc_b200.so")
+    uses = []
+    for f in glob.glob(os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", "*")):
+        src = open(f).read()
+        uses += [(os.path.basename(f), ln.strip()) for ln in src.splitlines() if "getenv(" in ln]
+    # the only getenv in the sources is measure_env()'s, inside #ifdef DVC_MEASURE (cudart's own imports do not count)
+    assert len(uses) == 1 and uses[0][1].startswith("static int measure_env("), uses
+    src = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", "dvc_b200.cu")).read()
+    i = src.index("static int measure_env(")
+    assert src.rfind("#ifdef DVC_MEASURE", 0, i) > src.rfind("#endif", 0, i)

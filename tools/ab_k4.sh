@@ -1,3 +1,6 @@
+# environment switches exist only in the -DDVC_MEASURE flavour of the library: build it (here or before gpurun) and select it
+export DVC_LIB_FLAVOUR=measure
+[ -f dynamic_video_compression_surveillance_b200/libdvc_b200_measure.so ] || python dynamic_video_compression_surveillance_b200/build.py --measure
 # A/B of K4 variants inside one job (same box): env switches read at first launch of each process
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=serial,temperature.gpu --format=csv,noheader

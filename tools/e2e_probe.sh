@@ -1,3 +1,6 @@
+# environment switches exist only in the -DDVC_MEASURE flavour of the library: build it (here or before gpurun) and select it
+export DVC_LIB_FLAVOUR=measure
+[ -f dynamic_video_compression_surveillance_b200/libdvc_b200_measure.so ] || python dynamic_video_compression_surveillance_b200/build.py --measure
 # usage: bash tools/e2e_probe.sh "ENV=.. ENV=.." ...   : each argument is one configuration, run alone on GPU 0 and then on 2 GPUs at once
 for cfg in "$@"; do
   echo "== $cfg"
