@@ -23,7 +23,7 @@ class DvcConfig(C.Structure):
                 ("motion_threshold", C.c_float), ("min_area", C.c_double), ("kernel_size", C.c_int32),
                 ("release_factor", C.c_double), ("quantization_level", C.c_float), ("window_size", C.c_int32),
                 ("alpha_fraction", C.c_double), ("morph_kernel", C.c_int32), ("morph_shape", C.c_int32),
-                ("max_batch", C.c_int32), ("device", C.c_int32), ("src_width", C.c_int32), ("src_height", C.c_int32)]
+                ("max_batch", C.c_int32), ("device", C.c_int32), ("src_width", C.c_int32), ("src_height", C.c_int32), ("n_streams", C.c_int32)]
 
 
 class DvcCounters(C.Structure):

@@ -483,6 +483,7 @@ struct ProfRec { int kid; int launches; cudaEvent_t a, b; };
 struct dvc_handle {
     dvc_config cfg;
     int H, W, wpr;
+    int S;                        // streams of this handle (cfg.n_streams, >= 1): a lock-step group shares every launch
     size_t plane_words, plane_bytes, frame_bytes;
     bool aligned;                 // W % 16 == 0: vector paths
     long long n_masks;            // masks produced so far in this stream
@@ -526,16 +527,25 @@ struct dvc_handle {
     char err[512];
 };
 
+// Frames per stream in one chunk of dvc_process_host's copy pipeline: small enough that the first upload and the last
+// download (the only copies nothing overlaps) are short against the PCIe-bound steady state, large enough for full-size
+// kernels: about 8 frames per chunk over all streams of the handle.
+static int host_chunk_frames(const dvc_handle* h) {
+    const int total = std::max(1, measure_env("DVC_HOST_CHUNK", 8));
+    return std::max(1, std::min(h->cfg.max_batch, (total + h->S - 1) / h->S));
+}
+
 static int alloc_staging(dvc_handle* h) {
     char* ERRBUF = h->err;
     if (h->staging) return DVC_OK;
-    const size_t fb = h->frame_bytes * h->cfg.max_batch;
+    const size_t nst = (size_t)h->S * host_chunk_frames(h);
+    const size_t fb = h->frame_bytes * nst;
     for (int b = 0; b < 2; ++b) {
         CU(cudaMalloc(&h->st_in[b], fb));
         CU(cudaMalloc(&h->st_ov[b], fb));
         CU(cudaMalloc(&h->st_cp[b], fb));
-        CU(cudaMalloc(&h->st_mask[b], h->plane_bytes * h->cfg.max_batch));
-        if (h->resizing) CU(cudaMalloc(&h->st_src[b], h->src_frame_bytes * h->cfg.max_batch));
+        CU(cudaMalloc(&h->st_mask[b], h->plane_bytes * nst));
+        if (h->resizing) CU(cudaMalloc(&h->st_src[b], h->src_frame_bytes * nst));
         CU(cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
     }
@@ -594,18 +604,21 @@ extern "C" void dvc_default_config(dvc_config* c) {
     c->morph_shape = DVC_SHAPE_ELLIPSE;
     c->max_batch = 16;
     c->device = 0;
+    c->n_streams = 1;
 }
 
 static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     char* ERRBUF = h->err;
     h->cfg = *cfg;
     h->W = cfg->width; h->H = cfg->height;
+    h->cfg.n_streams = h->S = std::max(1, cfg->n_streams);
     h->wpr = words_per_row(h->W);
     h->plane_words = (size_t)h->H * h->wpr;
     h->plane_bytes = (size_t)h->H * h->W;
     h->frame_bytes = h->plane_bytes * 3;
     h->aligned = (h->W % 16) == 0;
-    const int T = cfg->max_batch;
+    const int S = h->S;
+    const int T = cfg->max_batch * S;          // planes of scratch per set: max_batch frames of every stream
     h->seg_len = std::max(1, measure_env("DVC_SEG_LEN", 8));
     h->gray_impl = measure_env("DVC_GRAY_IMPL", 2);
     CU(cudaSetDevice(cfg->device));
@@ -620,7 +633,7 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
         CU(cudaMalloc(&h->resize_tables, blob.size()));
         CU(cudaMemcpy(h->resize_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     }
-    for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&h->prev_gray[i], h->plane_bytes)); CU(cudaMemset(h->prev_gray[i], 0, h->plane_bytes)); }
+    for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&h->prev_gray[i], h->plane_bytes * S)); CU(cudaMemset(h->prev_gray[i], 0, h->plane_bytes * S)); }
     for (int s = 0; s < 2; ++s)
         for (int k = 0; k < 3; ++k) {
             CU(cudaMalloc(&h->bits[s][k], h->plane_words * 4 * T));
@@ -638,8 +651,8 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     CU(cudaMemset(h->counters_dev, 0, sizeof(Counters)));
     h->chain.n = 0; h->chain.halo_top = h->chain.halo_bot = 0;
     if (cfg->mode == DVC_MODE_FD) {
-        CU(cudaMalloc(&h->acc, h->plane_bytes));
-        CU(cudaMemset(h->acc, 0, h->plane_bytes));
+        CU(cudaMalloc(&h->acc, h->plane_bytes * S));
+        CU(cudaMemset(h->acc, 0, h->plane_bytes * S));
         CU(cudaMalloc(&h->blurred, h->plane_bytes * T));
         int rc = ccl_scratch_alloc(h->err, h->ccl, std::min(T, 64), h->H, h->W);
         if (rc) return rc;
@@ -648,9 +661,9 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     } else {
         if (cfg->window_size < 1 || cfg->window_size > 31)
             return set_err(h->err, DVC_ERR_UNSUPPORTED, "window_size %d: supported range is 1..31", cfg->window_size);
-        h->ring_cap = T + cfg->window_size + 1;
-        CU(cudaMalloc(&h->ring, h->plane_words * 4 * h->ring_cap));
-        CU(cudaMemset(h->ring, 0, h->plane_words * 4 * h->ring_cap));
+        h->ring_cap = cfg->max_batch + cfg->window_size + 1;
+        CU(cudaMalloc(&h->ring, h->plane_words * 4 * h->ring_cap * S));
+        CU(cudaMemset(h->ring, 0, h->plane_words * 4 * h->ring_cap * S));
         window_min_counts(cfg->alpha_fraction, cfg->window_size, h->min_counts);
         if (cfg->morph_kernel > 0) {
             if (!chain_push(h->chain, DVC_MORPH_CLOSE, cfg->morph_shape, cfg->morph_kernel) ||
@@ -722,9 +735,9 @@ extern "C" int dvc_begin_stream(dvc_handle* h, const uint8_t* prev_gray_host) {
     if (!h || !prev_gray_host) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_begin_stream: null argument");
     CU(cudaSetDevice(h->cfg.device));
     CU(handle_join(h));
-    CU(h_copy(h, h->prev_gray[h->cur], prev_gray_host, h->plane_bytes, cudaMemcpyHostToDevice));
-    if (h->acc) CU(h_fill0(h, h->acc, h->plane_bytes));
-    if (h->ring) CU(h_fill0(h, h->ring, h->plane_words * 4 * h->ring_cap));
+    CU(h_copy(h, h->prev_gray[h->cur], prev_gray_host, h->plane_bytes * h->S, cudaMemcpyHostToDevice));
+    if (h->acc) CU(h_fill0(h, h->acc, h->plane_bytes * h->S));
+    if (h->ring) CU(h_fill0(h, h->ring, h->plane_words * 4 * h->ring_cap * h->S));
     h->n_masks = 0;
     return DVC_OK;
 }
@@ -735,9 +748,9 @@ static const uint32_t STATE_MAGIC = 0x31435644u;   // "DVC1"
 
 extern "C" size_t dvc_state_bytes(const dvc_handle* h) {
     if (!h) return 0;
-    size_t n = sizeof(StateHeader) + h->plane_bytes;
+    size_t n = h->plane_bytes;
     n += h->cfg.mode == DVC_MODE_FD ? h->plane_bytes : (size_t)h->cfg.window_size * h->plane_words * 4;
-    return n;
+    return sizeof(StateHeader) + n * h->S;      // header | per stream: prev_gray | acc or K raw planes
 }
 
 extern "C" int dvc_get_state(dvc_handle* h, void* buf, size_t bytes) {
@@ -745,19 +758,22 @@ extern "C" int dvc_get_state(dvc_handle* h, void* buf, size_t bytes) {
     if (!h || !buf || bytes < dvc_state_bytes(h)) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_get_state: buffer too small");
     CU(cudaSetDevice(h->cfg.device));
     CU(handle_join(h));
-    StateHeader hd = {STATE_MAGIC, (uint32_t)h->cfg.mode, (uint32_t)h->W, (uint32_t)h->H, (uint32_t)h->cfg.window_size, 0, h->n_masks};
+    StateHeader hd = {STATE_MAGIC, (uint32_t)h->cfg.mode, (uint32_t)h->W, (uint32_t)h->H, (uint32_t)h->cfg.window_size, (uint32_t)h->S, h->n_masks};
     uint8_t* p = (uint8_t*)buf;
     memcpy(p, &hd, sizeof(hd)); p += sizeof(hd);
-    CU(h_copy(h, p, h->prev_gray[h->cur], h->plane_bytes, cudaMemcpyDeviceToHost)); p += h->plane_bytes;
-    if (h->cfg.mode == DVC_MODE_FD) {
-        CU(h_copy(h, p, h->acc, h->plane_bytes, cudaMemcpyDeviceToHost));
-    } else {
-        const int K = h->cfg.window_size;
-        for (int i = 0; i < K; ++i) {       // slot i holds mask n_masks-K+i (zeros if before the stream start)
-            const long long f = h->n_masks - K + i;
-            if (f >= 0) CU(h_copy(h, p, h->ring + (size_t)(f % h->ring_cap) * h->plane_words, h->plane_words * 4, cudaMemcpyDeviceToHost));
-            else memset(p, 0, h->plane_words * 4);
-            p += h->plane_words * 4;
+    for (int st = 0; st < h->S; ++st) {
+        CU(h_copy(h, p, h->prev_gray[h->cur] + (size_t)st * h->plane_bytes, h->plane_bytes, cudaMemcpyDeviceToHost)); p += h->plane_bytes;
+        if (h->cfg.mode == DVC_MODE_FD) {
+            CU(h_copy(h, p, h->acc + (size_t)st * h->plane_bytes, h->plane_bytes, cudaMemcpyDeviceToHost)); p += h->plane_bytes;
+        } else {
+            const int K = h->cfg.window_size;
+            const uint32_t* ring = h->ring + (size_t)st * h->ring_cap * h->plane_words;
+            for (int i = 0; i < K; ++i) {       // slot i holds mask n_masks-K+i (zeros if before the stream start)
+                const long long f = h->n_masks - K + i;
+                if (f >= 0) CU(h_copy(h, p, ring + (size_t)(f % h->ring_cap) * h->plane_words, h->plane_words * 4, cudaMemcpyDeviceToHost));
+                else memset(p, 0, h->plane_words * 4);
+                p += h->plane_words * 4;
+            }
         }
     }
     return DVC_OK;
@@ -770,20 +786,23 @@ extern "C" int dvc_set_state(dvc_handle* h, const void* buf, size_t bytes) {
     const uint8_t* p = (const uint8_t*)buf;
     memcpy(&hd, p, sizeof(hd)); p += sizeof(hd);
     if (hd.magic != STATE_MAGIC || hd.mode != (uint32_t)h->cfg.mode || hd.W != (uint32_t)h->W || hd.H != (uint32_t)h->H ||
-        (h->cfg.mode == DVC_MODE_WINDOW && hd.K != (uint32_t)h->cfg.window_size))
+        (h->cfg.mode == DVC_MODE_WINDOW && hd.K != (uint32_t)h->cfg.window_size) || std::max(1u, hd.reserved) != (uint32_t)h->S)
         return set_err(h->err, DVC_ERR_INVALID, "dvc_set_state: blob does not match this handle's configuration");
     CU(cudaSetDevice(h->cfg.device));
     CU(handle_join(h));
-    CU(h_copy(h, h->prev_gray[h->cur], p, h->plane_bytes, cudaMemcpyHostToDevice)); p += h->plane_bytes;
     h->n_masks = hd.n_masks;
-    if (h->cfg.mode == DVC_MODE_FD) {
-        CU(h_copy(h, h->acc, p, h->plane_bytes, cudaMemcpyHostToDevice));
-    } else {
-        const int K = h->cfg.window_size;
-        for (int i = 0; i < K; ++i) {
-            const long long f = h->n_masks - K + i;
-            if (f >= 0) CU(h_copy(h, h->ring + (size_t)(f % h->ring_cap) * h->plane_words, p, h->plane_words * 4, cudaMemcpyHostToDevice));
-            p += h->plane_words * 4;
+    for (int st = 0; st < h->S; ++st) {
+        CU(h_copy(h, h->prev_gray[h->cur] + (size_t)st * h->plane_bytes, p, h->plane_bytes, cudaMemcpyHostToDevice)); p += h->plane_bytes;
+        if (h->cfg.mode == DVC_MODE_FD) {
+            CU(h_copy(h, h->acc + (size_t)st * h->plane_bytes, p, h->plane_bytes, cudaMemcpyHostToDevice)); p += h->plane_bytes;
+        } else {
+            const int K = h->cfg.window_size;
+            uint32_t* ring = h->ring + (size_t)st * h->ring_cap * h->plane_words;
+            for (int i = 0; i < K; ++i) {
+                const long long f = h->n_masks - K + i;
+                if (f >= 0) CU(h_copy(h, ring + (size_t)(f % h->ring_cap) * h->plane_words, p, h->plane_words * 4, cudaMemcpyHostToDevice));
+                p += h->plane_words * 4;
+            }
         }
     }
     return DVC_OK;
@@ -865,13 +884,14 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
     uint32_t* const bits_b = h->bits[set][1];
     uint32_t* const bits_c = h->bits[set][2];
     const int H = h->H, W = h->W, wpr = h->wpr;
+    const int S = h->S, ST = S * T;          // T frames of each of the S streams: buffers are [S][T] (stream-major)
     const uint32_t thr = (uint32_t)std::max(0.0f, std::floor(h->cfg.motion_threshold));
     const uint32_t* over127 = nullptr;
     const uint32_t* nonzero = nullptr;
     const unsigned g16 = cdiv((size_t)((W + 15) / 16) * H, 256);
     if (h->cfg.mode == DVC_MODE_WINDOW) {
         const int nseg = (T + h->seg_len - 1) / h->seg_len;
-        dim3 g1(g16, nseg);
+        dim3 g1(g16, nseg, S);
         uint8_t* pg_in = h->prev_gray[h->cur];
         uint8_t* pg_out = h->prev_gray[h->cur ^ 1];
         { ProfScope ps(h, DVC_PROF_FRONT, 1, st);
@@ -886,7 +906,7 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         }
         CHECK_LAUNCH();
         h->cur ^= 1;
-        dim3 g2(cdiv(h->plane_words, 256), nseg);
+        dim3 g2(cdiv(h->plane_words, 256), nseg, S);
         { ProfScope ps(h, DVC_PROF_VOTE, 1, st);
         k_window_vote<<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, (int)(h->n_masks % h->ring_cap), T, h->cfg.window_size, h->min_counts, bits_a, h->seg_len);
         }
@@ -894,44 +914,46 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         const uint32_t* fin = bits_a;
         if (h->chain.n) {
             ProfScope ps(h, DVC_PROF_MORPH, 1, st);
-            int rc = launch_morph_chain(h->err, bits_a, bits_b, T, H, W, h->chain, st);
+            int rc = launch_morph_chain(h->err, bits_a, bits_b, ST, H, W, h->chain, st);
             if (rc) return rc;
             fin = bits_b;
         }
         over127 = nonzero = fin;
         if (mask_out) {
             ProfScope ps(h, DVC_PROF_MISC, 1, st);
-            int rc = unpack_from_bits(fin, mask_out, T, H, W, st);
+            int rc = unpack_from_bits(fin, mask_out, ST, H, W, st);
             if (rc) return rc;
         }
     } else {
-        dim3 gb((W + BL_TW - 1) / BL_TW, (H + BL_TH - 1) / BL_TH, T);
+        dim3 gb((W + BL_TW - 1) / BL_TW, (H + BL_TH - 1) / BL_TH, ST);
         { ProfScope ps(h, DVC_PROF_FRONT, 1, st);
         if (h->aligned) k_gray_blur5<true><<<gb, 256, 0, st>>>(frames, h->blurred, H, W);
         else k_gray_blur5<false><<<gb, 256, 0, st>>>(frames, h->blurred, H, W);
         }
         CHECK_LAUNCH();
-        dim3 gd(g16, T);
+        dim3 gd(g16, T, S);
         { ProfScope ps(h, DVC_PROF_DIFF, 1, st);
         if (h->aligned) k_diff_thresh_planes<true><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, bits_a, wpr, thr);
         else k_diff_thresh_planes<false><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, bits_a, wpr, thr);
         }
         CHECK_LAUNCH();
-        CU(cudaMemcpyAsync(h->prev_gray[h->cur ^ 1], h->blurred + (size_t)(T - 1) * h->plane_bytes, h->plane_bytes, cudaMemcpyDeviceToDevice, st));
+        for (int sidx = 0; sidx < S; ++sidx)
+            CU(cudaMemcpyAsync(h->prev_gray[h->cur ^ 1] + (size_t)sidx * h->plane_bytes,
+                               h->blurred + ((size_t)sidx * T + (T - 1)) * h->plane_bytes, h->plane_bytes, cudaMemcpyDeviceToDevice, st));
         h->cur ^= 1;
         int rc;
-        { ProfScope ps(h, DVC_PROF_CCL, 7 * ((T + h->ccl.frames - 1) / h->ccl.frames), st);
-        rc = launch_contour_filter(h->err, bits_a, bits_b, T, H, W, h->cfg.min_area, h->ccl, st);
+        { ProfScope ps(h, DVC_PROF_CCL, 7 * ((ST + h->ccl.frames - 1) / h->ccl.frames), st);
+        rc = launch_contour_filter(h->err, bits_a, bits_b, ST, H, W, h->cfg.min_area, h->ccl, st);
         }
         if (rc) return rc;
         { ProfScope ps(h, DVC_PROF_MORPH, 1, st);
-        rc = launch_morph_chain(h->err, bits_b, bits_a, T, H, W, h->chain, st);      // dilate -> bits_a
+        rc = launch_morph_chain(h->err, bits_b, bits_a, ST, H, W, h->chain, st);      // dilate -> bits_a
         }
         if (rc) return rc;
         const float alpha = (float)h->cfg.release_factor, beta = (float)(1.0 - h->cfg.release_factor);
         { ProfScope ps(h, DVC_PROF_EMA, 1, st);
-        if (h->aligned) k_ema<true><<<g16, 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
-        else k_ema<false><<<g16, 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
+        if (h->aligned) k_ema<true><<<dim3(g16, S), 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
+        else k_ema<false><<<dim3(g16, S), 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
         }
         CHECK_LAUNCH();
         over127 = bits_b;
@@ -943,7 +965,7 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
     }
     if (overlay || compressed) {
         ProfScope ps(h, DVC_PROF_DEGRADE, 1, st_k4);
-        int rc = launch_degrade(h->err, frames, over127, nonzero, compressed, overlay, T, H, W, h->cfg.block_size,
+        int rc = launch_degrade(h->err, frames, over127, nonzero, compressed, overlay, ST, H, W, h->cfg.block_size,
                                 h->cfg.quantization_level, DVC_DEGRADE_FD, h->counters_dev, st_k4);
         if (rc) return rc;
     }
@@ -952,9 +974,9 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         h->ev_used[set] = true;
     }
     h->n_masks += T;
-    h->counters_host.frames += T;
-    h->counters_host.pixels += (uint64_t)T * H * W;
-    h->counters_host.blocks += (uint64_t)T * ((H + h->cfg.block_size - 1) / h->cfg.block_size) * ((W + h->cfg.block_size - 1) / h->cfg.block_size);   // clipped edge blocks count (frame_differencing.py:117-118)
+    h->counters_host.frames += ST;
+    h->counters_host.pixels += (uint64_t)ST * H * W;
+    h->counters_host.blocks += (uint64_t)ST * ((H + h->cfg.block_size - 1) / h->cfg.block_size) * ((W + h->cfg.block_size - 1) / h->cfg.block_size);   // clipped edge blocks count (frame_differencing.py:117-118)
     return DVC_OK;
 }
 
@@ -1012,10 +1034,8 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
     CU(cudaSetDevice(h->cfg.device));
     int rc = alloc_staging(h);
     if (rc) return rc;
-    // chunk size of the copy pipeline: small enough that the first upload and the last download (the only copies
-    // nothing overlaps) are short against the PCIe-bound steady state, large enough for full-size kernels
-    static const int host_chunk = std::max(1, measure_env("DVC_HOST_CHUNK", 8));
-    const int Tc = std::min(h->cfg.max_batch, host_chunk);
+    const int Tc = host_chunk_frames(h);
+    const int S = h->S;
     const int64_t nchunks = (n_frames + Tc - 1) / Tc;
     CU(handle_join(h));                   // join whatever dvc_process_batch left in flight (this handle only)
     for (int64_t c = 0; c < nchunks; ++c) {
@@ -1024,15 +1044,21 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
         const int T = (int)std::min<int64_t>(Tc, n_frames - f0);
         // the input buffer is free once the degrade kernel that read it (chunk c-2) is done
         if (c >= 2) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_k4[b], 0));
+        // host buffers are [S][n_frames] (stream-major), the device staging of a chunk is [S][T]: one copy per stream
         if (h->resizing) {
             // frames arrive at the capture's size: upload, then the reference's cv2.resize (frame_differencing.py:91) on the GPU
-            CU(cudaMemcpyAsync(h->st_src[b], frames_host + (size_t)f0 * h->src_frame_bytes, (size_t)T * h->src_frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
-            rc = launch_resize(h->err, h->st_src[b], h->st_in[b], T, h->cfg.src_height, h->cfg.src_width, h->H, h->W, 3,
+            for (int sidx = 0; sidx < S; ++sidx)
+                CU(cudaMemcpyAsync(h->st_src[b] + (size_t)sidx * T * h->src_frame_bytes,
+                                   frames_host + ((size_t)sidx * n_frames + f0) * h->src_frame_bytes, (size_t)T * h->src_frame_bytes,
+                                   cudaMemcpyHostToDevice, h->s_h2d));
+            rc = launch_resize(h->err, h->st_src[b], h->st_in[b], S * T, h->cfg.src_height, h->cfg.src_width, h->H, h->W, 3,
                                resize_tables_view(h->resize_tables, h->H, h->W), h->s_h2d);
             if (rc) { handle_join(h); return rc; }
             h->launches += 1;
         } else
-        CU(cudaMemcpyAsync(h->st_in[b], frames_host + (size_t)f0 * h->frame_bytes, (size_t)T * h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+        for (int sidx = 0; sidx < S; ++sidx)
+            CU(cudaMemcpyAsync(h->st_in[b] + (size_t)sidx * T * h->frame_bytes, frames_host + ((size_t)sidx * n_frames + f0) * h->frame_bytes,
+                               (size_t)T * h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
         CU(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
         CU(cudaStreamWaitEvent(h->s_mask, h->ev_h2d[b], 0));
         if (c >= 2) {
@@ -1046,9 +1072,12 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
                                 mask_host ? h->st_mask[b] : nullptr, h->s_mask, h->s_k4, b);
         if (rc) { handle_join(h); return rc; }
         CU(cudaStreamWaitEvent(h->s_d2h, h->ev_k4[b], 0));
-        if (overlay_host) CU(cudaMemcpyAsync(overlay_host + (size_t)f0 * h->frame_bytes, h->st_ov[b], (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
-        if (compressed_host) CU(cudaMemcpyAsync(compressed_host + (size_t)f0 * h->frame_bytes, h->st_cp[b], (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
-        if (mask_host) CU(cudaMemcpyAsync(mask_host + (size_t)f0 * h->plane_bytes, h->st_mask[b], (size_t)T * h->plane_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+        for (int sidx = 0; sidx < S; ++sidx) {
+            const size_t ho = (size_t)sidx * n_frames + f0, so = (size_t)sidx * T;
+            if (overlay_host) CU(cudaMemcpyAsync(overlay_host + ho * h->frame_bytes, h->st_ov[b] + so * h->frame_bytes, (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+            if (compressed_host) CU(cudaMemcpyAsync(compressed_host + ho * h->frame_bytes, h->st_cp[b] + so * h->frame_bytes, (size_t)T * h->frame_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+            if (mask_host) CU(cudaMemcpyAsync(mask_host + ho * h->plane_bytes, h->st_mask[b] + so * h->plane_bytes, (size_t)T * h->plane_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+        }
         CU(cudaEventRecord(h->ev_d2h[b], h->s_d2h));
     }
     CU(cudaStreamSynchronize(h->s_d2h));

@@ -38,6 +38,8 @@ DEVI void store_u8x16_generic(uint8_t* row, int x0, int W, const uint32_t (&v)[4
 //
 // ring:   raw-mask ring buffer, plane of frame f lives in slot f % ring_cap
 // f0:     global index of frames[0] within the stream
+// blockIdx.z = stream of a lock-step stream group (dvc_config.n_streams): frames [S][T], one prev-gray plane, ring and
+// gray output run per stream, laid out stream-major.
 // ------------------------------------------------------------------------------------------------
 template <bool ALIGNED, int GRAY = 0>   // GRAY: 0 = PRMT + IMAD, 1 = IDP.4A, 2 = IDP.2A
 __global__ void __launch_bounds__(256)
@@ -54,6 +56,14 @@ k_gray_diff_thresh(const uint8_t* __restrict__ frames, int T, int H, int W,
     const size_t row_off = (size_t)y * W * 3, px_off = (size_t)y * W + x0;
     const size_t plane_words = (size_t)H * wpr;
     const uint32_t vmask = (W - x0 >= 16) ? 0xffffu : ((1u << (W - x0)) - 1u);
+    {
+        const size_t s = blockIdx.z;
+        frames += s * T * frame_bytes;
+        prev_gray_in += s * plane_bytes;
+        if (gray_state_out) gray_state_out += s * plane_bytes;
+        if (gray_all_out) gray_all_out += s * T * plane_bytes;
+        ring += s * ring_cap * plane_words;
+    }
 
     uint32_t pg[4], w[12];
     if (t0 == 0) {
@@ -234,13 +244,16 @@ k_gray_blur5(const uint8_t* __restrict__ frames, uint8_t* __restrict__ blurred, 
 template <bool ALIGNED>
 __global__ void __launch_bounds__(256)
 k_diff_thresh_planes(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ prev_gray, int H, int W,
-                     uint32_t* __restrict__ bits_out, int wpr, uint32_t thr) {
+                     uint32_t* __restrict__ bits_out, int wpr, uint32_t thr) {     // grid (.., T, S): planes [S][T], prev_gray [S]
     const int gpr = (W + 15) >> 4;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)gpr * H) return;
     const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx << 4;
     const int t = blockIdx.y;
     const size_t plane_bytes = (size_t)H * W;
+    planes += (size_t)blockIdx.z * gridDim.y * plane_bytes;
+    prev_gray += (size_t)blockIdx.z * plane_bytes;
+    bits_out += (size_t)blockIdx.z * gridDim.y * H * wpr;
     const uint8_t* cur = planes + (size_t)t * plane_bytes + (size_t)y * W;
     const uint8_t* prv = (t == 0 ? prev_gray : planes + (size_t)(t - 1) * plane_bytes) + (size_t)y * W;
     uint32_t a[4], b[4];

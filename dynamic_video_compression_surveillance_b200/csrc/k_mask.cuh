@@ -50,6 +50,8 @@ k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int
     const size_t plane_words = (size_t)H * wpr;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= plane_words) return;
+    ring += (size_t)blockIdx.z * ring_cap * plane_words;          // blockIdx.z = stream of a lock-step group
+    voted += (size_t)blockIdx.z * T * plane_words;
     const int t0 = blockIdx.y * seg_len, t1 = min(T, t0 + seg_len);
     const uint32_t vm = valid_mask((int)(idx % wpr), W);
     uint32_t c[CNT_BITS] = {0, 0, 0, 0, 0};
@@ -121,6 +123,12 @@ k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t*
     const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx << 4;
     const size_t plane_words = (size_t)H * wpr, plane_bytes = (size_t)H * W;
     const int npx = min(16, W - x0);
+    {   // blockIdx.y = stream of a lock-step group: one accumulator plane per stream, T planes of everything else
+        const size_t s = blockIdx.y;
+        acc += s * plane_bytes;
+        dilated += s * T * plane_words; over127 += s * T * plane_words; nonzero += s * T * plane_words;
+        if (acc_all) acc_all += s * T * plane_bytes;
+    }
     uint32_t a[4];
     uint8_t* arow = acc + (size_t)y * W;
     if (ALIGNED) { uint4 t = *reinterpret_cast<const uint4*>(arow + x0); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }

@@ -46,13 +46,18 @@ def pinned_empty(shape) -> torch.Tensor:
 
 class FramePipeline:
     """Per-stream state + the loop body.  Keyword names and defaults are the reference's
-    (frame_differencing.py:21-30; motion_compression_opt.py:29-31)."""
+    (frame_differencing.py:21-30; motion_compression_opt.py:29-31).
+
+    ``n_streams=S > 1`` makes the object a lock-step group of S independent camera streams (the reference processes its
+    files one after another, windows.py:142-160; BASELINE config 4) whose kernels share every launch: all frame / output
+    arrays gain a leading stream axis ([S, T, H, W, 3]), ``begin_stream`` takes [S, H, W] planes, and every call
+    advances each stream by T frames.  Results per stream equal those of S separate pipelines."""
 
     def __init__(self, width: int, height: int, mode: str = "fd", *, block_size: int = 4, motion_threshold: float = 0.5,
                  min_area: float = 500, kernel_size: int = 7, release_factor: float = 0.5,
                  quantization_level: float = 100, window_size: int = 30, alpha_fraction: float = 0.2,
                  morph_kernel: int = 2, morph_shape: str = "ellipse", max_batch: int = 16, device: int | None = None,
-                 src_size: tuple | None = None):
+                 src_size: tuple | None = None, n_streams: int = 1):
         _require_cuda()
         self._lib = _lib.load()
         self.width, self.height, self.mode = int(width), int(height), mode
@@ -70,6 +75,8 @@ class FramePipeline:
         self.src_width, self.src_height = (int(src_size[0]), int(src_size[1])) if src_size else (self.width, self.height)
         if (self.src_width, self.src_height) != (self.width, self.height):
             cfg.src_width, cfg.src_height = self.src_width, self.src_height
+        self.n_streams = max(1, int(n_streams))
+        cfg.n_streams = self.n_streams
         self.cfg = cfg
         self.max_batch = int(max_batch)
         self._h = C.c_void_p()
@@ -100,8 +107,9 @@ class FramePipeline:
     def begin_stream(self, prev_gray: np.ndarray):
         """Seed prev_gray (frame_differencing.py:75-77 / motion_compression_opt.py:60) and clear the mask state."""
         g = np.ascontiguousarray(prev_gray, dtype=np.uint8)
-        if g.shape != (self.height, self.width):
-            raise ValueError(f"prev_gray must be [{self.height}, {self.width}]")
+        want = (self.height, self.width) if self.n_streams == 1 else (self.n_streams, self.height, self.width)
+        if g.shape != want and g.shape != (1,) + want:
+            raise ValueError(f"prev_gray must be {list(want)}")
         self._check(self._lib.dvc_begin_stream(self._h, g.ctypes.data))
 
     def get_state(self) -> bytes:
@@ -140,14 +148,15 @@ class FramePipeline:
     # -- the loop body ------------------------------------------------------------------------------
     def process_device(self, frames: torch.Tensor, overlay: torch.Tensor | None = None,
                        compressed: torch.Tensor | None = None, mask: torch.Tensor | None = None, stream=None):
-        """frames [T,H,W,3] uint8 on the GPU, T <= max_batch.  Outputs are written into the given tensors
-        (None = not produced).  Asynchronous on the current (or given) torch stream."""
+        """frames [T,H,W,3] uint8 on the GPU ([S,T,H,W,3] for a stream group), T <= max_batch.  Outputs are written
+        into the given tensors (None = not produced).  Asynchronous on the current (or given) torch stream."""
         _dev_u8(frames, "frames")
-        T = frames.shape[0]
-        if tuple(frames.shape[1:]) != (self.height, self.width, 3):
-            raise ValueError("frames must be [T, H, W, 3]")
+        lead = () if self.n_streams == 1 else (self.n_streams,)
+        T = frames.shape[len(lead)]
+        if tuple(frames.shape) != lead + (T, self.height, self.width, 3):
+            raise ValueError("frames must be [T, H, W, 3]" if not lead else f"frames must be [{self.n_streams}, T, H, W, 3]")
         for name, t, shp in (("overlay", overlay, frames.shape), ("compressed", compressed, frames.shape),
-                             ("mask", mask, frames.shape[:3])):
+                             ("mask", mask, frames.shape[:-1])):
             if t is not None:
                 _dev_u8(t, name)
                 if tuple(t.shape) != tuple(shp):
@@ -183,12 +192,13 @@ class FramePipeline:
             if tuple(a.shape) != tuple(shape):
                 raise ValueError(f"{name} has the wrong shape")
             return a.ctypes.data
-        n = int(frames.shape[0])
-        fshape = (n, self.height, self.width, 3)
-        self._check(self._lib.dvc_process_host(self._h, host_ptr(frames, (n, self.src_height, self.src_width, 3), "frames"), n,
+        lead = () if self.n_streams == 1 else (self.n_streams,)       # stream groups: [S, N, H, W, 3], stream-major
+        n = int(frames.shape[len(lead)])
+        fshape = lead + (n, self.height, self.width, 3)
+        self._check(self._lib.dvc_process_host(self._h, host_ptr(frames, lead + (n, self.src_height, self.src_width, 3), "frames"), n,
                                                host_ptr(overlay, fshape, "overlay"),
                                                host_ptr(compressed, fshape, "compressed"),
-                                               host_ptr(mask, fshape[:3], "mask")))
+                                               host_ptr(mask, fshape[:-1], "mask")))
 
 
 # ---------------------------------------------------------------------------------------------------

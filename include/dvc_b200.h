@@ -78,6 +78,11 @@ typedef struct dvc_config {
     int32_t src_width, src_height; /* 0, or the size of the frames handed to dvc_process_host when it differs from
                                     * width x height: the library then does the reference's cv2.resize (default
                                     * INTER_LINEAR, frame_differencing.py:74,91) on the GPU after the upload */
+    int32_t n_streams;            /* 0 or 1: one stream.  S > 1: a lock-step group of S independent camera streams (the reference
+                                   * loops over files one by one, windows.py:142-160; BASELINE config 4) that share every kernel
+                                   * launch.  Each call then advances every stream by n_frames: frame / output buffers are
+                                   * [S][n_frames][H][W](x3), dvc_begin_stream takes [S][H][W] planes, state blobs and counters
+                                   * cover all S streams. */
 } dvc_config;
 
 typedef struct dvc_handle dvc_handle;

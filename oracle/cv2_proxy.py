@@ -104,6 +104,18 @@ class Cv2Proxy:
         self._tap("addWeighted", r)
         return r
 
+    # taps of temporal_smoothing_flow (motion_compression_opt.py:82,89-90)
+    def cartToPolar(self, x, y, *a, **k):
+        r = _cv2.cartToPolar(x, y, *a, **k)
+        self._tap("flow_magnitude", r[0])
+        return r
+
+    def morphologyEx(self, src, op, kernel, *a, **k):
+        r = _cv2.morphologyEx(src, op, kernel, *a, **k)
+        self._tap("morph_in_%d" % op, src)
+        self._tap("morph_out_%d" % op, r)
+        return r
+
 
 def _load_reference_module(name):
     path = os.path.join(REFERENCE_DIR, name + ".py")
@@ -155,6 +167,26 @@ def run_reference_mco_compress(frames, masks):
     with tempfile.TemporaryDirectory() as tmp:
         mod.compress_with_motion("in.mp4", "mask.mp4", tmp)
         return store[os.path.join(tmp, "compressed.mp4")]
+
+
+def run_reference_temporal_smoothing_flow(frames, **kwargs):
+    """Run the reference's ``temporal_smoothing_flow`` (motion_compression_opt.py:29-109) unmodified on an in-memory clip.
+    Farneback flow runs as the reference calls it; the proxy taps what flows between the statements the GPU path
+    replaces: the flow magnitude (cartToPolar, :82; ``mag > flow_threshold`` is the raw mask, :83), the voted mask going
+    into MORPH_CLOSE (:86 -> :89), the mask leaving MORPH_OPEN (:90), and the rectangle mask handed to the mask writer
+    (:93-98).  Returns dict(raw=[...], voted=[...], morphed=[...], rect=[...], overlay=[...], result=(frames, total, avg))."""
+    mod = _load_reference_module("motion_compression_opt")
+    store, taps = {}, {}
+    mod.cv2 = Cv2Proxy(store, taps)
+    store["in.mp4"] = frames
+    thr = kwargs.get("flow_threshold", 0.5)
+    with tempfile.TemporaryDirectory() as tmp:
+        result = mod.temporal_smoothing_flow("in.mp4", tmp, **kwargs)
+        rect = store[os.path.join(tmp, kwargs.get("mask_save_name", "mask.mp4"))]
+        overlay = store[os.path.join(tmp, kwargs.get("save_name", "overlay.mp4"))]
+    raw = [(m > thr).astype(np.uint8) * 255 for m in taps.get("flow_magnitude", [])]
+    return dict(raw=raw, voted=taps.get("morph_in_%d" % _cv2.MORPH_CLOSE, []), morphed=taps.get("morph_out_%d" % _cv2.MORPH_OPEN, []),
+                rect=rect, overlay=overlay, result=result)
 
 
 def run_reference_window_vote(raw_masks, alpha_fraction, window_size, morph_kernel):

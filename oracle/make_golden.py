@@ -98,6 +98,57 @@ def make_window(name="window_vote_48x80"):
     print(name, "ok")
 
 
+OF_CASES = {
+    # name: (height, width, n_frames, seed, kwargs of temporal_smoothing_flow)
+    "of_default_240x352": (240, 352, 44, 41, {}),                                                    # window 30, ellipse 2 (the call site's values)
+    "of_k5_m3_80x112": (80, 112, 24, 42, dict(window_size=5, alpha_fraction=0.5, morph_kernel=3, flow_threshold=0.3)),
+}
+
+
+def make_of(name, spec):
+    """temporal_smoothing_flow (motion_compression_opt.py:29-109) run unmodified: raw flow masks in, and the voted,
+    morphed and rectangle masks the reference produced from them."""
+    h, w, n, seed, kw = spec
+    clip = make_clip((h, w), n, seed=seed)
+    yy, xx = np.mgrid[0:h, 0:w]          # smooth background: Farneback needs texture gradients, not white noise
+    clip.background = np.stack([(xx * 255 // w), (yy * 255 // h), ((xx + yy) * 255 // (w + h))], -1).astype(np.uint8)
+    frames = list(clip.frames())
+    a = cv2_proxy.run_reference_temporal_smoothing_flow(frames, **kw)
+    b = cv2_proxy.run_reference_temporal_smoothing_flow(frames, **kw)
+    for k in ("raw", "voted", "morphed", "rect"):
+        assert len(a[k]) == n - 1, (k, len(a[k]))
+        assert all(np.array_equal(x, y) for x, y in zip(a[k], b[k])), f"reference not reproducible: {k}"
+    assert all(np.array_equal(x, y) for x, y in zip(a["overlay"], frames[1:]))      # overlay.mp4 is the unmodified frame (:99)
+    import cv2
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), recipe=np.array([h, w, n, seed]), kwargs=np.array(repr(kw)),
+                        cv2_version=np.array(cv2.__version__), raw=pack(a["raw"]), voted=pack(a["voted"]),
+                        morphed=pack(a["morphed"]), rect=pack(a["rect"]))
+    print(name, "ok", "motion px per frame:", [int((m != 0).sum()) for m in a["rect"][-3:]])
+
+
+def make_config1(name="fd_config1_480x640x300"):
+    """BASELINE configs[0]: frame_differencing.py, all defaults, on the synthetic 640x480 300-frame clip; the unmodified
+    reference takes ~3 minutes, so only hashes (every mask, overlay and compressed frame) and the reference's own timing
+    file are stored."""
+    import time
+    h, w, n, seed = 480, 640, 300, 0
+    frames = list(make_clip((h, w), n, seed=seed).frames())
+    t0 = time.time()
+    a = cv2_proxy.run_reference_fd(frames)
+    dt = time.time() - t0
+    import cv2
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), recipe=np.array([h, w, n, seed, 0]), kwargs=np.array(repr({})),
+                        cv2_version=np.array(cv2.__version__), numpy_version=np.array(np.__version__),
+                        acc_sha=np.array([sha(x) for x in a["acc"]]), raw_sha=np.array([sha(x) for x in a["raw"]]),
+                        filtered_sha=np.array([sha(x) for x in a["filtered"]]),
+                        overlay_sha=np.array([sha(x) for x in a["overlay"]]),
+                        compressed_sha=np.array([sha(x) for x in a["compressed"]]),
+                        static_px_last=np.array(int((a["acc"][-1] == 0).sum())),
+                        execution_times=np.array(a["execution_times"]),
+                        cpu_seconds=np.array(dt), cpu_threads=np.array(cv2.getNumThreads()), cpu_count=np.array(os.cpu_count()))
+    print(name, "ok", f"{dt:.1f} s for {n - 1} frames = {dt / (n - 1):.3f} s/frame;", a["execution_times"].replace("\n", " | "))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     only = sys.argv[1:]                       # optional fixture names: regenerate just those
@@ -108,6 +159,11 @@ def main():
         make_mco()
     if not only or "window_vote_48x80" in only:
         make_window()
+    for name, spec in OF_CASES.items():
+        if not only or name in only:
+            make_of(name, spec)
+    if "fd_config1_480x640x300" in only:      # ~3 minutes: only on request
+        make_config1()
 
 
 if __name__ == "__main__":

@@ -27,3 +27,16 @@ def load_fd(name):
     kw = ast.literal_eval(str(z["kwargs"]))
     frames = make_clip((h, w), n, seed=seed, temporal_noise=bool(noise)).frames()
     return z, frames, kw, (h, w, n)
+
+
+OF_FIXTURES = ["of_default_240x352", "of_k5_m3_80x112"]
+
+
+def load_of(name):
+    """Masks tapped from the UNMODIFIED temporal_smoothing_flow (oracle/make_golden.py::make_of): raw flow masks in, voted /
+    morphed / rectangle masks out, plus the keyword arguments of the run."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    h, w, n, seed = (int(v) for v in z["recipe"])
+    kw = dict(flow_threshold=0.5, alpha_fraction=0.2, window_size=30, morph_kernel=2)       # motion_compression_opt.py:29-30
+    kw.update(ast.literal_eval(str(z["kwargs"])))
+    return {k: unpack(z[k], w) for k in ("raw", "voted", "morphed", "rect")}, kw, (h, w, n)

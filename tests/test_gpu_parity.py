@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from oracle import loops, stage_ops as so
-from tests.golden_util import FD_CLIPPED_FIXTURE, FD_FIXTURES, load_fd, sha, unpack
+from tests.golden_util import FD_CLIPPED_FIXTURE, FD_FIXTURES, GOLDEN, OF_FIXTURES, load_fd, load_of, sha, unpack
 
 pytestmark = pytest.mark.gpu
 
@@ -852,6 +852,62 @@ def test_config4_concurrent_streams_are_independent(P):
         pipes[s].close()
 
 
+@pytest.mark.parametrize("mode", ["window", "fd"])
+@pytest.mark.parametrize("shape", [(96, 128), (62, 110)])
+def test_stream_group_equals_separate_pipelines(P, mode, shape):
+    """dvc_config.n_streams: S camera streams advanced in lock step by shared launches (BASELINE config 4) must give, per
+    stream, exactly what S separate handles give: masks, overlays, compressed frames, counters, over several batches of
+    uneven length, through the device-pointer call and the host-buffer call, and across a state hand-off."""
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w = shape
+    S, n = 3, 23
+    kw = dict(window_size=4, alpha_fraction=0.3, morph_kernel=2, kernel_size=5) if mode == "window" else dict(min_area=40, kernel_size=5)
+    clips = [make_clip((h, w), n, seed=50 + s, temporal_noise=(s == 1)).frames() for s in range(S)]
+    seed_of = (lambda f: so.bgr2gray(f)) if mode == "window" else loops.first_frame_gray_fd
+    solo_ov, solo_cp, solo_mk, solo_cnt = [], [], [], {}
+    for s in range(S):
+        pipe = P.FramePipeline(w, h, mode, max_batch=8, **kw)
+        pipe.begin_stream(seed_of(clips[s][0]))
+        ov = np.empty((n - 1, h, w, 3), np.uint8); cp = np.empty_like(ov); mk = np.empty((n - 1, h, w), np.uint8)
+        pipe.process_host(np.ascontiguousarray(clips[s][1:]), ov, cp, mk)
+        for k, v in pipe.counters().items():
+            solo_cnt[k] = solo_cnt.get(k, 0) + v
+        pipe.close()
+        solo_ov.append(ov); solo_cp.append(cp); solo_mk.append(mk)
+    solo_ov, solo_cp, solo_mk = np.stack(solo_ov), np.stack(solo_cp), np.stack(solo_mk)
+    body = np.ascontiguousarray(np.stack([c[1:] for c in clips]))                 # [S, n-1, H, W, 3]
+    seeds = np.stack([seed_of(c[0]) for c in clips])
+    # (a) host-buffer call, whole clip
+    grp = P.FramePipeline(w, h, mode, max_batch=8, n_streams=S, **kw)
+    grp.begin_stream(seeds)
+    ov = np.empty_like(body); cp = np.empty_like(body); mk = np.empty(body.shape[:-1], np.uint8)
+    grp.process_host(body, ov, cp, mk)
+    assert np.array_equal(mk, solo_mk) and np.array_equal(ov, solo_ov) and np.array_equal(cp, solo_cp)
+    assert grp.counters() == solo_cnt
+    # (b) device-pointer call in uneven batches, with a state hand-off to a fresh group in the middle
+    grp.begin_stream(seeds)
+    dbody = dev(body)
+    dov = torch.empty_like(dbody); dcp = torch.empty_like(dbody); dmk = torch.empty(dbody.shape[:-1], dtype=torch.uint8, device="cuda")
+    t = 0
+    for T in (8, 3, 1, 8, 2):
+        if t == 11:
+            blob = grp.get_state()
+            grp.close()
+            grp = P.FramePipeline(w, h, mode, max_batch=8, n_streams=S, **kw)
+            grp.set_state(blob)
+        sl = slice(t, t + T)
+        fin = dbody[:, sl].contiguous()
+        o, c = torch.empty_like(fin), torch.empty_like(fin)
+        m = torch.empty((S, T, h, w), dtype=torch.uint8, device="cuda")
+        grp.process_device(fin, o, c, m)
+        dov[:, sl], dcp[:, sl], dmk[:, sl] = o, c, m
+        t += T
+    torch.cuda.synchronize()
+    grp.close()
+    assert t == n - 1
+    assert np.array_equal(host(dmk), solo_mk) and np.array_equal(host(dov), solo_ov) and np.array_equal(host(dcp), solo_cp)
+
+
 def test_config5_farneback_masks_to_mco_degrade_1080p(P):
     """configs[4]: masks from the reference's Farneback + window vote + rectangles arithmetic
     (motion_compression_opt.py:72-97, on the CPU) fed to the shared degrade kernel in MCO flavour at 1080p."""
@@ -884,6 +940,48 @@ def test_config5_farneback_masks_to_mco_degrade_1080p(P):
     comp = host(comp)
     for i in (0, n - 2):
         _check_degraded_mco(comp[i], so.degrade_mco(frames[i + 1], masks[i]), frames[i + 1], masks[i])
+
+
+@pytest.mark.parametrize("name", OF_FIXTURES)
+def test_of_mask_chain_against_unmodified_reference_fixture(P, name):
+    """k_window_vote, k_morph_chain and the rectangle kernels against masks tapped from the UNMODIFIED
+    temporal_smoothing_flow (motion_compression_opt.py:83-97; Farneback stays on the CPU and is part of the fixture):
+    stage by stage, and through the drop-in's chunked host helper with carried history."""
+    from dynamic_video_compression_surveillance_b200 import host_loop
+    m, kw, (h, w, n) = load_of(name)
+    K, alpha, mk = kw["window_size"], kw["alpha_fraction"], kw["morph_kernel"]
+    voted = P.temporal_ring(dev(m["raw"]), K, alpha)
+    assert np.array_equal(host(voted), m["voted"])
+    morphed = P.morph(P.morph(dev(m["voted"]), "close", mk, "ellipse"), "open", mk, "ellipse")
+    assert np.array_equal(host(morphed), m["morphed"])
+    assert np.array_equal(host(P.mask_rectangles(dev(m["morphed"]))), m["rect"])
+    # the drop-in feeds chunks of raw masks with the deque's history carried on the host
+    got, hist = [], []
+    for c0 in range(0, n - 1, 7):
+        chunk = [x for x in m["raw"][c0:c0 + 7]]
+        got.append(host_loop.smooth_rect_masks_gpu(chunk, hist, K, alpha, mk))
+        hist = (hist + chunk)[-(K - 1):] if K > 1 else []
+    assert np.array_equal(np.concatenate(got), m["rect"])
+
+
+def test_config1_480p_300_frames_against_unmodified_reference(P):
+    """BASELINE configs[0]: frame_differencing.py with all defaults on the synthetic 640x480 300-frame clip.  The fixture
+    holds the SHA-256 of every accumulated mask, overlay frame and compressed frame the UNMODIFIED reference produced
+    (oracle/make_golden.py::make_config1, ~3 CPU minutes); the GPU loop must reproduce all 299 of each."""
+    z = np.load(os.path.join(GOLDEN, "fd_config1_480x640x300.npz"))
+    h, w, n, seed, noise = (int(v) for v in z["recipe"])
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    frames = make_clip((h, w), n, seed=seed, temporal_noise=bool(noise)).frames()
+    pipe = P.FramePipeline(w, h, "fd", max_batch=32)
+    pipe.begin_stream(loops.first_frame_gray_fd(frames[0]))
+    ov = np.empty((n - 1, h, w, 3), np.uint8); cp = np.empty_like(ov); acc = np.empty((n - 1, h, w), np.uint8)
+    pipe.process_host(np.ascontiguousarray(frames[1:]), ov, cp, acc)
+    pipe.close()
+    assert [sha(x) for x in acc] == list(z["acc_sha"])
+    assert [sha(x) for x in ov] == list(z["overlay_sha"])
+    if _exact(4):
+        assert [sha(x) for x in cp] == list(z["compressed_sha"])
+    assert int((acc[-1] == 0).sum()) == int(z["static_px_last"])
 
 
 def test_random_loop_configurations_against_oracle():

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import loops, stage_ops as so
-from tests.golden_util import FD_CLIPPED_FIXTURE, FD_FIXTURES, GOLDEN, load_fd, sha, unpack
+from tests.golden_util import FD_CLIPPED_FIXTURE, FD_FIXTURES, GOLDEN, OF_FIXTURES, load_fd, load_of, sha, unpack
 
 
 @pytest.mark.parametrize("name", FD_FIXTURES + [FD_CLIPPED_FIXTURE])
@@ -82,3 +82,35 @@ def test_window_vote_matches_reference_fixture():
             voted = np.where(cnt >= mc[len(win) - 1], 255, 0).astype(np.uint8)
             got = so.morph_open(so.morph_close(voted, kernel), kernel)
             assert np.array_equal(got, ref[t]), (key, t)
+
+
+@pytest.mark.parametrize("name", OF_FIXTURES)
+def test_of_mask_chain_matches_unmodified_temporal_smoothing_flow(name):
+    """motion_compression_opt.py:83-97 as run by the unmodified function (Farneback included): the numpy restatements of
+    the window vote, close / open and contours -> rectangles reproduce every tapped mask."""
+    m, kw, (h, w, n) = load_of(name)
+    K, alpha = kw["window_size"], kw["alpha_fraction"]
+    mc = so.window_min_counts(alpha, K)
+    kernel = so.structuring_ellipse(kw["morph_kernel"])
+    for t in range(n - 1):
+        win = m["raw"][max(0, t - K + 1):t + 1]
+        voted = np.where((win != 0).sum(axis=0) >= mc[len(win) - 1], 255, 0).astype(np.uint8)
+        assert np.array_equal(voted, m["voted"][t]), ("voted", t)
+        assert np.array_equal(so.window_vote(list(win), alpha), m["voted"][t])
+        morphed = so.morph_open(so.morph_close(voted, kernel), kernel)
+        assert np.array_equal(morphed, m["morphed"][t]), ("morphed", t)
+        assert np.array_equal(so.mask_rectangles(morphed), m["rect"][t]), ("rect", t)
+
+
+def test_config1_fixture_is_present_and_self_consistent():
+    """BASELINE configs[0] (640x480, 300 frames, fd defaults) through the unmodified reference: hashes only; the oracle
+    loop reproduces the first frames here, the GPU test (tests/test_gpu_parity.py) checks all 299."""
+    z = np.load(os.path.join(GOLDEN, "fd_config1_480x640x300.npz"))
+    h, w, n, seed, noise = (int(v) for v in z["recipe"])
+    assert (h, w, n) == (480, 640, 300) and len(z["compressed_sha"]) == n - 1
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    frames = make_clip((h, w), 4, seed=seed).frames()
+    got = loops.fd_loop(list(frames))
+    assert [sha(x) for x in got["acc"]] == list(z["acc_sha"][:3])
+    assert [sha(x) for x in got["overlay"]] == list(z["overlay_sha"][:3])
+    assert [sha(x) for x in got["compressed"]] == list(z["compressed_sha"][:3])
