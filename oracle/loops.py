@@ -63,6 +63,13 @@ def literal_degrade_fd(frame, acc, block_size, quantization_level):
     return cv2.cvtColor(cv2.merge(channels), cv2.COLOR_YCrCb2BGR)
 
 
+def colour_round_trip_only(frame):
+    """The cv2 calls around the Python block loop without the loop itself (frame_differencing.py:115-116,129-130): the
+    "cv2-only stage baseline" of BASELINE.md section 3 (``degrade="colour_only"`` in the loops below)."""
+    channels = list(cv2.split(cv2.cvtColor(frame, cv2.COLOR_BGR2YCrCb)))
+    return cv2.cvtColor(cv2.merge(channels), cv2.COLOR_YCrCb2BGR)
+
+
 def fd_loop(frames, block_size=4, motion_threshold=0.5, min_area=500, kernel_size=7, release_factor=0.5,
             quantization_level=100, literal_blocks=False, prev_gray=None, acc=None, degrade=True):
     """frame_differencing.py:67-133 on an in-memory clip.  ``frames[0]`` seeds prev_gray unless
@@ -91,7 +98,9 @@ def fd_loop(frames, block_size=4, motion_threshold=0.5, min_area=500, kernel_siz
         out["dilated"].append(dilated)
         out["acc"].append(acc)
         out["overlay"].append(overlay)
-        if degrade:
+        if degrade == "colour_only":
+            out["compressed"].append(colour_round_trip_only(frame))
+        elif degrade:
             if literal_blocks:
                 comp = literal_degrade_fd(frame, acc, block_size, quantization_level)
             else:
@@ -140,7 +149,9 @@ def window_loop(frames, window_size=5, alpha_fraction=0.2, morph_kernel=2, morph
         out["voted"].append(voted)
         out["mask"].append(m)
         out["overlay"].append(overlay)
-        if degrade:
+        if degrade == "colour_only":
+            out["compressed"].append(colour_round_trip_only(frame))
+        elif degrade:
             if literal_blocks:
                 comp = literal_degrade_fd(frame, m, block_size, quantization_level)
             else:
