@@ -173,7 +173,7 @@ def cpu_warm_state(clip, mode, n_warm=12):
     """Loop state after frames 1..n_warm (past the EMA / window warm-up, so blocks are static as in steady state);
     computed with the vectorised oracle path, which the tests pin to the literal one."""
     from oracle import loops
-    frames = [clip[t] for t in range(n_warm + 1)]
+    frames = [clip[t % len(clip)] for t in range(n_warm + 1)]
     if mode == "window":
         kw = dict(LOOP); kw["literal_blocks"] = False
         r = loops.window_loop(frames, degrade=False, **kw)

@@ -95,7 +95,7 @@ static bool make_prim(int shape, int k, bool erode, MorphPrim& p) {
             p.small_rows[p.dy[i] + 1] = (int8_t)(1 | (p.lo[i] == -1 ? 2 : 0) | (p.hi[i] == 1 ? 4 : 0));
     // kernels specialised at compile time (k_mask.cuh: rect_pass<K>, small_pass<FU,FM,FD>)
     p.kind = 0;
-    if (sep && shape == DVC_SHAPE_RECT && (k & 1) && k >= 3 && k <= 15) p.kind = (int16_t)(100 + k);
+    if (sep && shape == DVC_SHAPE_RECT && (k & 1) && k >= 3) p.kind = (int16_t)(100 + k);      // every odd k up to MORPH_MAX_K
     if (small && p.small_rows[0] == 1 && p.small_rows[1] == 3 && p.small_rows[2] == 0) p.kind = 1;
     if (small && p.small_rows[0] == 1 && p.small_rows[1] == 7 && p.small_rows[2] == 1) p.kind = 2;
     return true;
@@ -103,11 +103,27 @@ static bool make_prim(int shape, int k, bool erode, MorphPrim& p) {
 
 static bool chain_push(MorphChain& ch, int op, int shape, int k) {
     auto push = [&](bool erode) {
+        // Two consecutive odd rectangles of the same polarity are one rectangle: the Minkowski sum (k1 + k2 - 1), which is
+        // exact with cv2's "ignore what is outside the image" borders because the intermediate pixel of any two-step path
+        // lies between its end points, inside the image.  CLOSE, OPEN, DILATE with one k x k element (BASELINE config 3)
+        // is D E E D D = D(k) E(2k-1) D(2k-1): three passes instead of five, and a pass costs the same for any k.
+        if (ch.n > 0 && shape == DVC_SHAPE_RECT && (k & 1) && k >= 3) {
+            MorphPrim& q = ch.p[ch.n - 1];
+            const int kq = q.kind - 100;
+            if (q.kind >= 103 && (bool)q.erode == erode && kq + k - 1 <= MORPH_MAX_K) {
+                if (!make_prim(DVC_SHAPE_RECT, kq + k - 1, erode, q)) return false;
+                ch.halo_top += k / 2;
+                ch.halo_bot += k / 2;
+                ch.pad = std::max<int>(ch.pad, (kq + k - 1) / 2);
+                return true;
+            }
+        }
         if (ch.n >= MORPH_MAX_PRIMS) return false;
         MorphPrim& p = ch.p[ch.n];
         if (!make_prim(shape, k, erode, p)) return false;
         ch.halo_top += -std::min<int>(p.dy[0], 0);
         ch.halo_bot += std::max<int>(p.dy[p.nrows - 1], 0);
+        if (p.kind >= 100) ch.pad = std::max<int>(ch.pad, (p.kind - 100) / 2);       // rect_pass<K> reads K / 2 rows beyond its run
         ++ch.n;
         return true;
     };
@@ -180,7 +196,8 @@ static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, 
         int dev = 0, lim = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        CU(cudaFuncSetAttribute(k_morph_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CU(cudaFuncSetAttribute(k_morph_chain<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CU(cudaFuncSetAttribute(k_morph_chain<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         g_morph_smem_limit = lim;
         once.commit();
     }
@@ -190,21 +207,27 @@ static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, 
             if (ch.p[i].lo[k] > 0 || ch.p[i].hi[k] < 0)
                 return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "structuring element row that does not span its anchor column");
     if (wpr > 256) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "frames wider than 8192 pixels are not supported by the morphology kernel");
-    // Band height: ~36 KB of shared memory per CTA (two planes) keeps ~6 CTAs resident per SM; chains with a
-    // large halo get bands at least twice the halo so the redundant rows stay under a third.
+    // Band height: ~36 KB of shared memory per CTA (two planes) keeps ~6 CTAs of 256 threads resident per SM.  Chains with a
+    // large halo (BASELINE config 3: five 15x15 primitives = 35 rows on each side) would recompute most of such a band, so
+    // they take the whole shared memory of an SM for one band (halo rows under ~40 % of the staged rows) and make up the
+    // occupancy with 1024 threads in that one CTA.
     const size_t row_bytes = 2 * (size_t)wpr * 4;
     const size_t limit = (size_t)g_morph_smem_limit - 64;
     static const int target_kb = std::max(4, measure_env("DVC_MORPH_SMEM_KB", 36));
+    const int pad = 2 * ch.pad;                          // zero rows above and below each staged plane (not counted in the target)
     int band = (int)((size_t)target_kb * 1024 / row_bytes) - halo;
-    band = std::max(band, std::max(16, 2 * halo));
-    band = std::min<int>(band, (int)(limit / row_bytes) - halo);
+    if (band < 2 * halo) band = (int)(limit / row_bytes) - halo - pad;
+    band = std::max(band, 16);
+    band = std::min<int>(band, (int)(limit / row_bytes) - halo - pad);
     if (band < 1) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "morphology chain halo %d rows x %d words does not fit in shared memory", halo, wpr);
     band = std::min(band, H);
     const int nbands = (H + band - 1) / band;
     band = (H + nbands - 1) / nbands;
-    const size_t smem = 2 * (size_t)(band + halo) * wpr * 4 + 16;
+    const size_t smem = 2 * (size_t)(band + halo + pad) * wpr * 4 + 16;
+    const int threads = smem > 110 * 1024 ? 1024 : smem > 72 * 1024 ? 512 : 256;     // CTAs per SM: 1, 2, 3+
     dim3 grid(nbands, n);
-    k_morph_chain<<<grid, 256, smem, st>>>(src, dst, H, W, wpr, band, ch);
+    if (threads == 256) k_morph_chain<256><<<grid, 256, smem, st>>>(src, dst, H, W, wpr, band, ch);
+    else k_morph_chain<1024><<<grid, threads, smem, st>>>(src, dst, H, W, wpr, band, ch);
     CHECK_LAUNCH();
     return DVC_OK;
 }
@@ -649,7 +672,7 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     }
     CU(cudaMalloc(&h->counters_dev, sizeof(Counters)));
     CU(cudaMemset(h->counters_dev, 0, sizeof(Counters)));
-    h->chain.n = 0; h->chain.halo_top = h->chain.halo_bot = 0;
+    h->chain.n = 0; h->chain.pad = 0; h->chain.halo_top = h->chain.halo_bot = 0;
     if (cfg->mode == DVC_MODE_FD) {
         CU(cudaMalloc(&h->acc, h->plane_bytes * S));
         CU(cudaMemset(h->acc, 0, h->plane_bytes * S));
@@ -1230,7 +1253,7 @@ extern "C" int dvc_morph_u8(const uint8_t* src, uint8_t* dst, int32_t n, int32_t
     if (op < DVC_MORPH_ERODE || op > DVC_MORPH_CLOSE || (shape != DVC_SHAPE_RECT && shape != DVC_SHAPE_ELLIPSE))
         return set_err(nullptr, DVC_ERR_INVALID, "dvc_morph_u8: bad op/shape");
     MorphChain ch;
-    ch.n = 0; ch.halo_top = ch.halo_bot = 0;
+    ch.n = 0; ch.pad = 0; ch.halo_top = ch.halo_bot = 0;
     if (!chain_push(ch, op, shape, k)) return set_err(nullptr, DVC_ERR_UNSUPPORTED, "dvc_morph_u8: kernel size %d outside 1..%d", k, MORPH_MAX_K);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t pw = (size_t)H * words_per_row(W);

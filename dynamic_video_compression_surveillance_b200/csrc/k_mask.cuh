@@ -187,6 +187,7 @@ struct MorphPrim {
 };
 struct MorphChain {
     int n;
+    int pad;                           // zero rows kept above / below the staged planes: the largest reach of a rect_pass<K> primitive
     int halo_top, halo_bot;            // rows of input needed above / below an output band
     MorphPrim p[MORPH_MAX_PRIMS];
 };
@@ -258,41 +259,68 @@ DEVI uint32_t hrun_or_c(uint32_t prev, uint32_t cur, uint32_t next) {
     return res;
 }
 
-// k x k rectangle, k odd (anchor in the middle): horizontal pass A -> B, vertical pass B -> A
+// OR over the symmetric bit window [i - R, i + R] (K = 2R + 1 <= 33) of word x with neighbours p (lower bits) and n: the
+// 64-bit window T = (n:x:p) >> (32 - R) puts global bit i - R at bit i, then a one-sided log-doubling OR of width K leaves
+// the answer in the low word (the high word only ever needs its low K - 1 bits).
+template <int K>
+DEVI uint32_t hwin_or(uint32_t p, uint32_t x, uint32_t n) {
+    constexpr int R = K / 2;
+    uint32_t lo = __funnelshift_r(p, x, 32 - R), hi = __funnelshift_r(x, n, 32 - R);
+    int c = 1;
+#pragma unroll
+    for (int s = 1; 2 * s <= K; s *= 2) { lo |= __funnelshift_r(lo, hi, s); hi |= hi >> s; c = 2 * s; }
+    if (K > c) lo |= __funnelshift_r(lo, hi, K - c);
+    return lo;
+}
+
+// MorphChain::pad rows of padding above and below each staged plane (zero = "ignored" in the dilation domain) let the
+// vertical passes read beyond the band without range checks.
+
+// k x k rectangle, k odd (anchor in the middle): horizontal pass A -> B, vertical pass B -> A.
+// B holds dilation-domain values; its rows outside the image (and the padding) stay zero for the whole kernel, so the
+// vertical pass needs no range checks.
 template <int K>
 DEVI void rect_pass(uint32_t* A, uint32_t* B, const BandCtx& c, uint32_t flip) {
     constexpr int R = K / 2;
+    const int n = c.rb - c.ra, wpr = c.wpr;
     {
-        const uint32_t* row = A + c.ra * c.wpr;
-        uint32_t* out = B + c.ra * c.wpr + c.j;
-        for (int r = c.ra; r < c.rb; ++r, row += c.wpr, out += c.wpr) {
-            const uint32_t p = (row[c.jp] ^ flip) & c.pm, x = (row[c.j] ^ flip) & c.vm, n = (row[c.jn] ^ flip) & c.nm;
-            *out = hrun_or_c<R + 1, R + 1>(p, x, n) & c.vm;
+        const uint32_t* row = A + c.ra * wpr;
+        uint32_t* out = B + c.ra * wpr + c.j;
+        for (int i = 0; i < n; ++i, row += wpr, out += wpr) {
+            const uint32_t p = (row[c.jp] ^ flip) & c.pm, x = (row[c.j] ^ flip) & c.vm, nx = (row[c.jn] ^ flip) & c.nm;
+            *out = hwin_or<K>(p, x, nx) & c.vm;
         }
     }
     __syncthreads();
-    // vertical: the thread walks its rows with the last K row words in registers (slot = row offset mod K, all indices
-    // compile-time after unrolling by K): one shared-memory load per output instead of K
-    {
-        uint32_t w[K];
+    // vertical: van Herk / Gil-Werman on the thread's run of rows.  Rows are cut into blocks of K starting at ra - R; the
+    // window of output ra + m K + u is the suffix of block m from offset u OR the prefix of block m + 1 up to offset u - 1.
+    // Per output: one shared-memory load, one OR into the running prefix, one OR for the suffix scan, one OR to combine --
+    // independent of K.
+    if (n > 0) {
+        const uint32_t* q = B + (c.ra - R) * wpr + c.j;         // next row to load
+        uint32_t* o = A + c.ra * wpr + c.j;                     // next output row
+        uint32_t sfx[K];                                        // suffix ORs of the current block (the only per-row state kept)
 #pragma unroll
-        for (int d = 0; d < K - 1; ++d) {                      // rows ra-R .. ra+R-1 -> slots 0 .. K-2
-            const int rr = c.ra - R + d;
-            w[d] = (rr >= c.r_lo && rr < c.r_hi) ? B[rr * c.wpr + c.j] : 0u;
-        }
-        w[K - 1] = 0u;
-        for (int r0 = c.ra; r0 < c.rb; r0 += K) {
+        for (int d = 0; d < K; ++d, q += wpr) sfx[d] = *q;
 #pragma unroll
-            for (int u = 0; u < K; ++u) {
-                const int r = r0 + u;
-                if (r < c.rb) {
-                    const int rn = r + R;                      // the row entering the window: slot (u + K - 1) % K
-                    w[(u + K - 1) % K] = (rn >= c.r_lo && rn < c.r_hi) ? B[rn * c.wpr + c.j] : 0u;
-                    uint32_t acc = 0;
+        for (int d = K - 2; d >= 0; --d) sfx[d] |= sfx[d + 1];
+        for (int left = n; left > 0; left -= K) {
+            uint32_t pfx = 0u;
+            *o = (sfx[0] ^ flip) & c.vm;
+            o += wpr;
+            const uint32_t* qb = q;                             // first row of the next block
 #pragma unroll
-                    for (int d = 0; d < K; ++d) acc |= w[d];
-                    A[r * c.wpr + c.j] = (acc ^ flip) & c.vm;
+            for (int u = 1; u < K; ++u, q += wpr, o += wpr) {
+                if (u < left) {
+                    pfx |= *q;
+                    *o = ((sfx[u] | pfx) ^ flip) & c.vm;
                 }
+            }
+            if (left > K) {                                     // suffix scan of the next block: its rows are read once more
+                sfx[K - 1] = *q;
+                q += wpr;
+#pragma unroll
+                for (int d = K - 2; d >= 0; --d) sfx[d] = qb[d * wpr] | sfx[d + 1];
             }
         }
     }
@@ -332,14 +360,16 @@ DEVI void small_pass(const uint32_t* A, uint32_t* B, const BandCtx& c, uint32_t 
 // Erosion runs as NOT dilate NOT: the complement is folded into the first read and the last write of the
 // primitive.  Rows outside the image and bits beyond W are 'ignored' pixels: they read as 0 in the dilation
 // domain of either polarity, so only rows [r_lo, r_hi) of the staged band are ever touched.
-__global__ void __launch_bounds__(256)
+template <int MAXT>      // 256: several CTAs per SM (small halos); 1024: one CTA owns the SM's shared memory (large halos)
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? 4 : 1)
 k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int H, int W, int wpr, int band_rows,
               MorphChain ch) {
     extern __shared__ __align__(128) uint32_t smem[];
     const int ext_rows = band_rows + ch.halo_top + ch.halo_bot;
-    uint32_t* A = smem;
-    uint32_t* B = smem + (size_t)ext_rows * wpr;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)ext_rows * wpr);
+    const size_t plane = (size_t)(ext_rows + 2 * ch.pad) * wpr;          // words per staged plane, padding included
+    uint32_t* A = smem + (size_t)ch.pad * wpr;                           // row 0 of the band
+    uint32_t* B = A + plane;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * plane);
     const int y0 = blockIdx.x * band_rows;                    // first output row of this band
     const int ey0 = y0 - ch.halo_top;                         // image row of ext row 0
     const size_t plane_words = (size_t)H * wpr;
@@ -359,6 +389,16 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(A + (size_t)r_lo * wpr)), "l"(sp + (size_t)(ey0 + r_lo) * wpr), "r"(bytes),
                        "r"(smem_u32(bar)) : "memory");
+    }
+    // rows of either plane that no pass ever writes -- the padding and the band rows outside the image -- are zeroed once
+    // (they are disjoint from the rows the bulk copy fills, so this overlaps the copy)
+    {
+        const int top = (ch.pad + r_lo) * wpr, bot0 = (ch.pad + r_hi) * wpr, total = (int)plane;
+        for (int pl = 0; pl < 2; ++pl) {
+            uint32_t* base = smem + pl * plane;
+            for (int i = tid; i < top; i += nt) base[i] = 0u;
+            for (int i = bot0 + tid; i < total; i += nt) base[i] = 0u;
+        }
     }
     // thread -> (row group, word column)
     const int groups = nt / wpr;                              // >= 1 (host guarantees wpr <= blockDim)
@@ -395,6 +435,15 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
                 case 111: rect_pass<11>(A, B, cx, flip); swap = false; break;
                 case 113: rect_pass<13>(A, B, cx, flip); swap = false; break;
                 case 115: rect_pass<15>(A, B, cx, flip); swap = false; break;
+                case 117: rect_pass<17>(A, B, cx, flip); swap = false; break;
+                case 119: rect_pass<19>(A, B, cx, flip); swap = false; break;
+                case 121: rect_pass<21>(A, B, cx, flip); swap = false; break;
+                case 123: rect_pass<23>(A, B, cx, flip); swap = false; break;
+                case 125: rect_pass<25>(A, B, cx, flip); swap = false; break;
+                case 127: rect_pass<27>(A, B, cx, flip); swap = false; break;
+                case 129: rect_pass<29>(A, B, cx, flip); swap = false; break;
+                case 131: rect_pass<31>(A, B, cx, flip); swap = false; break;
+                case 133: rect_pass<33>(A, B, cx, flip); swap = false; break;
                 case 1: small_pass<1, 3, 0>(A, B, cx, flip); break;     // MORPH_ELLIPSE 2x2
                 case 2: small_pass<1, 7, 1>(A, B, cx, flip); break;     // MORPH_ELLIPSE 3x3 (a cross)
                 default: break;
