@@ -676,7 +676,6 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     if (cfg->mode == DVC_MODE_FD) {
         CU(cudaMalloc(&h->acc, h->plane_bytes * S));
         CU(cudaMemset(h->acc, 0, h->plane_bytes * S));
-        CU(cudaMalloc(&h->blurred, h->plane_bytes * T));
         int rc = ccl_scratch_alloc(h->err, h->ccl, std::min(T, 64), h->H, h->W);
         if (rc) return rc;
         if (cfg->kernel_size > 0 && !chain_push(h->chain, DVC_MORPH_DILATE, DVC_SHAPE_RECT, cfg->kernel_size))
@@ -948,21 +947,17 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
             if (rc) return rc;
         }
     } else {
-        dim3 gb((W + BL_TW - 1) / BL_TW, (H + BL_TH - 1) / BL_TH, ST);
+        // gray -> blur5 -> absdiff -> threshold fused and walking the frames of a segment: the blurred planes stay in registers
+        const int tiles = (wpr / 4) * ((H + FF_TH - 1) / FF_TH);
+        const int want_segs = std::max(1, (1500 + tiles * S - 1) / (tiles * S));          // enough CTAs for a few waves
+        const int seg = std::min(32, std::max(4, (T + want_segs - 1) / want_segs));
+        const int nseg = (T + seg - 1) / seg;
+        dim3 gf(wpr / 4, (H + FF_TH - 1) / FF_TH, S * nseg);
         { ProfScope ps(h, DVC_PROF_FRONT, 1, st);
-        if (h->aligned) k_gray_blur5<true><<<gb, 256, 0, st>>>(frames, h->blurred, H, W);
-        else k_gray_blur5<false><<<gb, 256, 0, st>>>(frames, h->blurred, H, W);
+        if (h->aligned) k_fd_front<true><<<gf, 256, 0, st>>>(frames, T, H, W, h->prev_gray[h->cur], h->prev_gray[h->cur ^ 1], bits_a, wpr, thr, seg, nseg);
+        else k_fd_front<false><<<gf, 256, 0, st>>>(frames, T, H, W, h->prev_gray[h->cur], h->prev_gray[h->cur ^ 1], bits_a, wpr, thr, seg, nseg);
         }
         CHECK_LAUNCH();
-        dim3 gd(g16, T, S);
-        { ProfScope ps(h, DVC_PROF_DIFF, 1, st);
-        if (h->aligned) k_diff_thresh_planes<true><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, bits_a, wpr, thr);
-        else k_diff_thresh_planes<false><<<gd, 256, 0, st>>>(h->blurred, h->prev_gray[h->cur], H, W, bits_a, wpr, thr);
-        }
-        CHECK_LAUNCH();
-        for (int sidx = 0; sidx < S; ++sidx)
-            CU(cudaMemcpyAsync(h->prev_gray[h->cur ^ 1] + (size_t)sidx * h->plane_bytes,
-                               h->blurred + ((size_t)sidx * T + (T - 1)) * h->plane_bytes, h->plane_bytes, cudaMemcpyDeviceToDevice, st));
         h->cur ^= 1;
         int rc;
         { ProfScope ps(h, DVC_PROF_CCL, 7 * ((ST + h->ccl.frames - 1) / h->ccl.frames), st);

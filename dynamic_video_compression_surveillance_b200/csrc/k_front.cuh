@@ -267,6 +267,190 @@ k_diff_thresh_planes(const uint8_t* __restrict__ planes, const uint8_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 (fd mode), fused and time-walking: BGR -> gray -> GaussianBlur(5,5),0 -> absdiff(previous blurred frame) ->
+// threshold -> raw-mask bit-plane (frame_differencing.py:92-97), one CTA per 128 x 64 tile walking a segment of frames.
+// The blurred frames never touch HBM: each thread keeps the previous blurred values of its 8 px x 4 rows in registers, so
+// the kernel reads 3 B/px and writes 1/8 B/px (k_gray_blur5 + k_diff_thresh_planes moved 3 + 1 + 2 B/px); only the last
+// blurred frame of the batch is stored (it is the stream's prev_gray, :133).  The thread -> task mapping and every
+// reflected source offset are computed once, outside the frame loop.
+// grid (tiles_x, tiles_y, S * nseg): z = stream * nseg + segment; a segment that does not start the batch first blurs
+// the frame before it (1 / seg_len extra work) instead of waiting for its neighbour.
+// ------------------------------------------------------------------------------------------------
+constexpr int FF_TW = 128, FF_TH = 64, FF_PAD = 16, FF_GP = FF_TW + 2 * FF_PAD, FF_ROWS = FF_TH + 4;
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256, 5)
+k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_t* __restrict__ prev_gray_in,
+           uint8_t* __restrict__ prev_gray_out, uint32_t* __restrict__ bits_out, int wpr, uint32_t thr, int seg_len, int nseg) {
+    __shared__ __align__(16) uint8_t sg[FF_ROWS * FF_GP];            // gray, column c <-> x = x0 - FF_PAD + c
+    __shared__ __align__(16) uint2 sh[FF_ROWS * (FF_TW / 4)];         // horizontal pass: (even, odd) 16-bit lane pairs per 4 px
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * FF_TW, y0 = blockIdx.y * FF_TH;
+    const int stream = blockIdx.z / nseg, seg = blockIdx.z - stream * nseg;
+    const int t0 = seg * seg_len, t1 = min(T, t0 + seg_len);
+    const size_t frame_bytes = (size_t)H * W * 3, plane_bytes = (size_t)H * W, plane_words = (size_t)H * wpr;
+    frames += (size_t)stream * T * frame_bytes;
+    bits_out += (size_t)stream * T * plane_words;
+    prev_gray_in += (size_t)stream * plane_bytes;
+    if (prev_gray_out) prev_gray_out += (size_t)stream * plane_bytes;
+    const int tw = min(FF_TW, W - x0);                                // valid columns of this tile (> 0 by construction)
+
+    // ---- per-thread task tables (frame independent) ----
+    // gray: 68 rows x 8 groups of 16 px = 544 tasks, three rounds
+    int g_src[3], g_dst[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int task = tid + 256 * i, r = task >> 3, g = task & 7, x = x0 + g * 16;
+        g_src[i] = -1; g_dst[i] = 0;
+        if (task < FF_ROWS * 8 && x < W) {
+            g_src[i] = (reflect101(y0 - 2 + r, H) * W + x) * 3;       // frames are < 2^31 bytes (checked on the host)
+            g_dst[i] = r * FF_GP + FF_PAD + g * 16;
+        }
+    }
+    // halo columns: 68 rows x 4 = 272 tasks (left x0-2, x0-1; right: the two columns after the tile's last valid one)
+    int h_src[2], h_dst[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int task = tid + 256 * i;
+        h_src[i] = -2; h_dst[i] = 0;
+        if (task < FF_ROWS * 4) {
+            const int r = task >> 2, k = task & 3;
+            const int dx = k < 2 ? k - 2 : tw + (k - 2);
+            const int xx = reflect101(x0 + dx, W);
+            h_dst[i] = r * FF_GP + FF_PAD + dx;
+            if (xx >= x0 && xx < x0 + tw) h_src[i] = -(r * FF_GP + FF_PAD + (xx - x0)) - 16;      // < -2: copy inside the tile
+            else h_src[i] = (reflect101(y0 - 2 + r, H) * W + xx) * 3;
+        }
+    }
+    // vertical / output: thread = 8 px x 4 rows
+    const int cgp = tid & 15, rg = tid >> 4;
+    const int ox = x0 + cgp * 8, oy = y0 + rg * 4;
+    const int lane = tid & 31;
+    uint32_t pv[4][2];                                                // previous blurred values of this thread's pixels
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pv[i][0] = pv[i][1] = 0u; }
+    if (t0 == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int y = oy + i;
+            if (y < H && ox < W) {
+                const uint8_t* q = prev_gray_in + (size_t)y * W + ox;
+                if (ALIGNED) { const uint2 v = *reinterpret_cast<const uint2*>(q); pv[i][0] = v.x; pv[i][1] = v.y; }
+                else for (int b = 0; b < min(8, W - ox); ++b) pv[i][b >> 2] |= (uint32_t)q[b] << ((b & 3) * 8);
+            }
+        }
+    }
+    // words of the bit-plane: lanes 4k..4k+3 hold the four bytes of one 32-bit word; after the 4 x 4 byte transpose below
+    // lane (lane & 3) = q owns the word of row q
+    const int wj = (x0 >> 5) + (cgp >> 2);
+    const uint32_t wvm = valid_mask(wj, W);
+
+    for (int t = (t0 == 0 ? 0 : t0 - 1); t < t1; ++t) {
+        const uint8_t* fr = frames + (size_t)t * frame_bytes;
+        const bool emit = t >= t0;
+        // phase 1a: interior gray
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (g_src[i] >= 0) {
+                uint32_t w[12], gg[4];
+                const uint8_t* row = fr + g_src[i];
+                if constexpr (ALIGNED) {       // W % 16 == 0: every 16-px group inside the image is whole and 16-byte aligned
+                    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(row)), q1 = __ldg(reinterpret_cast<const uint4*>(row) + 1),
+                                q2 = __ldg(reinterpret_cast<const uint4*>(row) + 2);
+                    w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w; w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+                    w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
+                } else {
+                    const int x = x0 + ((tid + 256 * i) & 7) * 16;
+                    load_bgr16_generic(row - (size_t)x * 3, x, W, w);
+                }
+                gray16_dp2a(w, gg);
+                *reinterpret_cast<uint4*>(&sg[g_dst[i]]) = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+            }
+        }
+        __syncthreads();
+        // phase 1b: halo columns
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (h_src[i] != -2) {
+                uint8_t v;
+                if (h_src[i] < -2) v = sg[-(h_src[i] + 16)];
+                else { const uint8_t* p = fr + h_src[i]; v = (uint8_t)gray_of(p[0], p[1], p[2]); }
+                sg[h_dst[i]] = v;
+            }
+        }
+        __syncthreads();
+        // phase 2: horizontal 5 taps on 16-bit lanes (see k_gray_blur5): rows (tid >> 5) + 8 i, 4-px group tid & 31
+        {
+            const int cg = tid & 31;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const int r = (tid >> 5) + 8 * i;
+                if (r < FF_ROWS) {
+                    const uint32_t* g = reinterpret_cast<const uint32_t*>(&sg[r * FF_GP + FF_PAD]) + cg;
+                    const uint32_t prev = g[-1], cur = g[0], next = g[1];
+                    const uint32_t a = __funnelshift_r(prev, cur, 16), b = __funnelshift_r(prev, cur, 24);
+                    const uint32_t d = __funnelshift_r(cur, next, 8), e = __funnelshift_r(cur, next, 16);
+                    uint2 h;
+                    {
+                        const uint32_t ae = __byte_perm(a, 0u, 0x4240u) + __byte_perm(e, 0u, 0x4240u);
+                        const uint32_t bd = __byte_perm(b, 0u, 0x4240u) + __byte_perm(d, 0u, 0x4240u);
+                        h.x = ae + 4u * bd + 6u * __byte_perm(cur, 0u, 0x4240u);
+                    }
+                    {
+                        const uint32_t ae = __byte_perm(a, 0u, 0x4341u) + __byte_perm(e, 0u, 0x4341u);
+                        const uint32_t bd = __byte_perm(b, 0u, 0x4341u) + __byte_perm(d, 0u, 0x4341u);
+                        h.y = ae + 4u * bd + 6u * __byte_perm(cur, 0u, 0x4341u);
+                    }
+                    sh[r * (FF_TW / 4) + cg] = h;
+                }
+            }
+        }
+        __syncthreads();
+        // phase 3: vertical 5 taps + rounding for 8 px x 4 rows, absdiff + threshold against the previous blurred values
+        {
+            const uint4* col = reinterpret_cast<const uint4*>(sh) + (rg * 4) * (FF_TW / 8) + cgp;
+            uint4 w0 = col[0], w1 = col[FF_TW / 8], w2 = col[2 * (FF_TW / 8)], w3 = col[3 * (FF_TW / 8)];
+            uint32_t rows_bits = 0;                                   // byte i = the 8 mask bits of row i
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 w4 = col[(4 + i) * (FF_TW / 8)];
+                const uint32_t ve0 = (w0.x + w4.x) + 4u * (w1.x + w3.x) + 6u * w2.x + 0x00800080u;
+                const uint32_t vo0 = (w0.y + w4.y) + 4u * (w1.y + w3.y) + 6u * w2.y + 0x00800080u;
+                const uint32_t ve1 = (w0.z + w4.z) + 4u * (w1.z + w3.z) + 6u * w2.z + 0x00800080u;
+                const uint32_t vo1 = (w0.w + w4.w) + 4u * (w1.w + w3.w) + 6u * w2.w + 0x00800080u;
+                const uint32_t o0 = ((ve0 >> 8) & 0x00ff00ffu) | (vo0 & 0xff00ff00u);
+                const uint32_t o1 = ((ve1 >> 8) & 0x00ff00ffu) | (vo1 & 0xff00ff00u);
+                if (emit) rows_bits |= (diff_gt_bits4(o0, pv[i][0], thr) | (diff_gt_bits4(o1, pv[i][1], thr) << 4)) << (8 * i);
+                pv[i][0] = o0; pv[i][1] = o1;
+                w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+            }
+            if (emit) {
+                // 4 x 4 byte transpose over lanes 4k..4k+3: lane q ends with the 32-bit plane word of row q
+                const uint32_t p1 = __shfl_xor_sync(0xffffffffu, rows_bits, 1);
+                const uint32_t a1 = (lane & 1) ? __byte_perm(rows_bits, p1, 0x3715u) : __byte_perm(rows_bits, p1, 0x6240u);
+                const uint32_t p2 = __shfl_xor_sync(0xffffffffu, a1, 2);
+                const uint32_t word = (lane & 2) ? __byte_perm(a1, p2, 0x3276u) : __byte_perm(a1, p2, 0x5410u);
+                const int y = oy + (lane & 3);
+                if (y < H && wj < wpr) bits_out[(size_t)t * plane_words + (size_t)y * wpr + wj] = word & wvm;
+            }
+        }
+        // (the next frame's phase 1 writes sg, which nobody reads after the barrier above; its phase 2 writes sh only after
+        //  two more barriers, by which time every thread has left phase 3)
+    }
+    if (t1 == T && prev_gray_out) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int y = oy + i;
+            if (y < H && ox < W) {
+                uint8_t* q = prev_gray_out + (size_t)y * W + ox;
+                if (ALIGNED) *reinterpret_cast<uint2*>(q) = make_uint2(pv[i][0], pv[i][1]);
+                else for (int b = 0; b < min(8, W - ox); ++b) q[b] = (uint8_t)(pv[i][b >> 2] >> ((b & 3) * 8));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // u8 mask (0 / non-zero) <-> bit-plane, n images per launch (blockIdx.y).  One thread per 16 pixels: a 16-byte load,
 // SWAR byte tests, multiply-gather of the four flag bits per word, one 16-bit store (and the reverse).
 // ------------------------------------------------------------------------------------------------

@@ -43,7 +43,7 @@ DEVI uint32_t bs_ge(const uint32_t (&c)[CNT_BITS], uint32_t m) {   // per-lane c
 // slot0 = slot of frame f0 in the ring; all slot arithmetic is 32-bit with wrap-around compares
 __global__ void __launch_bounds__(256)
 k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int wpr, long long f0, int slot0, int T,
-              int K, MinCounts mc, uint32_t* __restrict__ voted, int seg_len) {
+              int K, const __grid_constant__ MinCounts mc, uint32_t* __restrict__ voted, int seg_len) {
     __shared__ uint8_t s_mc[32];
     if (threadIdx.x < 32) s_mc[threadIdx.x] = mc.v[threadIdx.x];
     __syncthreads();
