@@ -51,6 +51,7 @@ SYMBOLS = {
     "dvc_create": (C.c_int, [C.POINTER(DvcConfig), C.POINTER(_P)]),
     "dvc_destroy": (C.c_int, [_P]),
     "dvc_begin_stream": (C.c_int, [_P, _P]),
+    "dvc_begin_stream_frames": (C.c_int, [_P, _P]),
     "dvc_state_bytes": (C.c_size_t, [_P]),
     "dvc_get_state": (C.c_int, [_P, _P, C.c_size_t]),
     "dvc_set_state": (C.c_int, [_P, _P, C.c_size_t]),
@@ -73,6 +74,7 @@ SYMBOLS = {
     "dvc_resize_linear_u8": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "dvc_degrade_blend_u8": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
     "dvc_dct_blocks_f32": (C.c_int, [_P, _P, _L, _I, _I, _I, _P]),
+    "dvc_gaussian_blur_u8": (C.c_int, [_P, _P, _I, _I, _I, _I, _D, _P]),
 }
 
 _lib = None

@@ -343,6 +343,49 @@ static int launch_resize(char* ERRBUF, const uint8_t* src, uint8_t* dst, int n, 
     return DVC_OK;
 }
 
+// OpenCV's fixed-point Gaussian kernel for uint8 images (getGaussianKernelBitExact + getGaussianKernelFixedPoint_ED):
+// the double-precision kernel, normalised to sum 1, is rounded to 8 fractional bits from the ends towards the middle
+// with the rounding error carried along, so the taps sum to exactly 256.  sigma <= 0 uses cv2's rule (and its table of
+// small kernels for ksize <= 7).
+static bool gaussian_taps_fixed(int n, double sigma, GaussTaps& tp) {
+    if (n < 1 || n > 33 || !(n & 1)) return false;
+    tp.n = n;
+    double k[33];
+    static const double small_tab[4][7] = {{1.0}, {0.25, 0.5, 0.25}, {0.0625, 0.25, 0.375, 0.25, 0.0625},
+                                           {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125}};
+    if (sigma <= 0 && n <= 7) {
+        for (int i = 0; i < n; ++i) k[i] = small_tab[n >> 1][i];
+    } else {
+        const double sg = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
+        const double scale2x = -0.5 / (sg * sg), c = (n - 1) * 0.5;
+        double sum = 0;
+        for (int i = 0; i < n; ++i) { k[i] = std::exp(scale2x * (i - c) * (i - c)); sum += k[i]; }
+        for (int i = 0; i < n; ++i) k[i] /= sum;
+    }
+    double err = 0;
+    const int h = n / 2;
+    for (int i = 0; i < h; ++i) {
+        const double adj = k[i] * 256.0 + err;
+        const double v = std::nearbyint(adj);
+        err = adj - v;
+        tp.k[i] = tp.k[n - 1 - i] = (uint16_t)v;
+    }
+    tp.k[h] = (uint16_t)std::nearbyint(k[h] * 256.0 + err);
+    return true;
+}
+
+static int launch_gaussian(char* ERRBUF, const uint8_t* src, uint8_t* dst, uint16_t* tmp, int n, int H, int W, int ksize, double sigma,
+                           cudaStream_t st) {
+    GaussTaps tp;
+    if (!gaussian_taps_fixed(ksize, sigma, tp))
+        return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "GaussianBlur ksize %d: odd sizes 1..33 are implemented", ksize);
+    dim3 grid(cdiv((size_t)H * W, 256), n);
+    k_gauss_h<<<grid, 256, 0, st>>>(src, tmp, H, W, tp);
+    k_gauss_v<<<grid, 256, 0, st>>>(tmp, dst, H, W, tp);
+    CHECK_LAUNCH();
+    return DVC_OK;
+}
+
 // partial blocks at the right / bottom edge of frames whose size is not a multiple of the block size
 static int launch_degrade_edges(char* ERRBUF, const uint8_t* frames, const uint32_t* over127, const uint32_t* nonzero,
                                 uint8_t* compressed, uint8_t* overlay, int n, int H, int W, int bs, float q, int flavour,
@@ -912,10 +955,26 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
     const uint32_t* nonzero = nullptr;
     const unsigned g16 = cdiv((size_t)((W + 15) / 16) * H, 256);
     if (h->cfg.mode == DVC_MODE_WINDOW) {
-        const int nseg = (T + h->seg_len - 1) / h->seg_len;
-        dim3 g1(g16, nseg, S);
         uint8_t* pg_in = h->prev_gray[h->cur];
         uint8_t* pg_out = h->prev_gray[h->cur ^ 1];
+        const int K = h->cfg.window_size;
+        static const bool fuse_env = measure_env("DVC_FUSE_VOTE", 1) != 0;
+        if (h->aligned && K <= 8 && h->gray_impl == 2 && fuse_env) {
+            // K1 + K2 in one kernel (k_gray_diff_vote): long segments, each rebuilding its K - 1 frames of history
+            const int seg = std::max(K, 32), nsegf = (T + seg - 1) / seg;
+            dim3 gf(g16, nsegf, S);
+            ProfScope ps(h, DVC_PROF_FRONT, 1, st);
+#define DVC_VOTE_CASE(KK) case KK: k_gray_diff_vote<KK><<<gf, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, h->ring, wpr, h->ring_cap, h->n_masks, thr, seg, h->min_counts, bits_a); break;
+            switch (K) {
+                DVC_VOTE_CASE(1) DVC_VOTE_CASE(2) DVC_VOTE_CASE(3) DVC_VOTE_CASE(4)
+                DVC_VOTE_CASE(5) DVC_VOTE_CASE(6) DVC_VOTE_CASE(7) DVC_VOTE_CASE(8)
+            }
+#undef DVC_VOTE_CASE
+            CHECK_LAUNCH();
+            h->cur ^= 1;
+        } else {
+        const int nseg = (T + h->seg_len - 1) / h->seg_len;
+        dim3 g1(g16, nseg, S);
         { ProfScope ps(h, DVC_PROF_FRONT, 1, st);
         if (h->aligned && h->gray_impl == 2)
             k_gray_diff_thresh<true, 2><<<g1, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, nullptr, h->ring, wpr, h->ring_cap, h->n_masks, thr, h->seg_len);
@@ -933,6 +992,7 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         k_window_vote<<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, (int)(h->n_masks % h->ring_cap), T, h->cfg.window_size, h->min_counts, bits_a, h->seg_len);
         }
         CHECK_LAUNCH();
+        }
         const uint32_t* fin = bits_a;
         if (h->chain.n) {
             ProfScope ps(h, DVC_PROF_MORPH, 1, st);
@@ -1383,5 +1443,57 @@ extern "C" int dvc_dct_blocks_f32(const float* src, float* dst, int64_t n, int32
     if (!src || !dst) return set_err(nullptr, DVC_ERR_INVALID, "dvc_dct_blocks_f32: null pointer");
     k_dct_blocks<<<(unsigned)cdiv((size_t)n, 128), 128, 0, (cudaStream_t)stream>>>(src, dst, (long long)n, bh, bw, inverse);
     CHECK_LAUNCH();
+    return DVC_OK;
+}
+
+extern "C" int dvc_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, int32_t n, int32_t H, int32_t W, int32_t ksize, double sigma,
+                                    void* stream) {
+    char* ERRBUF = nullptr;
+    int rc = check_dims(n, H, W, "dvc_gaussian_blur_u8");
+    if (rc || n == 0) return rc;
+    if (!src || !dst) return set_err(nullptr, DVC_ERR_INVALID, "dvc_gaussian_blur_u8: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    ScopedAsyncBuf tmp(st);
+    CU(tmp.alloc((size_t)n * H * W * 2));
+    return launch_gaussian(nullptr, src, dst, (uint16_t*)tmp.p, n, H, W, ksize, sigma, st);
+}
+
+extern "C" int dvc_begin_stream_frames(dvc_handle* h, const uint8_t* first_frames_host) {
+    char* ERRBUF = h ? h->err : nullptr;
+    if (!h || !first_frames_host) return set_err(h ? h->err : nullptr, DVC_ERR_INVALID, "dvc_begin_stream_frames: null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(handle_join(h));
+    const int S = h->S, H = h->H, W = h->W;
+    cudaStream_t st = h->s_mask;
+    ScopedAsyncBuf src(st), bgr(st), gray(st), tmp(st);
+    CU(src.alloc((size_t)S * h->src_frame_bytes));
+    CU(cudaMemcpyAsync(src.p, first_frames_host, (size_t)S * h->src_frame_bytes, cudaMemcpyHostToDevice, st));
+    const uint8_t* frames = (const uint8_t*)src.p;
+    if (h->resizing) {                                   // frame_differencing.py:74
+        CU(bgr.alloc((size_t)S * h->frame_bytes));
+        int rc = launch_resize(h->err, (const uint8_t*)src.p, (uint8_t*)bgr.p, S, h->cfg.src_height, h->cfg.src_width, H, W, 3,
+                               resize_tables_view(h->resize_tables, H, W), st);
+        if (rc) return rc;
+        frames = (const uint8_t*)bgr.p;
+    }
+    dim3 g(cdiv((size_t)((W + 15) / 16) * H, 256), S);
+    uint8_t* pg = h->prev_gray[h->cur];
+    if (h->cfg.mode == DVC_MODE_FD) {                    // :75-77: gray, then GaussianBlur((25, 25), 30)
+        CU(gray.alloc((size_t)S * h->plane_bytes));
+        CU(tmp.alloc((size_t)S * h->plane_bytes * 2));
+        if (h->aligned) k_bgr2gray<true><<<g, 256, 0, st>>>(frames, (uint8_t*)gray.p, H, W);
+        else k_bgr2gray<false><<<g, 256, 0, st>>>(frames, (uint8_t*)gray.p, H, W);
+        CHECK_LAUNCH();
+        int rc = launch_gaussian(h->err, (const uint8_t*)gray.p, pg, (uint16_t*)tmp.p, S, H, W, 25, 30.0, st);
+        if (rc) return rc;
+    } else {                                             // motion_compression_opt.py:60: gray only
+        if (h->aligned) k_bgr2gray<true><<<g, 256, 0, st>>>(frames, pg, H, W);
+        else k_bgr2gray<false><<<g, 256, 0, st>>>(frames, pg, H, W);
+        CHECK_LAUNCH();
+    }
+    if (h->acc) CU(cudaMemsetAsync(h->acc, 0, h->plane_bytes * S, st));
+    if (h->ring) CU(cudaMemsetAsync(h->ring, 0, h->plane_words * 4 * h->ring_cap * S, st));
+    h->n_masks = 0;
+    CU(cudaStreamSynchronize(st));
     return DVC_OK;
 }

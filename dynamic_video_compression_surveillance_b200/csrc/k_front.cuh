@@ -451,6 +451,35 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
 }
 
 // ------------------------------------------------------------------------------------------------
+// cv2.GaussianBlur on uint8, any odd ksize <= 33 and sigma (frame_differencing.py:77: the first frame's (25,25), sigma 30
+// blur that seeds prev_gray).  OpenCV's uint8 path is fixed point: an 8.8 kernel made from the double-precision Gaussian
+// by error-diffusion rounding so that it sums to exactly 256 (host: gaussian_taps_fixed), a horizontal pass into 8.8
+// values, a vertical pass into 16.16, then (v + 2^15) >> 16, BORDER_REFLECT_101.  Runs once per stream: two plain passes.
+// ------------------------------------------------------------------------------------------------
+struct GaussTaps { int n; uint16_t k[33]; };
+
+__global__ void __launch_bounds__(256)
+k_gauss_h(const uint8_t* __restrict__ src, uint16_t* __restrict__ tmp, int H, int W, const __grid_constant__ GaussTaps tp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)H * W) return;
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W), r = tp.n >> 1;
+    const uint8_t* row = src + (size_t)blockIdx.y * H * W + (size_t)y * W;
+    uint32_t acc = 0;
+    for (int j = 0; j < tp.n; ++j) acc += (uint32_t)tp.k[j] * row[reflect101(x - r + j, W)];
+    tmp[(size_t)blockIdx.y * H * W + i] = (uint16_t)acc;                 // <= 255 * 256
+}
+__global__ void __launch_bounds__(256)
+k_gauss_v(const uint16_t* __restrict__ tmp, uint8_t* __restrict__ dst, int H, int W, const __grid_constant__ GaussTaps tp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)H * W) return;
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W), r = tp.n >> 1;
+    const uint16_t* pl = tmp + (size_t)blockIdx.y * H * W;
+    uint32_t acc = 0;
+    for (int j = 0; j < tp.n; ++j) acc += (uint32_t)tp.k[j] * pl[(size_t)reflect101(y - r + j, H) * W + x];
+    dst[(size_t)blockIdx.y * H * W + i] = (uint8_t)min(255u, (acc + 32768u) >> 16);
+}
+
+// ------------------------------------------------------------------------------------------------
 // u8 mask (0 / non-zero) <-> bit-plane, n images per launch (blockIdx.y).  One thread per 16 pixels: a 16-byte load,
 // SWAR byte tests, multiply-gather of the four flag bits per word, one 16-bit store (and the reverse).
 // ------------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 //                   write of the final band
 #pragma once
 #include "common.cuh"
+#include "k_front.cuh"
 
 namespace dvc {
 
@@ -96,6 +97,103 @@ k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int
         }
         s_new = sn; s_old = so;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2 fused (window mode, window_size <= 8): the K1 thread that turns 16 pixels of a segment of frames into raw mask
+// bits also keeps their window count (bit-sliced, 4 bits per pixel in four registers) and the last K raw pieces (a 128-bit
+// shift register), so the vote costs a dozen ALU instructions per frame instead of a second kernel that re-reads the ring
+// (motion_compression_opt.py:84-86 on top of frame_differencing.py:92,96-97).  A segment that does not start the batch
+// rebuilds its K - 1 frames of history from the frames themselves (K extra frame reads per segment: segments are long);
+// the first segment reads the previous batch's raw planes from the ring.  The ring is still written: it is the stream's
+// mask_queue state (dvc_get_state) and the next batch's history.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+k_gray_diff_vote(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_t* __restrict__ prev_gray_in,
+                 uint8_t* __restrict__ gray_state_out, uint32_t* __restrict__ ring, int wpr, int ring_cap, long long f0,
+                 uint32_t thr, int seg_len, const __grid_constant__ MinCounts mc, uint32_t* __restrict__ voted) {
+    const int gpr = W >> 4;                                     // W % 16 == 0 (host guarantees)
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)gpr * H) return;
+    const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx << 4;
+    const int t0 = blockIdx.y * seg_len, t1 = min(T, t0 + seg_len);
+    const size_t frame_bytes = (size_t)H * W * 3, plane_bytes = (size_t)H * W, plane_words = (size_t)H * wpr;
+    const size_t row_off = (size_t)y * W * 3 + (size_t)x0 * 3, px_off = (size_t)y * W + x0;
+    {
+        const size_t s = blockIdx.z;
+        frames += s * T * frame_bytes;
+        prev_gray_in += s * plane_bytes;
+        if (gray_state_out) gray_state_out += s * plane_bytes;
+        ring += s * ring_cap * plane_words;
+        voted += s * T * plane_words;
+    }
+    uint16_t* const ring16 = reinterpret_cast<uint16_t*>(ring) + (size_t)y * wpr * 2 + gx;
+    uint16_t* const vote16 = reinterpret_cast<uint16_t*>(voted) + (size_t)y * wpr * 2 + gx;
+    auto gray_of_frame = [&](int t, uint32_t (&g)[4]) {
+        const uint8_t* fr = frames + (size_t)t * frame_bytes + row_off;
+        uint32_t w[12];
+        load16(fr, *reinterpret_cast<uint32_t(*)[4]>(&w[0]));
+        load16(fr + 16, *reinterpret_cast<uint32_t(*)[4]>(&w[4]));
+        load16(fr + 32, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
+        gray16_dp2a(w, g);
+    };
+    uint32_t hst[4] = {0u, 0u, 0u, 0u};                          // raw pieces, newest in the low half of hst[0]
+    uint32_t c[4] = {0u, 0u, 0u, 0u};                            // bit-sliced count of the window (<= 8)
+    auto push = [&](uint32_t b) {
+        hst[3] = __funnelshift_l(hst[2], hst[3], 16); hst[2] = __funnelshift_l(hst[1], hst[2], 16);
+        hst[1] = __funnelshift_l(hst[0], hst[1], 16); hst[0] = (hst[0] << 16) | b;
+    };
+    auto add = [&](uint32_t x) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const uint32_t tt = c[i] & x; c[i] ^= x; x = tt; }
+    };
+    auto sub = [&](uint32_t x) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const uint32_t tt = ~c[i] & x; c[i] ^= x; x = tt; }
+    };
+    const long long fs = f0 + t0;                               // stream index of the segment's first frame
+    int nin = (int)min((long long)(K - 1), fs);                 // raw masks in the window before frame t0
+    uint32_t pg[4];
+    if (t0 == 0) {
+        load16(prev_gray_in + px_off, pg);
+        for (int i = nin; i >= 1; --i) {                         // previous batch's planes, oldest first
+            const uint32_t b = ring16[(size_t)((f0 - i) % ring_cap) * plane_words * 2];
+            push(b); add(b);
+        }
+    } else {
+        gray_of_frame(t0 - nin - 1, pg);                         // t0 >= seg_len >= K: these frames are in this batch
+        for (int t = t0 - nin; t < t0; ++t) {
+            uint32_t g[4];
+            gray_of_frame(t, g);
+            uint32_t b = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { b |= diff_gt_bits4(g[q], pg[q], thr) << (4 * q); pg[q] = g[q]; }
+            push(b); add(b);
+        }
+    }
+    for (int t = t0; t < t1; ++t) {
+        uint32_t g[4];
+        gray_of_frame(t, g);
+        uint32_t b = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { b |= diff_gt_bits4(g[q], pg[q], thr) << (4 * q); pg[q] = g[q]; }
+        if (nin == K) sub((hst[(K - 1) >> 1] >> (((K - 1) & 1) * 16)) & 0xffffu);      // the piece pushed K frames ago leaves
+        else ++nin;
+        add(b);
+        push(b);
+        const uint32_t m = mc.v[nin - 1];
+        uint32_t ge = 0u;
+        if (m < 16u) {
+            ge = 0xffffu;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ge = ((m >> i) & 1u) ? (c[i] & ge) : (c[i] | ge);
+        }
+        const size_t slot = (size_t)((f0 + t) % ring_cap);
+        ring16[slot * plane_words * 2] = (uint16_t)b;
+        vote16[(size_t)t * plane_words * 2] = (uint16_t)ge;
+    }
+    if (t1 == T && gray_state_out) store16(gray_state_out + px_off, pg);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -70,7 +70,6 @@ def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int
     import threading
 
     w, h = size_wh
-    seed = cv2.GaussianBlur(cv2.cvtColor(cv2.resize(first_frame, (w, h)), cv2.COLOR_BGR2GRAY), (25, 25), 30)
     run = FdRun()
     n_sets = 3 if threaded else 1
     shape = (max_batch, h, w, 3)
@@ -150,7 +149,7 @@ def run_fd_stream(cap, first_frame, sinks, size_wh, params: dict, max_batch: int
                 pass
 
     with P.FramePipeline(w, h, "fd", max_batch=max_batch, device=device, src_size=(src_w, src_h), **params) as pipe:
-        pipe.begin_stream(seed)
+        pipe.begin_stream_frames(first_frame)     # resize + gray + (25, 25) sigma-30 blur on the GPU (frame_differencing.py:74-77)
         if not threaded:
             st = sets[0]
             while True:

@@ -112,6 +112,16 @@ class FramePipeline:
             raise ValueError(f"prev_gray must be {list(want)}")
         self._check(self._lib.dvc_begin_stream(self._h, g.ctypes.data))
 
+    def begin_stream_frames(self, first_frames: np.ndarray):
+        """Seed the stream(s) from the first decoded frame(s) [src_h, src_w, 3] ([S, ...] for a group): resize, BGR2GRAY and (fd
+        mode) the (25, 25), sigma 30 blur run on the GPU (frame_differencing.py:74-77)."""
+        f = np.ascontiguousarray(first_frames, dtype=np.uint8)
+        want = (self.src_height, self.src_width, 3)
+        want = want if self.n_streams == 1 else (self.n_streams,) + want
+        if f.shape != want and f.shape != (1,) + want:
+            raise ValueError(f"first_frames must be {list(want)}")
+        self._check(self._lib.dvc_begin_stream_frames(self._h, f.ctypes.data))
+
     def get_state(self) -> bytes:
         n = self._lib.dvc_state_bytes(self._h)
         buf = np.empty(n, np.uint8)
@@ -315,4 +325,13 @@ def dct_blocks(blocks: torch.Tensor, inverse: bool = False) -> torch.Tensor:
     out = torch.empty_like(blocks)
     _lib_call("dvc_dct_blocks_f32", blocks.data_ptr(), out.data_ptr(), blocks.shape[0], blocks.shape[1], blocks.shape[2],
               1 if inverse else 0, _stream_ptr(None))
+    return out
+
+
+def gaussian_blur(planes: torch.Tensor, ksize: int, sigma: float) -> torch.Tensor:
+    """cv2.GaussianBlur(img, (ksize, ksize), sigma) on uint8 planes [N,H,W] (frame_differencing.py:77,93)."""
+    _dev_u8(planes, "planes")
+    n, h, w = planes.shape
+    out = torch.empty_like(planes)
+    _lib_call("dvc_gaussian_blur_u8", planes.data_ptr(), out.data_ptr(), n, h, w, int(ksize), float(sigma), _stream_ptr(None))
     return out

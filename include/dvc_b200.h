@@ -112,6 +112,11 @@ int dvc_destroy(dvc_handle* h);
  * the (25,25),sigma=30 blur, which stays on the host; motion_compression_opt.py:60 in window mode) and
  * clear accumulated_mask / the mask window.  Synchronous. */
 int dvc_begin_stream(dvc_handle* h, const uint8_t* prev_gray_host);
+/* The same from the first FRAME(S) of the stream(s), HOST [S][src_h][src_w][3] BGR as decoded: the library does the
+ * reference's first-frame work on the GPU -- cv2.resize when cfg.src_width / src_height are set (frame_differencing.py:74),
+ * BGR2GRAY (:75) and, in FD mode, GaussianBlur((25, 25), 30) (:77; OpenCV's fixed-point Gaussian, bit for bit) -- and
+ * clears accumulated_mask / the mask window.  Synchronous. */
+int dvc_begin_stream_frames(dvc_handle* h, const uint8_t* first_frames_host);
 /* Chunk hand-off: serialise / restore prev_gray + EMA plane or mask window.
  * Query the size with dvc_state_bytes().  Synchronous, host buffers. */
 size_t dvc_state_bytes(const dvc_handle* h);
@@ -205,6 +210,10 @@ int dvc_degrade_blend_u8(const uint8_t* bgr_dev, const uint8_t* mask_dev, uint8_
                          uint8_t* overlay_dev, int32_t n, int32_t H, int32_t W, int32_t block_size,
                          float quantization_level, int32_t flavour, uint64_t* counters_dev, void* stream);
 
+/* cv2.GaussianBlur(src, (ksize, ksize), sigma) on n uint8 planes [H][W], default border (REFLECT_101), ksize odd <= 33:
+ * frame_differencing.py:77 ((25, 25), 30) and :93 ((5, 5), 0); OpenCV's 8.8 fixed-point kernel and rounding, bit for bit. */
+int dvc_gaussian_blur_u8(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n, int32_t H, int32_t W, int32_t ksize, double sigma,
+                         void* stream);
 /* cv2.dct / cv2.idct on n float32 blocks [n][bh][bw] (bh, bw in 1..8), frame_differencing.py:122,124 and
  * motion_compression_opt.py:165,167: the transform pair the degrade kernels apply, bit for bit (8 x 8 is cv2's
  * dedicated 2-D routine, every other shape rows-then-columns through the 1-D routine of each length). */

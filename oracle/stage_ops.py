@@ -107,6 +107,47 @@ def _gaussian_blur5_small(gray: np.ndarray) -> np.ndarray:
     return out.astype(np.uint8)
 
 
+_SMALL_GAUSS = {1: [1.0], 3: [0.25, 0.5, 0.25], 5: [0.0625, 0.25, 0.375, 0.25, 0.0625],
+                7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125]}
+
+
+def gaussian_kernel_fixed(ksize: int, sigma: float) -> np.ndarray:
+    """OpenCV's 8.8 fixed-point Gaussian kernel for uint8 images (getGaussianKernelBitExact +
+    getGaussianKernelFixedPoint_ED): the normalised double kernel rounded to 8 fractional bits from the ends towards the
+    middle with the rounding error carried along; the taps sum to exactly 256.  (25, 30) -> 10 10 10 10 10 10 10 11 10 11 ..."""
+    n = int(ksize)
+    if sigma <= 0 and n in _SMALL_GAUSS:
+        k = np.array(_SMALL_GAUSS[n], np.float64)
+    else:
+        sg = sigma if sigma > 0 else ((n - 1) * 0.5 - 1) * 0.3 + 0.8
+        c = (n - 1) * 0.5
+        k = np.exp((-0.5 / (sg * sg)) * (np.arange(n) - c) ** 2)
+        k = k / k.sum()
+    res = np.zeros(n, np.int64)
+    err = 0.0
+    for i in range(n // 2):
+        adj = k[i] * 256.0 + err
+        v = int(np.rint(adj))
+        err = adj - v
+        res[i] = res[n - 1 - i] = v
+    res[n // 2] = int(np.rint(k[n // 2] * 256.0 + err))
+    return res
+
+
+def gaussian_blur_fixed(gray: np.ndarray, ksize: int, sigma: float) -> np.ndarray:
+    """cv2.GaussianBlur(gray, (ksize, ksize), sigma) on uint8 (frame_differencing.py:77,93): separable 8.8 fixed point,
+    BORDER_REFLECT_101, (v + 2^15) >> 16."""
+    k = gaussian_kernel_fixed(ksize, sigma)
+    r = len(k) // 2
+    h, w = gray.shape
+    yi = np.array([_reflect101_index(i, h) for i in range(-r, h + r)])
+    xi = np.array([_reflect101_index(i, w) for i in range(-r, w + r)])
+    p = gray.astype(np.int64)[yi][:, xi]
+    hs = sum(int(c) * p[:, i:i + w] for i, c in enumerate(k))
+    vs = sum(int(c) * hs[j:j + h, :] for j, c in enumerate(k))
+    return np.clip((vs + (1 << 15)) >> 16, 0, 255).astype(np.uint8)
+
+
 def absdiff(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """cv2.absdiff on uint8 (frame_differencing.py:96)."""
     return np.abs(a.astype(np.int16) - b.astype(np.int16)).astype(np.uint8)

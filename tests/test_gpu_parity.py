@@ -129,6 +129,45 @@ def test_temporal_ema_all_accumulator_values(P):
         assert np.array_equal(got, cv2.addWeighted(a0, rf, dil[0], 1 - rf, 0)), rf
 
 
+@pytest.mark.parametrize("ksize,sigma", [(25, 30.0), (5, 0), (3, 0), (7, 2.3), (11, 3.0), (31, 10.0), (33, 12.0), (1, 0)])
+def test_gaussian_blur(P, ksize, sigma):
+    """cv2.GaussianBlur on uint8 (frame_differencing.py:77: the first frame's (25, 25), sigma 30; :93): fixed point, exact."""
+    r = rng(ksize)
+    for shape in [(96, 128), (70, 91), (64, 14), (270, 480)]:
+        img = r.integers(0, 256, (2,) + shape, dtype=np.uint8)
+        got = host(P.gaussian_blur(dev(img), ksize, sigma))
+        for i in range(2):
+            assert np.array_equal(got[i], cv2.GaussianBlur(img[i], (ksize, ksize), sigma)), (ksize, sigma, shape)
+
+
+@pytest.mark.parametrize("mode", ["fd", "window"])
+@pytest.mark.parametrize("scale", [1.0, 0.5])
+def test_begin_stream_frames_does_the_first_frame_work_on_the_gpu(P, mode, scale):
+    """dvc_begin_stream_frames: resize + BGR2GRAY + (fd) GaussianBlur((25, 25), 30) of the first frame on the GPU
+    (frame_differencing.py:74-77) must seed exactly the state the host-side cv2 calls seed."""
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    sh, sw, n = 128, 192, 10
+    frames = make_clip((sh, sw), n, seed=77).frames()
+    w, h = int(sw * scale), int(sh * scale)
+    kw = dict(min_area=40) if mode == "fd" else dict(window_size=3, alpha_fraction=0.4)
+    first = frames[0] if scale == 1.0 else cv2.resize(frames[0], (w, h))
+    seed = loops.first_frame_gray_fd(first) if mode == "fd" else so.bgr2gray(first)
+    outs = []
+    for use_frames in (False, True):
+        pipe = P.FramePipeline(w, h, mode, max_batch=4, src_size=(sw, sh) if scale != 1.0 else None, **kw)
+        if use_frames:
+            pipe.begin_stream_frames(frames[0])
+        else:
+            pipe.begin_stream(seed)
+        ov = np.empty((n - 1, h, w, 3), np.uint8); cp = np.empty_like(ov); mk = np.empty((n - 1, h, w), np.uint8)
+        pipe.process_host(np.ascontiguousarray(frames[1:]), ov, cp, mk)
+        pipe.close()
+        outs.append((ov, cp, mk))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    assert outs[0][2].any()
+
+
 def _blob_mask(r, shape, n):
     m = np.zeros(shape, np.uint8)
     h, w = shape

@@ -266,3 +266,16 @@ def test_dct_closed_forms_are_the_orthonormal_dct(shape):
     y = (rng.standard_normal((500,) + shape) * 100).astype(np.float32)
     assert np.abs(so.dct_block_closed_form(y, True) - idctn(y.astype(np.float64), axes=(1, 2), norm="ortho")).max() < 2e-4
     assert np.abs(so.dct_block_closed_form(f, True) - x).max() < 2e-3
+
+
+@pytest.mark.parametrize("ksize,sigma", [(25, 30.0), (5, 0), (3, 0), (7, 0), (9, 0), (5, 1.0), (7, 2.3), (11, 3.0), (21, 7.5), (31, 10.0),
+                                         (13, 100.0), (3, 0.3), (25, 0), (33, 12.0)])
+def test_gaussian_blur_fixed_point(ksize, sigma):
+    """frame_differencing.py:77 ((25, 25), 30 on the first frame) and :93: OpenCV's uint8 GaussianBlur is an 8.8 fixed-point
+    separable filter whose taps come from error-diffusion rounding; restated exactly."""
+    import cv2
+    rng = _rng(ksize * 7 + 1)
+    for shape in [(120, 160), (70, 91), (64, 14)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        assert np.array_equal(so.gaussian_blur_fixed(img, ksize, sigma), cv2.GaussianBlur(img, (ksize, ksize), sigma)), (ksize, sigma, shape)
+    assert int(so.gaussian_kernel_fixed(ksize, sigma).sum()) == 256
