@@ -143,7 +143,7 @@ static void window_min_counts(double alpha, int K, MinCounts& mc) {
         const double rhs = alpha * L * 255;
         int c = 0;
         while (!((double)(c * 255) >= rhs) && c <= L) ++c;
-        mc.v[L - 1] = (uint8_t)std::min(c, 63);
+        mc.v[L - 1] = (uint8_t)std::min(c, 255);
     }
 }
 
@@ -389,13 +389,13 @@ static int launch_gaussian(char* ERRBUF, const uint8_t* src, uint8_t* dst, uint1
 // partial blocks at the right / bottom edge of frames whose size is not a multiple of the block size
 static int launch_degrade_edges(char* ERRBUF, const uint8_t* frames, const uint32_t* over127, const uint32_t* nonzero,
                                 uint8_t* compressed, uint8_t* overlay, int n, int H, int W, int bs, float q, int flavour,
-                                Counters* counters, cudaStream_t st) {
-    if (H % bs == 0 && W % bs == 0) return DVC_OK;
-    const int n_edge = (W % bs ? (H + bs - 1) / bs : 0) + (H % bs ? W / bs : 0);
+                                Counters* counters, cudaStream_t st, bool all_blocks = false) {
+    if (!all_blocks && H % bs == 0 && W % bs == 0) return DVC_OK;
+    const int n_edge = all_blocks ? ((W + bs - 1) / bs) * ((H + bs - 1) / bs) : (W % bs ? (H + bs - 1) / bs : 0) + (H % bs ? W / bs : 0);
     dim3 grid(cdiv(n_edge, 64), n);
     const int wpr = words_per_row(W);
-    if (flavour == DVC_DEGRADE_FD) k_degrade_edges<0><<<grid, 64, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, bs, q, counters);
-    else k_degrade_edges<1><<<grid, 64, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, bs, q, counters);
+    if (flavour == DVC_DEGRADE_FD) k_degrade_edges<0><<<grid, 64, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, bs, q, counters, all_blocks);
+    else k_degrade_edges<1><<<grid, 64, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, bs, q, counters, all_blocks);
     CHECK_LAUNCH();
     return DVC_OK;
 }
@@ -404,10 +404,13 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
                           uint8_t* compressed, uint8_t* overlay, int n, int H, int W, int bs, float q, int flavour,
                           Counters* counters, cudaStream_t st) {
     const int wpr = words_per_row(W);
-    if (bs != 4 && bs != 8) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "block_size %d: the GPU path implements 4 and 8", bs);
+    if (bs < 1 || bs > 8)
+        return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "block_size %d: the GPU path implements 1..8 (cv2's DCT routines for longer blocks are not restated)", bs);
     if (flavour == DVC_DEGRADE_MCO && bs != 8) return set_err(ERRBUF, DVC_ERR_INVALID, "MCO flavour uses 8x8 blocks");
     if (!(q > 0.0f)) return set_err(ERRBUF, DVC_ERR_INVALID, "quantization_level must be > 0");
     if (n <= 0) return DVC_OK;
+    if (bs != 4 && bs != 8)      // rare block sizes: every block through the general one-thread-per-block path (exact, not fast)
+        return launch_degrade_edges(ERRBUF, frames, over127, nonzero, compressed, overlay, n, H, W, bs, q, flavour, counters, st, true);
     if (H % bs || W % bs) {
         // full blocks by the kernels below (they floor H and W to whole blocks), partial edge blocks by a small second launch
         int rc = launch_degrade_edges(ERRBUF, frames, over127, nonzero, compressed, overlay, n, H, W, bs, q, flavour, counters, st);
@@ -724,8 +727,8 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
         if (cfg->kernel_size > 0 && !chain_push(h->chain, DVC_MORPH_DILATE, DVC_SHAPE_RECT, cfg->kernel_size))
             return set_err(h->err, DVC_ERR_UNSUPPORTED, "kernel_size %d: supported range is 1..%d", cfg->kernel_size, MORPH_MAX_K);
     } else {
-        if (cfg->window_size < 1 || cfg->window_size > 31)
-            return set_err(h->err, DVC_ERR_UNSUPPORTED, "window_size %d: supported range is 1..31", cfg->window_size);
+        if (cfg->window_size < 1 || cfg->window_size > WINDOW_MAX)
+            return set_err(h->err, DVC_ERR_UNSUPPORTED, "window_size %d: supported range is 1..%d", cfg->window_size, WINDOW_MAX);
         h->ring_cap = cfg->max_batch + cfg->window_size + 1;
         CU(cudaMalloc(&h->ring, h->plane_words * 4 * h->ring_cap * S));
         CU(cudaMemset(h->ring, 0, h->plane_words * 4 * h->ring_cap * S));
@@ -773,8 +776,8 @@ extern "C" int dvc_create(const dvc_config* cfg, dvc_handle** out) {
     if (cfg->width < 1 || cfg->height < 1 || cfg->max_batch < 1)
         return set_err(nullptr, DVC_ERR_INVALID, "dvc_create: width, height and max_batch must be >= 1");
     if (cfg->mode != DVC_MODE_FD && cfg->mode != DVC_MODE_WINDOW) return set_err(nullptr, DVC_ERR_INVALID, "dvc_create: unknown mode %d", cfg->mode);
-    if (cfg->block_size != 4 && cfg->block_size != 8)
-        return set_err(nullptr, DVC_ERR_UNSUPPORTED, "block_size %d: the GPU path implements 4 and 8", cfg->block_size);
+    if (cfg->block_size < 1 || cfg->block_size > 8)
+        return set_err(nullptr, DVC_ERR_UNSUPPORTED, "block_size %d: the GPU path implements 1..8 (cv2's DCT routines for longer blocks are not restated)", cfg->block_size);
     if (!(cfg->quantization_level > 0.0f)) return set_err(nullptr, DVC_ERR_INVALID, "quantization_level must be > 0");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -989,7 +992,8 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         h->cur ^= 1;
         dim3 g2(cdiv(h->plane_words, 256), nseg, S);
         { ProfScope ps(h, DVC_PROF_VOTE, 1, st);
-        k_window_vote<<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, (int)(h->n_masks % h->ring_cap), T, h->cfg.window_size, h->min_counts, bits_a, h->seg_len);
+        if (K <= 31) k_window_vote<5><<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, (int)(h->n_masks % h->ring_cap), T, K, h->min_counts, bits_a, h->seg_len);
+        else k_window_vote<7><<<g2, 256, 0, st>>>(h->ring, h->ring_cap, H, W, wpr, h->n_masks, (int)(h->n_masks % h->ring_cap), T, K, h->min_counts, bits_a, h->seg_len);
         }
         CHECK_LAUNCH();
         }
@@ -1258,7 +1262,7 @@ extern "C" int dvc_temporal_ring_u8(const uint8_t* masks, uint8_t* smoothed, int
     int rc = check_dims(n, H, W, "dvc_temporal_ring_u8");
     if (rc || n == 0) return rc;
     if (!masks || !smoothed) return set_err(nullptr, DVC_ERR_INVALID, "dvc_temporal_ring_u8: null pointer");
-    if (window_size < 1 || window_size > 31) return set_err(nullptr, DVC_ERR_UNSUPPORTED, "window_size %d: supported range is 1..31", window_size);
+    if (window_size < 1 || window_size > WINDOW_MAX) return set_err(nullptr, DVC_ERR_UNSUPPORTED, "window_size %d: supported range is 1..%d", window_size, WINDOW_MAX);
     cudaStream_t st = (cudaStream_t)stream;
     const int wpr = words_per_row(W);
     const size_t pw = (size_t)H * wpr;
@@ -1271,7 +1275,8 @@ extern "C" int dvc_temporal_ring_u8(const uint8_t* masks, uint8_t* smoothed, int
     window_min_counts(alpha_fraction, window_size, mc);
     const int seg = 8, nseg = (n + seg - 1) / seg;
     dim3 g(cdiv(pw, 256), nseg);
-    k_window_vote<<<g, 256, 0, st>>>((const uint32_t*)ring.p, n, H, W, wpr, 0, 0, n, window_size, mc, (uint32_t*)voted.p, seg);
+    if (window_size <= 31) k_window_vote<5><<<g, 256, 0, st>>>((const uint32_t*)ring.p, n, H, W, wpr, 0, 0, n, window_size, mc, (uint32_t*)voted.p, seg);
+    else k_window_vote<7><<<g, 256, 0, st>>>((const uint32_t*)ring.p, n, H, W, wpr, 0, 0, n, window_size, mc, (uint32_t*)voted.p, seg);
     CHECK_LAUNCH();
     return unpack_from_bits((const uint32_t*)voted.p, smoothed, n, H, W, st);
 }

@@ -522,12 +522,14 @@ template <int FLAVOUR>
 __global__ void __launch_bounds__(64)
 k_degrade_edges(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127, const uint32_t* __restrict__ nonzero,
                 uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay, int H, int W, int wpr, int bs, float q,
-                Counters* __restrict__ counters) {
-    const int nbx = W / bs, nby = H / bs, nbx_c = (W + bs - 1) / bs, nby_c = (H + bs - 1) / bs;
+                Counters* __restrict__ counters, int all_blocks) {
+    const int nbx = W / bs, nbx_c = (W + bs - 1) / bs, nby_c = (H + bs - 1) / bs;
     const int n_right = W % bs ? nby_c : 0, n_bottom = H % bs ? nbx : 0;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_right + n_bottom) return;
-    const int bx = e < n_right ? nbx_c - 1 : e - n_right, by = e < n_right ? e : nby_c - 1;
+    // all_blocks: every block of the frame goes through this general path (block sizes other than 4 and 8)
+    if (e >= (all_blocks ? nbx_c * nby_c : n_right + n_bottom)) return;
+    const int bx = all_blocks ? e % nbx_c : (e < n_right ? nbx_c - 1 : e - n_right);
+    const int by = all_blocks ? e / nbx_c : (e < n_right ? e : nby_c - 1);
     const int x0 = bx * bs, y0 = by * bs, bw = min(bs, W - x0), bh = min(bs, H - y0);
     const uint8_t* fr = frames + (size_t)blockIdx.y * H * W * 3;
     const size_t plane_off = (size_t)blockIdx.y * H * wpr;

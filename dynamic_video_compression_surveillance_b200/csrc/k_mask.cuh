@@ -21,32 +21,35 @@ namespace dvc {
 // ------------------------------------------------------------------------------------------------
 // window vote
 // ------------------------------------------------------------------------------------------------
-struct MinCounts { uint8_t v[32]; };   // v[L-1] = smallest count that passes with L masks in the window
+constexpr int WINDOW_MAX = 127;        // window_size limit: the bit-sliced count has 5 bits up to 31 frames, 7 bits beyond
+struct MinCounts { uint8_t v[128]; };  // v[L-1] = smallest count that passes with L masks in the window
 
-constexpr int CNT_BITS = 5;            // window_size <= 31
-
-DEVI void bs_add(uint32_t (&c)[CNT_BITS], uint32_t x) {
+template <int CB>
+DEVI void bs_add(uint32_t (&c)[CB], uint32_t x) {
 #pragma unroll
-    for (int i = 0; i < CNT_BITS; ++i) { uint32_t t = c[i] & x; c[i] ^= x; x = t; }
+    for (int i = 0; i < CB; ++i) { uint32_t t = c[i] & x; c[i] ^= x; x = t; }
 }
-DEVI void bs_sub(uint32_t (&c)[CNT_BITS], uint32_t x) {
+template <int CB>
+DEVI void bs_sub(uint32_t (&c)[CB], uint32_t x) {
 #pragma unroll
-    for (int i = 0; i < CNT_BITS; ++i) { uint32_t t = ~c[i] & x; c[i] ^= x; x = t; }
+    for (int i = 0; i < CB; ++i) { uint32_t t = ~c[i] & x; c[i] ^= x; x = t; }
 }
-DEVI uint32_t bs_ge(const uint32_t (&c)[CNT_BITS], uint32_t m) {   // per-lane count >= m
-    if (m >= (1u << CNT_BITS)) return 0u;
+template <int CB>
+DEVI uint32_t bs_ge(const uint32_t (&c)[CB], uint32_t m) {   // per-lane count >= m
+    if (m >= (1u << CB)) return 0u;
     uint32_t ge = 0xffffffffu;
 #pragma unroll
-    for (int i = 0; i < CNT_BITS; ++i) ge = ((m >> i) & 1u) ? (c[i] & ge) : (c[i] | ge);
+    for (int i = 0; i < CB; ++i) ge = ((m >> i) & 1u) ? (c[i] & ge) : (c[i] | ge);
     return ge;
 }
 
 // slot0 = slot of frame f0 in the ring; all slot arithmetic is 32-bit with wrap-around compares
+template <int CNT_BITS>
 __global__ void __launch_bounds__(256)
 k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int wpr, long long f0, int slot0, int T,
               int K, const __grid_constant__ MinCounts mc, uint32_t* __restrict__ voted, int seg_len) {
-    __shared__ uint8_t s_mc[32];
-    if (threadIdx.x < 32) s_mc[threadIdx.x] = mc.v[threadIdx.x];
+    __shared__ uint8_t s_mc[128];
+    if (threadIdx.x < 128) s_mc[threadIdx.x] = mc.v[threadIdx.x];
     __syncthreads();
     const size_t plane_words = (size_t)H * wpr;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,7 +58,7 @@ k_window_vote(const uint32_t* __restrict__ ring, int ring_cap, int H, int W, int
     voted += (size_t)blockIdx.z * T * plane_words;
     const int t0 = blockIdx.y * seg_len, t1 = min(T, t0 + seg_len);
     const uint32_t vm = valid_mask((int)(idx % wpr), W);
-    uint32_t c[CNT_BITS] = {0, 0, 0, 0, 0};
+    uint32_t c[CNT_BITS] = {};
     const long long fs = f0 + t0;
     int s_new = (slot0 + t0) % ring_cap;
     const int nh = (int)min((long long)(K - 1), fs);       // history planes fs-nh .. fs-1

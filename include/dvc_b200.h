@@ -63,13 +63,13 @@ typedef struct dvc_config {
     int32_t width, height;        /* frame size after the reference's resize (frame_differencing.py:59-60); any size >= 1:
                                    * blocks clipped by the frame edge are handled as the reference slices them (:117-121) */
     int32_t mode;                 /* DVC_MODE_* */
-    int32_t block_size;           /* frame_differencing.py:22 (4); 4 or 8 */
+    int32_t block_size;           /* frame_differencing.py:22 (4); 1..8 (4 and 8 have the fast kernels) */
     float   motion_threshold;     /* frame_differencing.py:24 (0.5); cv2.threshold floors it */
     double  min_area;             /* frame_differencing.py:25 (500) */
     int32_t kernel_size;          /* frame_differencing.py:26 (7): k x k ones, dilate; 0 = skip (window mode) */
     double  release_factor;       /* frame_differencing.py:27 (0.5): addWeighted alpha; beta = 1 - alpha */
     float   quantization_level;   /* frame_differencing.py:28 (100) */
-    int32_t window_size;          /* motion_compression_opt.py:30 window_size (30), <= 31 */
+    int32_t window_size;          /* motion_compression_opt.py:30 window_size (30), <= 127 */
     double  alpha_fraction;       /* motion_compression_opt.py:29 alpha_fraction (0.2) */
     int32_t morph_kernel;         /* motion_compression_opt.py:30 morph_kernel (2); 0 = skip open/close */
     int32_t morph_shape;          /* DVC_SHAPE_ELLIPSE as in motion_compression_opt.py:62 */

@@ -147,7 +147,7 @@ def test_fd_error_convention(tmp_path, dropin_modules):
     # unsupported configuration: logged and swallowed inside the loop, outputs finalised, timing file written
     src = str(tmp_path / "c.mp4")
     _write_clip(src, _smooth_clip(64, 96, 6, 1))
-    fd.filter_and_dilate_movements(src, str(tmp_path / "o3"), block_size=6)
+    fd.filter_and_dilate_movements(src, str(tmp_path / "o3"), block_size=16)
     txt = open(os.path.join(str(tmp_path / "o3"), "c", "execution_times.txt")).read()
     assert "Frames processed: 0" in txt
 

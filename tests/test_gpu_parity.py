@@ -94,7 +94,8 @@ def test_morphology_tall_image_bands(P):
             assert np.array_equal(got[i], cv2.morphologyEx(masks[i], cv2.MORPH_CLOSE, kernel))
 
 
-@pytest.mark.parametrize("alpha,K", [(0.2, 30), (0.2, 5), (0.5, 4), (0.34, 7), (1.0, 3), (0.0, 3), (0.2, 1), (0.9, 31)])
+@pytest.mark.parametrize("alpha,K", [(0.2, 30), (0.2, 5), (0.5, 4), (0.34, 7), (1.0, 3), (0.0, 3), (0.2, 1), (0.9, 31), (0.3, 32), (0.55, 60),
+                                     (1.0, 127), (0.01, 100)])
 def test_temporal_ring(P, alpha, K):
     r = rng(7)
     n, shape = 70, (37, 83)
@@ -603,9 +604,35 @@ def test_unsupported_is_loud(P):
     from dynamic_video_compression_surveillance_b200._lib import DvcUnsupported
     frames = torch.zeros((1, 32, 48, 3), dtype=torch.uint8, device="cuda")
     with pytest.raises(DvcUnsupported):
-        P.degrade_blend(frames, torch.zeros((1, 32, 48), dtype=torch.uint8, device="cuda"), 6, 100, "fd")
+        P.degrade_blend(frames, torch.zeros((1, 32, 48), dtype=torch.uint8, device="cuda"), 16, 100, "fd")
     with pytest.raises(NotImplementedError):
-        P.FramePipeline(64, 64, "fd", block_size=6)
+        P.FramePipeline(64, 64, "fd", block_size=16)
+    with pytest.raises(NotImplementedError):
+        P.FramePipeline(64, 64, "window", window_size=200)
+
+
+@pytest.mark.parametrize("bs", [1, 2, 3, 5, 6, 7])
+def test_degrade_fd_other_block_sizes(P, bs):
+    """The reference takes any block_size (frame_differencing.py:22,117-127); sizes 1..8 other than 4 and 8 run every block
+    through the general exact path (1-D routines of k_dct8.cuh), clipped edge blocks included."""
+    r = rng(40 + bs)
+    h, w = 45, 70
+    exact = all(so.cv2_dct_matches_closed_form(a, b) for a in {bs, h % bs or bs} for b in {bs, w % bs or bs} if (a, b) != (1, 1))
+    frames = r.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    frames[1] = (frames[1] // 16) * 16
+    acc = (r.random((2, h, w)) < 0.003).astype(np.uint8) * 200
+    cnt = torch.zeros(5, dtype=torch.int64, device="cuda")
+    comp, ov = P.degrade_blend(dev(frames), dev(acc), bs, 100, "fd", True, cnt)
+    comp, ov = host(comp), host(ov)
+    for i in range(2):
+        assert np.array_equal(ov[i], so.overlay_paint(frames[i], acc[i]))
+        ref = so.degrade_fd(frames[i], acc[i], bs, 100)
+        if exact:
+            assert np.array_equal(comp[i], ref), (bs, i, int((comp[i] != ref).sum()))
+        else:
+            assert np.mean(np.abs(comp[i].astype(int) - ref.astype(int)) <= 1) > 0.99
+    c = host(cnt)
+    assert c[3] == 2 * (-(-h // bs)) * (-(-w // bs)) and c[4] == sum(int(so.block_all_zero(acc[i], bs).sum()) for i in range(2))
 
 
 # ---------------------------------------------------------------------------------------------------
