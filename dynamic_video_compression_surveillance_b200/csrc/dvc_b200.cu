@@ -722,7 +722,7 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
     if (cfg->mode == DVC_MODE_FD) {
         CU(cudaMalloc(&h->acc, h->plane_bytes * S));
         CU(cudaMemset(h->acc, 0, h->plane_bytes * S));
-        int rc = ccl_scratch_alloc(h->err, h->ccl, std::min(T, 64), h->H, h->W);
+        int rc = ccl_scratch_alloc(h->err, h->ccl, std::min(T, std::max(1, measure_env("DVC_CCL_CHUNK", 256))), h->H, h->W);
         if (rc) return rc;
         if (cfg->kernel_size > 0 && !chain_push(h->chain, DVC_MORPH_DILATE, DVC_SHAPE_RECT, cfg->kernel_size))
             return set_err(h->err, DVC_ERR_UNSUPPORTED, "kernel_size %d: supported range is 1..%d", cfg->kernel_size, MORPH_MAX_K);

@@ -98,7 +98,7 @@ def test_morphology_tall_image_bands(P):
                                      (1.0, 127), (0.01, 100)])
 def test_temporal_ring(P, alpha, K):
     r = rng(7)
-    n, shape = 70, (37, 83)
+    n, shape = (70 if K <= 31 else 170), (37, 83)
     masks = np.stack([(r.random(shape) < 0.3).astype(np.uint8) * 255 for _ in range(n)])
     got = host(P.temporal_ring(dev(masks), K, alpha))
     for t in range(n):
@@ -698,8 +698,8 @@ def test_window_front_end_gray_variants_measure_build():
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = os.path.join(root, "dynamic_video_compression_surveillance_b200", "libdvc_b200_measure.so")
-    if not os.path.exists(lib):
-        pytest.skip("measure flavour not built (python -m dynamic_video_compression_surveillance_b200.build --measure)")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(lib.replace("_measure.so", ".so")):
+        pytest.skip("measure flavour not built or older than the product library (python -m dynamic_video_compression_surveillance_b200.build --measure)")
     for flag in ("0", "1", "2"):
         env = dict(os.environ, DVC_LIB_FLAVOUR="measure", DVC_GRAY_IMPL=flag)
         r = subprocess.run([sys.executable, os.path.join(root, "tools", "gray_variants_check.py")], capture_output=True, text=True,
