@@ -255,12 +255,13 @@ static int launch_contour_filter(char* ERRBUF, const uint32_t* raw, uint32_t* ou
         static const bool row_skip = measure_env("DVC_CCL_ROWSKIP", 1) != 0;
         uint8_t* rf = row_skip ? sc.rowflag : nullptr;
         k_ccl_rowlink<true, true><<<grow, 256, 0, st>>>(r, sc.pa0, sc.paov, nullptr, nullptr, H, W, wpr, rf);
-        k_ccl_union<true, 4><<<grid, 256, 0, st>>>(r, sc.pa0, sc.paov, H, W, wpr, rf);
-        k_ccl_fill<<<grid, 256, 0, st>>>(r, sc.pa0, sc.paov, sc.filled, H, W, wpr, rf);
+        const dim3 gpos = CCL_GRID(wpr, H, m);
+        k_ccl_union<true, 4><<<gpos, 256, 0, st>>>(r, sc.pa0, sc.paov, H, W, wpr, rf);
+        k_ccl_fill<<<gpos, 256, 0, st>>>(r, sc.pa0, sc.paov, sc.filled, H, W, wpr, rf);
         k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, H, W, wpr, rf);
-        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, H, W, wpr, rf);
-        k_ccl_area<<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, H, W, wpr, rf);
-        k_ccl_select<<<grid, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, out + (size_t)i0 * pw, H, W, wpr, thr, rf);
+        k_ccl_union<false, 8><<<gpos, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, H, W, wpr, rf);
+        k_ccl_area<<<gpos, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, H, W, wpr, rf);
+        k_ccl_select<<<gpos, 256, 0, st>>>(sc.filled, sc.pb0, sc.pbov, sc.ar0, sc.arov, out + (size_t)i0 * pw, H, W, wpr, thr, rf);
         CHECK_LAUNCH();
     }
     return DVC_OK;
@@ -1402,7 +1403,7 @@ extern "C" int dvc_mask_rectangles_u8(const uint8_t* src, uint8_t* dst, int32_t 
         CU(cudaMemsetAsync(bd.p, 0x7f, 3 * d, st));           // 0x7f7f7f7f: larger than any coordinate or negated coordinate
         CU(cudaMemsetAsync(bo.p, 0x7f, 3 * o, st));
         k_ccl_rowlink<false, false><<<grow, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, nullptr, nullptr, H, W, wpr, nullptr);
-        k_ccl_union<false, 8><<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, H, W, wpr, nullptr);
+        k_ccl_union<false, 8><<<CCL_GRID(wpr, H, m), 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, H, W, wpr, nullptr);
         k_ccl_bbox<<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, bb, H, W, wpr);
         k_ccl_paint_rects<<<grid, 256, 0, st>>>(r, (int*)p0.p, (int*)pov.p, bb, (uint32_t*)b.p + (size_t)i0 * pw, H, W, wpr);
         CHECK_LAUNCH();

@@ -168,6 +168,15 @@ k_ccl_rowlink(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __
     if (INVERT && rowflag && lane == 0) rowflag[(size_t)blockIdx.y * H + y] = any_fg ? 1 : 0;
 }
 
+// thread -> (row y, word j, frame) without a division: CTAs of 64 words x 4 rows, grid (ceil(wpr / 64), ceil(H / 4), frames)
+#define CCL_GRID(wpr, H, frames) dim3((unsigned)(((wpr) + 63) / 64), (unsigned)(((H) + 3) / 4), (unsigned)(frames))
+#define CCL_THREAD_POS()                                                         \
+    const int j = (int)blockIdx.x * 64 + (int)(threadIdx.x & 63u);               \
+    const int y = (int)blockIdx.y * 4 + (int)(threadIdx.x >> 6);                 \
+    if (j >= wpr || y >= H) return;                                              \
+    const uint32_t idx = (uint32_t)y * (uint32_t)wpr + (uint32_t)j;              \
+    const uint32_t frame = blockIdx.z;
+
 // ---- unions with the row above (4- or 8-connected); horizontal links already exist ----------------------
 // All vertical links of one word (y, j) with row y - 1.
 template <bool INVERT, int CONN>
@@ -222,18 +231,17 @@ __global__ void __launch_bounds__(256)
 k_ccl_union(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov, int H, int W, int wpr,
             const uint8_t* __restrict__ rowflag) {
     const size_t plane_words = (size_t)H * wpr;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
-    if (idx >= (uint32_t)plane_words) return;
-    const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
+    CCL_THREAD_POS();
+    (void)idx;
     if (y == 0) return;
     if (rowflag) {
-        const uint8_t* f = rowflag + (size_t)blockIdx.y * H;
+        const uint8_t* f = rowflag + (size_t)frame * H;
         // background flood (INVERT): two foreground-free rows are both rooted at 'outside' already; foreground labelling: a row
         // without foreground has no nodes
         if (INVERT ? (f[y] == 0 && f[y - 1] == 0) : (f[y] == 0)) return;
     }
-    const uint32_t* plane = planes + (size_t)blockIdx.y * plane_words;
-    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
+    const uint32_t* plane = planes + (size_t)frame * plane_words;
+    const UF P = uf_of_frame(p0, pov, plane_words, frame);
     ccl_union_word<INVERT, CONN>(plane, P, y, j, H, W, wpr);
 }
 
@@ -242,15 +250,13 @@ __global__ void __launch_bounds__(256)
 k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __restrict__ pov,
            uint32_t* __restrict__ filled, int H, int W, int wpr, const uint8_t* __restrict__ rowflag) {
     const size_t plane_words = (size_t)H * wpr;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
-    if (idx >= (uint32_t)plane_words) return;
-    const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
-    if (rowflag && rowflag[(size_t)blockIdx.y * H + y] == 0) {             // no foreground in the row: all of it is outside
-        filled[(size_t)blockIdx.y * plane_words + idx] = 0u;
+    CCL_THREAD_POS();
+    if (rowflag && rowflag[(size_t)frame * H + y] == 0) {                  // no foreground in the row: all of it is outside
+        filled[(size_t)frame * plane_words + idx] = 0u;
         return;
     }
-    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
-    uint32_t m = plane_word<true>(planes + (size_t)blockIdx.y * plane_words, y, j, H, W, wpr);
+    const UF P = uf_of_frame(p0, pov, plane_words, frame);
+    uint32_t m = plane_word<true>(planes + (size_t)frame * plane_words, y, j, H, W, wpr);
     uint32_t outside = 0;
     int slot = 0;
     while (m) {
@@ -259,7 +265,7 @@ k_ccl_fill(const uint32_t* __restrict__ planes, int* __restrict__ p0, int* __res
         m &= ~run;
         if (uf_find_settled(P, node_id((int)idx, slot++)) == 0) outside |= run;
     }
-    filled[(size_t)blockIdx.y * plane_words + idx] = ~outside & valid_mask(j, W);
+    filled[(size_t)frame * plane_words + idx] = ~outside & valid_mask(j, W);
 }
 
 // ---- phase B: 2*area = 2*Q4 + Q3 per label --------------------------------------------------------
@@ -267,16 +273,14 @@ __global__ void __launch_bounds__(256)
 k_ccl_area(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __restrict__ pov, int* __restrict__ a0,
            int* __restrict__ aov, int H, int W, int wpr, const uint8_t* __restrict__ rowflag) {
     const size_t plane_words = (size_t)H * wpr;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;            // a plane has far fewer than 2^31 words: 32-bit index math
-    if (idx >= (uint32_t)plane_words) return;
-    const int y = (int)(idx / (uint32_t)wpr), j = (int)(idx - (uint32_t)y * (uint32_t)wpr);
+    CCL_THREAD_POS();
     if (rowflag) {
-        const uint8_t* f = rowflag + (size_t)blockIdx.y * H;
+        const uint8_t* f = rowflag + (size_t)frame * H;
         if (f[y] == 0 && (y + 1 >= H || f[y + 1] == 0)) return;           // both rows of the 2x2 windows are empty
     }
-    const uint32_t* F = filled + (size_t)blockIdx.y * plane_words;
-    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
-    const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
+    const uint32_t* F = filled + (size_t)frame * plane_words;
+    const UF P = uf_of_frame(p0, pov, plane_words, frame);
+    const UF A = uf_of_frame(a0, aov, plane_words, frame);
     const uint32_t a = plane_word<false>(F, y, j, H, W, wpr), b = plane_word<false>(F, y + 1, j, H, W, wpr);
     if (!(a | b)) return;
     const uint32_t an = plane_word<false>(F, y, j + 1, H, W, wpr), bn = plane_word<false>(F, y + 1, j + 1, H, W, wpr);
@@ -312,15 +316,15 @@ k_ccl_select(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __r
              int* __restrict__ aov, uint32_t* __restrict__ out, int H, int W, int wpr, int twice_min_area_floor,
              const uint8_t* __restrict__ rowflag) {
     const size_t plane_words = (size_t)H * wpr;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint32_t)plane_words) return;
-    if (rowflag && rowflag[(size_t)blockIdx.y * H + idx / (uint32_t)wpr] == 0) {
-        out[(size_t)blockIdx.y * plane_words + idx] = 0u;
+    CCL_THREAD_POS();
+    (void)j;
+    if (rowflag && rowflag[(size_t)frame * H + y] == 0) {
+        out[(size_t)frame * plane_words + idx] = 0u;
         return;
     }
-    const UF P = uf_of_frame(p0, pov, plane_words, blockIdx.y);
-    const UF A = uf_of_frame(a0, aov, plane_words, blockIdx.y);
-    uint32_t m = filled[(size_t)blockIdx.y * plane_words + idx];
+    const UF P = uf_of_frame(p0, pov, plane_words, frame);
+    const UF A = uf_of_frame(a0, aov, plane_words, frame);
+    uint32_t m = filled[(size_t)frame * plane_words + idx];
     uint32_t keep = 0;
     int slot = 0;
     while (m) {
@@ -329,7 +333,7 @@ k_ccl_select(const uint32_t* __restrict__ filled, int* __restrict__ p0, int* __r
         m &= ~run;
         if (__ldcg(uf_addr(A, uf_find_settled(P, node_id((int)idx, slot++)))) > twice_min_area_floor) keep |= run;
     }
-    out[(size_t)blockIdx.y * plane_words + idx] = keep;
+    out[(size_t)frame * plane_words + idx] = keep;
 }
 
 // ---- bounding rectangles of the 8-connected components (motion_compression_opt.py:93-97) ------------------
