@@ -379,30 +379,32 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
             }
         }
         __syncthreads();
-        // phase 2: horizontal 5 taps on 16-bit lanes (see k_gray_blur5): rows (tid >> 5) + 8 i, 4-px group tid & 31
-        {
-            const int cg = tid & 31;
+        // phase 2: horizontal 5 taps on 16-bit lanes, 16 px (four gray words) per task, same 544-task table as phase 1a.  Every
+        // word is widened once into even / odd pixel lanes (E = px0 | px2 << 16, O = px1 | px3 << 16); the shifted operands
+        // of the taps are funnel shifts of neighbouring E / O words: even outputs E(-1) + E(+1) + 4 (O(-1) + O) + 6 E, odd
+        // outputs O(-1) + O(+1) + 4 (E + E(+1)) + 6 O, where (-1) / (+1) is the lane-shifted word pair.  h <= 4080 per lane.
 #pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                const int r = (tid >> 5) + 8 * i;
-                if (r < FF_ROWS) {
-                    const uint32_t* g = reinterpret_cast<const uint32_t*>(&sg[r * FF_GP + FF_PAD]) + cg;
-                    const uint32_t prev = g[-1], cur = g[0], next = g[1];
-                    const uint32_t a = __funnelshift_r(prev, cur, 16), b = __funnelshift_r(prev, cur, 24);
-                    const uint32_t d = __funnelshift_r(cur, next, 8), e = __funnelshift_r(cur, next, 16);
-                    uint2 h;
-                    {
-                        const uint32_t ae = __byte_perm(a, 0u, 0x4240u) + __byte_perm(e, 0u, 0x4240u);
-                        const uint32_t bd = __byte_perm(b, 0u, 0x4240u) + __byte_perm(d, 0u, 0x4240u);
-                        h.x = ae + 4u * bd + 6u * __byte_perm(cur, 0u, 0x4240u);
-                    }
-                    {
-                        const uint32_t ae = __byte_perm(a, 0u, 0x4341u) + __byte_perm(e, 0u, 0x4341u);
-                        const uint32_t bd = __byte_perm(b, 0u, 0x4341u) + __byte_perm(d, 0u, 0x4341u);
-                        h.y = ae + 4u * bd + 6u * __byte_perm(cur, 0u, 0x4341u);
-                    }
-                    sh[r * (FF_TW / 4) + cg] = h;
+        for (int i = 0; i < 3; ++i) {
+            const int task = tid + 256 * i;
+            if (task < FF_ROWS * 8) {
+                const int r = task >> 3, g = task & 7;
+                const uint32_t* gw = reinterpret_cast<const uint32_t*>(&sg[r * FF_GP + FF_PAD + g * 16]);
+                const uint4 c4 = *reinterpret_cast<const uint4*>(gw);
+                const uint32_t wv[6] = {gw[-1], c4.x, c4.y, c4.z, c4.w, gw[4]};
+                uint32_t E[6], O[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { E[k] = __byte_perm(wv[k], 0u, 0x4240u); O[k] = __byte_perm(wv[k], 0u, 0x4341u); }
+                uint32_t hx[4], hy[4];
+#pragma unroll
+                for (int k = 1; k <= 4; ++k) {
+                    const uint32_t Em = __funnelshift_r(E[k - 1], E[k], 16), Om = __funnelshift_r(O[k - 1], O[k], 16);
+                    const uint32_t Ep = __funnelshift_r(E[k], E[k + 1], 16), Op = __funnelshift_r(O[k], O[k + 1], 16);
+                    hx[k - 1] = (Em + Ep) + 4u * (Om + O[k]) + 6u * E[k];
+                    hy[k - 1] = (Om + Op) + 4u * (E[k] + Ep) + 6u * O[k];
                 }
+                uint4* dst = reinterpret_cast<uint4*>(&sh[r * (FF_TW / 4) + g * 4]);
+                dst[0] = make_uint4(hx[0], hy[0], hx[1], hy[1]);
+                dst[1] = make_uint4(hx[2], hy[2], hx[3], hy[3]);
             }
         }
         __syncthreads();
