@@ -26,6 +26,27 @@ def shard_streams(n_streams: int, world_size: int, rank: int) -> list[int]:
     return list(range(start, start + base + (1 if rank < extra else 0)))
 
 
+def shard_streams_weighted(n_streams: int, weights: list) -> list[list[int]]:
+    """Contiguous stream ids per rank, counts proportional to ``weights`` (largest-remainder apportionment; ties go to the
+    lower rank).  Used for the end-to-end path, where a rank's sustainable rate is its host link's share of the box's IO
+    fabric, not its GPU: on the 8-GPU boxes of this pool four GPUs sit behind an uplink with 1.5x the bandwidth of the
+    other four, so equal shards leave the faster links idle a third of the time."""
+    w = [max(0.0, float(x)) for x in weights]
+    if not w or sum(w) <= 0:
+        raise ValueError("weights must contain a positive value")
+    total = sum(w)
+    quota = [n_streams * x / total for x in w]
+    counts = [int(q) for q in quota]
+    order = sorted(range(len(w)), key=lambda r: (-(quota[r] - counts[r]), r))
+    for r in order[:n_streams - sum(counts)]:
+        counts[r] += 1
+    out, start = [], 0
+    for c in counts:
+        out.append(list(range(start, start + c)))
+        start += c
+    return out
+
+
 @dataclass(frozen=True)
 class FrameChunk:
     rank: int

@@ -974,6 +974,38 @@ def test_stream_group_equals_separate_pipelines(P, mode, shape):
     assert np.array_equal(host(dmk), solo_mk) and np.array_equal(host(dov), solo_ov) and np.array_equal(host(dcp), solo_cp)
 
 
+@pytest.mark.parametrize("mode,shape,S", [("window", (96, 128), 1), ("window", (62, 110), 2), ("fd", (96, 128), 1), ("fd", (61, 83), 2)])
+def test_no_writes_outside_the_output_buffers(P, mode, shape, S):
+    """compute-sanitizer is closed on this pool (profiles/r2_sanitizer_unavailable.txt), so out-of-bounds global writes are hunted
+    with canaries: every output of the loop is a view inside one allocation, separated by 64 KB bands of 0xA5 that must survive."""
+    from dynamic_video_compression_surveillance_b200.synth import make_clip
+    h, w = shape
+    n, G = 11, 65536
+    kw = dict(window_size=4, alpha_fraction=0.3, morph_kernel=2, kernel_size=7) if mode == "window" else dict(min_area=30)
+    clips = [make_clip((h, w), n, seed=80 + s).frames() for s in range(S)]
+    seeds = np.stack([(so.bgr2gray(c[0]) if mode == "window" else loops.first_frame_gray_fd(c[0])) for c in clips])
+    body = np.ascontiguousarray(np.stack([c[1:] for c in clips]))
+    T = n - 1
+    fb, pb = S * T * h * w * 3, S * T * h * w
+    arena = torch.full((4 * G + 2 * fb + pb,), 0xA5, dtype=torch.uint8, device="cuda")
+    o_ov, o_cp, o_mk = G, 2 * G + fb, 3 * G + 2 * fb
+    lead = (S,) if S > 1 else ()
+    ov = arena[o_ov:o_ov + fb].view(lead + (T, h, w, 3)); cp = arena[o_cp:o_cp + fb].view(lead + (T, h, w, 3))
+    mk = arena[o_mk:o_mk + pb].view(lead + (T, h, w))
+    pipe = P.FramePipeline(w, h, mode, max_batch=T, n_streams=S, **kw)
+    pipe.begin_stream(seeds if S > 1 else seeds[0])
+    for overlap in (False, True):
+        pipe.set_overlap(overlap)
+        pipe.process_device(dev(body if S > 1 else body[0]), ov, cp, mk)
+        pipe.flush()
+        torch.cuda.synchronize()
+    pipe.close()
+    a = arena.cpu().numpy()
+    for lo, hi in ((0, o_ov), (o_ov + fb, o_cp), (o_cp + fb, o_mk), (o_mk + pb, a.size)):
+        assert (a[lo:hi] == 0xA5).all(), (mode, shape, S, lo, hi)
+    assert (a[o_mk:o_mk + pb] != 0xA5).any()
+
+
 def test_config5_farneback_masks_to_mco_degrade_1080p(P):
     """configs[4]: masks from the reference's Farneback + window vote + rectangles arithmetic
     (motion_compression_opt.py:72-97, on the CPU) fed to the shared degrade kernel in MCO flavour at 1080p."""

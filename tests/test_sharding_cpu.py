@@ -102,3 +102,13 @@ def test_counter_allreduce_gloo_world2():
                              static_blocks=frames * 20)
     assert sharding.motion_percentage(res[0][2]) == pytest.approx(7.0)
     assert sharding.static_block_percentage(res[0][2]) == pytest.approx(80.0)
+
+
+def test_shard_streams_weighted():
+    from dynamic_video_compression_surveillance_b200.sharding import shard_streams_weighted
+    sh = shard_streams_weighted(64, [792, 792, 792, 794, 1195, 1203, 1197, 1196])      # the per-GPU end-to-end rates measured on an 8-GPU box
+    assert [len(x) for x in sh] == [6, 6, 6, 6, 10, 10, 10, 10]
+    assert [i for part in sh for i in part] == list(range(64))
+    assert [len(x) for x in shard_streams_weighted(64, [1.0] * 8)] == [8] * 8
+    assert [len(x) for x in shard_streams_weighted(5, [1, 0, 1])] == [3, 0, 2]
+    assert [len(x) for x in shard_streams_weighted(7, [3, 1])] == [5, 2]
