@@ -558,6 +558,40 @@ def measure_streams(ctx, args, steps, sampler=None, want_e2e=True):
     return res
 
 
+def measure_mco(ctx, args, steps):
+    """BASELINE configs[4]: rectangle masks (what temporal_smoothing_flow hands over, motion_compression_opt.py:93-97) fed to the
+    shared degrade kernel in MCO flavour (8x8, three quantised planes, re-gray: :152-183) on resident 1080p frames."""
+    import torch
+    from dynamic_video_compression_surveillance_b200 import pipeline as P
+    from dynamic_video_compression_surveillance_b200.synth import make_clip, RESOLUTIONS
+    h, w = RESOLUTIONS[args.resolution]
+    n = 64
+    clip = make_clip(args.resolution, n, seed=5)
+    frames = device_clip(clip, n, ctx.dev)
+    masks = torch.zeros((n, h, w), dtype=torch.uint8, device=ctx.dev)
+    for t in range(n):
+        for (x, y, rw, rh) in clip.rect_positions(t):
+            masks[t, max(0, y - 8):y + rh + 9, max(0, x - 8):x + rw + 9] = 255
+    for _ in range(3):
+        P.degrade_blend(frames, masks, 8, 100, "mco", False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        P.degrade_blend(frames, masks, 8, 100, "mco", False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del frames, masks
+    torch.cuda.empty_cache()
+    peak, _ = peaks()
+    fps = steps * n / (ms / 1e3)
+    return {"workload": f"BASELINE configs[4]: {args.resolution} frames + rectangle masks -> degrade kernel, MCO flavour (8x8 blocks, Y/Cr/Cb "
+                        "quantised, re-gray), 64 resident frames per call incl. mask packing", "value": fps, "unit": UNIT,
+            "us_per_frame": 1e3 * ms / (steps * n), "alg_bytes_per_px": 7.0,
+            "frac_of_hbm_peak": fps * h * w * 7.0 / 1e9 / peak}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     from dynamic_video_compression_surveillance_b200.synth import RESOLUTIONS
@@ -587,6 +621,8 @@ def run_b200(args, rank, world, local_rank):
                 "dominant_kernel_us_per_frame": 1e3 * kms[top] / (fd["frames_per_step"] * fd_steps),
                 "dominant_kernel_frac_of_hbm_peak": alg.get(top, 0) * px * fd["frames_per_step"] * fd_steps / (kms[top] * 1e-3) / 1e9 / peak,
                 "alg_bytes_per_px": alg}}
+        if not args.no_fd and args.mode == "window":
+            extra.setdefault("modes", {})["mco_degrade"] = measure_mco(ctx, args, max(3, args.steps // 2))
         if not args.no_streams and args.mode == "window" and args.resolution == "1080p":
             st = measure_streams(ctx, args, max(3, args.steps // 2), want_e2e=not args.no_e2e)
             extra["streams64"] = {"workload": streams_config(args, h, w, 1)["workload"], "value": st["value"], "unit": UNIT,
