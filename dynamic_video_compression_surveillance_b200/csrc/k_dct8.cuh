@@ -40,6 +40,24 @@ DEVI void dct4_inv(float& x0, float& x1, float& x2, float& x3) {
 }
 
 
+// ---- packed pair of binary32 lanes in a 64-bit register pair ----
+struct P2 { unsigned long long v; };
+DEVI P2 p2(float lo, float hi) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+DEVI void unp2(P2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+
+DEVI P2 add(P2 a, P2 b) { P2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+DEVI P2 sub(P2 a, P2 b) { P2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+DEVI P2 mul(P2 a, P2 b) { P2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+DEVI P2 fma_(P2 a, P2 b, P2 c) { P2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+DEVI float add(float a, float b) { return __fadd_rn(a, b); }
+DEVI float sub(float a, float b) { return __fsub_rn(a, b); }
+DEVI float mul(float a, float b) { return __fmul_rn(a, b); }
+DEVI float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+template <typename T> DEVI T splat(float x);
+template <> DEVI float splat<float>(float x) { return x; }
+template <> DEVI P2 splat<P2>(float x) { return p2(x, x); }
+
 // 0.5 cos(j pi / 16), correctly rounded to float32 (j = 4: 1 / sqrt(8))
 #define DCT8_C1 0.490392625f
 #define DCT8_C2 0.461939752f
@@ -140,6 +158,135 @@ DEVI void dct8x8_col_inv(float& x0, float& x1, float& x2, float& x3, float& x4, 
     x1 = FA(t1, t6); x6 = FS(t1, t6);
     x2 = FA(t2, t5); x5 = FS(t2, t5);
     x3 = FA(t3, t4); x4 = FS(t3, t4);
+}
+
+// ---- the same 2-D sequences over T = float or the packed pair P2 (two rows, or two columns, per instruction) ----
+// A product that feeds an addition must stay a separate rounding: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+// in spite of the modifiers (k_degrade4p.cuh), so those few products go through scalar FMULs (mul_sep).  Negated addends are
+// folded into the constants (round(ab - c) = -round(c - ab)), because the packed fma has no negate modifier.
+DEVI float mul_sep(float a, float b) { return __fmul_rn(a, b); }
+DEVI P2 mul_sep(P2 a, float b) { float lo, hi; unp2(a, lo, hi); return p2(__fmul_rn(lo, b), __fmul_rn(hi, b)); }
+
+template <typename T>
+DEVI void dct8x8_row_fwd_t(T (&x)[8]) {
+    T s[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[i] = add(x[i], x[7 - i]); d[i] = sub(x[i], x[7 - i]); }
+#pragma unroll
+    for (int l = 0; l < 8; l += 2) {
+        T acc = mul(splat<T>(dct8_a(l, 0)), s[0]);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) acc = fma_(s[i], splat<T>(dct8_a(l, i)), acc);
+        x[l] = acc;
+    }
+#pragma unroll
+    for (int l = 1; l < 8; l += 2) {
+        T acc = mul(splat<T>(dct8_a(l, 3)), d[3]);
+#pragma unroll
+        for (int i = 2; i >= 0; --i) acc = fma_(d[i], splat<T>(dct8_a(l, i)), acc);
+        x[l] = acc;
+    }
+}
+template <typename T>
+DEVI void dct8x8_col_fwd_t(T& x0, T& x1, T& x2, T& x3, T& x4, T& x5, T& x6, T& x7) {
+    const T t0 = add(x0, x7), t1 = add(x1, x6), t2 = add(x2, x5), t3 = add(x3, x4);
+    const T m0 = sub(x0, x7), m1 = sub(x1, x6), m2 = sub(x2, x5), m3 = sub(x3, x4);
+    const T tp03 = add(t0, t3), tm03 = sub(t0, t3), tp12 = add(t1, t2), tm12 = sub(t1, t2);
+    x0 = mul(splat<T>(DCT8_C4), add(tp03, tp12));
+    x4 = mul(splat<T>(DCT8_C4), sub(tp03, tp12));
+    x2 = mul(splat<T>(DCT8_C2), fma_(tm12, splat<T>(DCT8_TG2), tm03));
+    x6 = mul(splat<T>(-DCT8_C2), fma_(tm03, splat<T>(-DCT8_TG2), tm12));          // C2 * fma(tm03, TG2, -tm12)
+    const T tp65 = mul_sep(add(m1, m2), DCT8_R), tm65 = mul_sep(sub(m1, m2), DCT8_R);   // products that feed additions
+    const T tp765 = add(m0, tp65), tm765 = sub(m0, tp65), tp465 = add(m3, tm65), tm465 = sub(m3, tm65);
+    x1 = mul(splat<T>(DCT8_C1), fma_(tp465, splat<T>(DCT8_TG1), tp765));
+    x7 = mul(splat<T>(-DCT8_C1), fma_(tp765, splat<T>(-DCT8_TG1), tp465));        // C1 * fma(tp765, TG1, -tp465)
+    x5 = mul(splat<T>(DCT8_C3), fma_(tm765, splat<T>(DCT8_TG3), tm465));
+    x3 = mul(splat<T>(DCT8_C3), fma_(tm465, splat<T>(-DCT8_TG3), tm765));
+}
+template <typename T>
+DEVI void dct8x8_row_inv_t(T (&u)[8]) {
+    T o[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        T e = mul(splat<T>(dct8_a(0, c)), u[0]), od = mul(splat<T>(dct8_a(1, c)), u[1]);
+#pragma unroll
+        for (int l = 2; l < 8; l += 2) { e = fma_(u[l], splat<T>(dct8_a(l, c)), e); od = fma_(u[l + 1], splat<T>(dct8_a(l + 1, c)), od); }
+        o[c] = add(e, od);
+        o[7 - c] = sub(e, od);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) u[c] = o[c];
+}
+template <typename T>
+DEVI void dct8x8_col_inv_t(T& x0, T& x1, T& x2, T& x3, T& x4, T& x5, T& x6, T& x7) {
+    const T tp765 = fma_(x7, splat<T>(DCT8_TG1), x1), q465 = fma_(x1, splat<T>(-DCT8_TG1), x7);       // q465 = -tp465
+    const T tm765 = fma_(x5, splat<T>(DCT8_TG3), x3), tm465 = fma_(x3, splat<T>(-DCT8_TG3), x5);
+    const T tm03 = fma_(x6, splat<T>(DCT8_TG2), x2), q12 = fma_(x2, splat<T>(-DCT8_TG2), x6);          // q12 = -tm12
+    const T t7 = add(tp765, tm765), tp65 = sub(tp765, tm765);
+    const T t4 = sub(tm465, q465);                                      // tp465 + tm465
+    const T p65 = mul_sep(tp65, DCT8_R), m65 = mul_sep(add(q465, tm465), -DCT8_R);     // m65 = (tp465 - tm465) * R
+    const T t6 = add(p65, m65), t5 = sub(p65, m65);
+    const T tp03 = add(x0, x4), tp12 = sub(x0, x4);
+    const T t0 = add(tp03, tm03), t3 = sub(tp03, tm03), t1 = sub(tp12, q12), t2 = add(tp12, q12);
+    x0 = add(t0, t7); x7 = sub(t0, t7);
+    x1 = add(t1, t6); x6 = sub(t1, t6);
+    x2 = add(t2, t5); x5 = sub(t2, t5);
+    x3 = add(t3, t4); x4 = sub(t3, t4);
+}
+
+// One 8x8 block through the packed pipe: rows are transformed two at a time (rp[i][c] = rows 2i, 2i+1 of column c), columns
+// two at a time (cp[r][j] = columns 2j, 2j+1 of row r); between passes the 2x2 sub-blocks are re-paired (register moves).
+// quant: P2 -> P2, np.round(d / q) * q on both lanes.  Same values as degrade_block8_exact, about 0.6x the instructions.
+template <typename Quant>
+DEVI void degrade_block8_packed(float (&v)[8][8], Quant quant) {
+    P2 rp[4][8], cp[8][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rp[i][c] = p2(v[2 * i][c], v[2 * i + 1][c]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dct8x8_row_fwd_t(rp[i]);
+    auto rows_to_cols = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a, c, b, d;
+                unp2(rp[i][2 * j], a, c);            // (row 2i, row 2i+1) of column 2j
+                unp2(rp[i][2 * j + 1], b, d);        // ... of column 2j+1
+                cp[2 * i][j] = p2(a, b);
+                cp[2 * i + 1][j] = p2(c, d);
+            }
+    };
+    auto cols_to_rows = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a, b, c, d;
+                unp2(cp[2 * i][j], a, b);
+                unp2(cp[2 * i + 1][j], c, d);
+                rp[i][2 * j] = p2(a, c);
+                rp[i][2 * j + 1] = p2(b, d);
+            }
+    };
+    rows_to_cols();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dct8x8_col_fwd_t(cp[0][j], cp[1][j], cp[2][j], cp[3][j], cp[4][j], cp[5][j], cp[6][j], cp[7][j]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cp[r][j] = mul(quant(cp[r][j]), splat<P2>(dct8_rowscale(r)));
+    cols_to_rows();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dct8x8_row_inv_t(rp[i]);
+    rows_to_cols();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dct8x8_col_inv_t(cp[0][j], cp[1][j], cp[2][j], cp[3][j], cp[4][j], cp[5][j], cp[6][j], cp[7][j]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) unp2(cp[r][j], v[r][2 * j], v[r][2 * j + 1]);
 }
 
 // clip(idct(round(dct(v) / q) * q)) of one 8x8 block held in registers; Q(d) is the caller's quantiser (same value as

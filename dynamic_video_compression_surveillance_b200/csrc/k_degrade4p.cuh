@@ -21,24 +21,6 @@
 
 namespace dvc {
 
-// ---- packed pair of binary32 lanes in a 64-bit register pair ----
-struct P2 { unsigned long long v; };
-DEVI P2 p2(float lo, float hi) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
-DEVI void unp2(P2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
-
-DEVI P2 add(P2 a, P2 b) { P2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-DEVI P2 sub(P2 a, P2 b) { P2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-DEVI P2 mul(P2 a, P2 b) { P2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-DEVI P2 fma_(P2 a, P2 b, P2 c) { P2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
-DEVI float add(float a, float b) { return __fadd_rn(a, b); }
-DEVI float sub(float a, float b) { return __fsub_rn(a, b); }
-DEVI float mul(float a, float b) { return __fmul_rn(a, b); }
-DEVI float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-
-template <typename T> DEVI T splat(float x);
-template <> DEVI float splat<float>(float x) { return x; }
-template <> DEVI P2 splat<P2>(float x) { return p2(x, x); }
-
 struct QuantP {
     float rcp[3];    // fl(1 / (q * 2^NE)),  NE = number of even indices among (row, col) = pending scale 2^-NE
     float nqs[3];    // -(q * 2^NE)
@@ -336,13 +318,12 @@ DEVI void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t ba
 // transform pair is the exact restatement of cv2's 2-D routine (k_dct8.cuh).
 // ------------------------------------------------------------------------------------------------
 DEVI void degrade_plane8(float (&v)[8][8], const QuantP& qp) {
-    degrade_block8_exact(v, [&qp](float d) { return quantise_t<0, false>(d, qp); });
+    degrade_block8_packed(v, [&qp](P2 d) { return quantise_t<0, false>(d, qp); });
 }
 
-// MCO keeps the thread's 8 x 24 input bytes and two quantised channel planes in shared memory ([row][thread], lane stride
-// 24 / 8 bytes: conflict-free) instead of registers, so the 64-float DCT block fits in 128 registers: 4 CTAs per SM instead
-// of the 2 a 255-register version gets.
-constexpr int K8_SMEM_MCO = 128 * (8 * 24 + 2 * 8 * 8);      // 40 960 bytes
+// MCO parks the Cr / Cb bytes of the block (later the quantised Cr bytes) in shared memory ([plane][row][thread] x 8 bytes,
+// conflict-free) while the 64-float block of the plane in flight lives in registers.
+constexpr int K8_SMEM_MCO = 128 * (3 * 8 * 8);               // 24 576 bytes: three planes of 8 x 8 bytes per thread
 
 template <int FLAVOUR>
 __global__ void __launch_bounds__(128, 4)
@@ -431,52 +412,64 @@ k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
                                 w[r][3], w[r][4], w[r][5]);
                 }
             } else {
-                // MCO: quantise Y, Cr, Cb (motion_compression_opt.py:162-168); YCrCb -> BGR (:171); BGR -> gray, replicated (:181-183)
+                // MCO: quantise Y, Cr, Cb (motion_compression_opt.py:162-168); YCrCb -> BGR (:171); BGR -> gray, replicated (:181-183).
+                // One pass over the pixels builds the luma block in registers and parks the Cr / Cb bytes in shared memory
+                // ([plane][row][thread] x 8 bytes: conflict-free); each plane is transformed in turn, its result bytes going back
+                // into the slot it came from.
                 extern __shared__ __align__(16) uint8_t k8_smem[];
-                const uint32_t sW = (uint32_t)__cvta_generic_to_shared(k8_smem) + threadIdx.x * 24u;           // + r * 128 * 24
-                const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(k8_smem) + 128u * 8u * 24u + threadIdx.x * 8u;   // + (k * 8 + r) * 128 * 8
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) sts64(sW + r * (128 * 24) + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
+                const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(k8_smem) + threadIdx.x * 8u;      // + (plane * 8 + row) * 128 * 8
                 float v[8][8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    uint32_t ya[4], yb[4], crw[2] = {0u, 0u}, cbw[2] = {0u, 0u};
+                    luma4_bits(w[r][0], w[r][1], w[r][2], ya);
+                    luma4_bits(w[r][3], w[r][4], w[r][5], yb);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t yf = c < 4 ? ya[c] : yb[c - 4];
+                        const int y = (int)(yf & 0xffu);
+                        const int cr = sat8((((int)byte_at(w[r], 3 * c + 2) - y) * 11682 + (128 << 14) + 8192) >> 14);
+                        const int cb = sat8((((int)byte_at(w[r], 3 * c) - y) * 9241 + (128 << 14) + 8192) >> 14);
+                        crw[c >> 2] |= (uint32_t)cr << ((c & 3) * 8);
+                        cbw[c >> 2] |= (uint32_t)cb << ((c & 3) * 8);
+                        v[r][c] = __fsub_rn(__uint_as_float(yf), 8388736.0f);          // 2^23 + Y - (2^23 + 128)
+                    }
+                    sts64(sQ + (0 * 8 + r) * (128 * 8), crw[0], crw[1]);
+                    sts64(sQ + (1 * 8 + r) * (128 * 8), cbw[0], cbw[1]);
+                }
+                degrade_plane8(v, qp);
+#pragma unroll
+                for (int r = 0; r < 8; ++r)                            // quantised luma bytes -> plane 2
+                    sts64(sQ + (2 * 8 + r) * (128 * 8),
+                          out_byte_bits(v[r][0]) | (out_byte_bits(v[r][1]) << 8) | (out_byte_bits(v[r][2]) << 16) | (out_byte_bits(v[r][3]) << 24),
+                          out_byte_bits(v[r][4]) | (out_byte_bits(v[r][5]) << 8) | (out_byte_bits(v[r][6]) << 16) | (out_byte_bits(v[r][7]) << 24));
 #pragma unroll 1
-                for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k < 2; ++k) {                          // Cr, then Cb
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        uint32_t x[6];
+                        uint32_t x[2];
+                        lds64(sQ + (k * 8 + r) * (128 * 8), x[0], x[1]);
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) lds64(sW + r * (128 * 24) + 8 * i, x[2 * i], x[2 * i + 1]);
-                        uint32_t ya[4], yb[4];
-                        luma4_bits(x[0], x[1], x[2], ya);
-                        luma4_bits(x[3], x[4], x[5], yb);
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const int y = (int)((c < 4 ? ya[c] : yb[c - 4]) & 0xffu);
-                            int val = y;
-                            if (k == 1) val = sat8((((int)byte_at(x, 3 * c + 2) - y) * 11682 + (128 << 14) + 8192) >> 14);
-                            if (k == 2) val = sat8((((int)byte_at(x, 3 * c) - y) * 9241 + (128 << 14) + 8192) >> 14);
-                            v[r][c] = (float)(val - 128);
-                        }
+                        for (int c = 0; c < 8; ++c) v[r][c] = (float)((int)byte_at(x, c) - 128);
                     }
                     degrade_plane8(v, qp);
-                    if (k < 2) {
+                    if (k == 0) {
 #pragma unroll
                         for (int r = 0; r < 8; ++r)
-                            sts64(sQ + (k * 8 + r) * (128 * 8),
+                            sts64(sQ + r * (128 * 8),
                                   out_byte_bits(v[r][0]) | (out_byte_bits(v[r][1]) << 8) | (out_byte_bits(v[r][2]) << 16) | (out_byte_bits(v[r][3]) << 24),
                                   out_byte_bits(v[r][4]) | (out_byte_bits(v[r][5]) << 8) | (out_byte_bits(v[r][6]) << 16) | (out_byte_bits(v[r][7]) << 24));
                     }
                 }
-                // v now holds the quantised Cb plane (before the + 128 / clip / truncation)
+                // v now holds the quantised Cb plane (before the + 128 / clip / truncation), slot 0 the quantised Cr bytes
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    uint32_t qy[2], qr[2], gy[8];
-                    lds64(sQ + r * (128 * 8), qy[0], qy[1]);
-                    lds64(sQ + (8 + r) * (128 * 8), qr[0], qr[1]);
+                    uint32_t qr[2], qyr[2], gy[8];
+                    lds64(sQ + r * (128 * 8), qr[0], qr[1]);
+                    lds64(sQ + (2 * 8 + r) * (128 * 8), qyr[0], qyr[1]);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const int y = (int)byte_at(qy, c), cr = (int)byte_at(qr, c) - 128, cb = (int)out_byte_bits(v[r][c]) - 128;
+                        const int y = (int)byte_at(qyr, c), cr = (int)byte_at(qr, c) - 128, cb = (int)out_byte_bits(v[r][c]) - 128;
                         const int b = sat8(y + ((29049 * cb + 8192) >> 14));
                         const int gg = sat8(y + ((-5636 * cb - 11698 * cr + 8192) >> 14));
                         const int rr = sat8(y + ((22987 * cr + 8192) >> 14));
