@@ -418,33 +418,29 @@ k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
                 // into the slot it came from.
                 extern __shared__ __align__(16) uint8_t k8_smem[];
                 const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(k8_smem) + threadIdx.x * 8u;      // + (plane * 8 + row) * 128 * 8
-                float v[8][8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    uint32_t ya[4], yb[4], crw[2] = {0u, 0u}, cbw[2] = {0u, 0u};
+                    uint32_t ya[4], yb[4], yw[2] = {0u, 0u}, crw[2] = {0u, 0u}, cbw[2] = {0u, 0u};
                     luma4_bits(w[r][0], w[r][1], w[r][2], ya);
                     luma4_bits(w[r][3], w[r][4], w[r][5], yb);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const uint32_t yf = c < 4 ? ya[c] : yb[c - 4];
-                        const int y = (int)(yf & 0xffu);
+                        const int y = (int)((c < 4 ? ya[c] : yb[c - 4]) & 0xffu);
                         const int cr = sat8((((int)byte_at(w[r], 3 * c + 2) - y) * 11682 + (128 << 14) + 8192) >> 14);
                         const int cb = sat8((((int)byte_at(w[r], 3 * c) - y) * 9241 + (128 << 14) + 8192) >> 14);
+                        yw[c >> 2] |= (uint32_t)y << ((c & 3) * 8);
                         crw[c >> 2] |= (uint32_t)cr << ((c & 3) * 8);
                         cbw[c >> 2] |= (uint32_t)cb << ((c & 3) * 8);
-                        v[r][c] = __fsub_rn(__uint_as_float(yf), 8388736.0f);          // 2^23 + Y - (2^23 + 128)
                     }
-                    sts64(sQ + (0 * 8 + r) * (128 * 8), crw[0], crw[1]);
-                    sts64(sQ + (1 * 8 + r) * (128 * 8), cbw[0], cbw[1]);
+                    sts64(sQ + (0 * 8 + r) * (128 * 8), yw[0], yw[1]);
+                    sts64(sQ + (1 * 8 + r) * (128 * 8), crw[0], crw[1]);
+                    sts64(sQ + (2 * 8 + r) * (128 * 8), cbw[0], cbw[1]);
                 }
-                degrade_plane8(v, qp);
-#pragma unroll
-                for (int r = 0; r < 8; ++r)                            // quantised luma bytes -> plane 2
-                    sts64(sQ + (2 * 8 + r) * (128 * 8),
-                          out_byte_bits(v[r][0]) | (out_byte_bits(v[r][1]) << 8) | (out_byte_bits(v[r][2]) << 16) | (out_byte_bits(v[r][3]) << 24),
-                          out_byte_bits(v[r][4]) | (out_byte_bits(v[r][5]) << 8) | (out_byte_bits(v[r][6]) << 16) | (out_byte_bits(v[r][7]) << 24));
+                // one copy of the transform in the instruction stream (three inlined copies do not fit the instruction cache):
+                // every plane comes from and goes back to its shared-memory slot
 #pragma unroll 1
-                for (int k = 0; k < 2; ++k) {                          // Cr, then Cb
+                for (int k = 0; k < 3; ++k) {
+                    float v[8][8];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
                         uint32_t x[2];
@@ -453,23 +449,21 @@ k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
                         for (int c = 0; c < 8; ++c) v[r][c] = (float)((int)byte_at(x, c) - 128);
                     }
                     degrade_plane8(v, qp);
-                    if (k == 0) {
 #pragma unroll
-                        for (int r = 0; r < 8; ++r)
-                            sts64(sQ + r * (128 * 8),
-                                  out_byte_bits(v[r][0]) | (out_byte_bits(v[r][1]) << 8) | (out_byte_bits(v[r][2]) << 16) | (out_byte_bits(v[r][3]) << 24),
-                                  out_byte_bits(v[r][4]) | (out_byte_bits(v[r][5]) << 8) | (out_byte_bits(v[r][6]) << 16) | (out_byte_bits(v[r][7]) << 24));
-                    }
+                    for (int r = 0; r < 8; ++r)
+                        sts64(sQ + (k * 8 + r) * (128 * 8),
+                              out_byte_bits(v[r][0]) | (out_byte_bits(v[r][1]) << 8) | (out_byte_bits(v[r][2]) << 16) | (out_byte_bits(v[r][3]) << 24),
+                              out_byte_bits(v[r][4]) | (out_byte_bits(v[r][5]) << 8) | (out_byte_bits(v[r][6]) << 16) | (out_byte_bits(v[r][7]) << 24));
                 }
-                // v now holds the quantised Cb plane (before the + 128 / clip / truncation), slot 0 the quantised Cr bytes
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    uint32_t qr[2], qyr[2], gy[8];
-                    lds64(sQ + r * (128 * 8), qr[0], qr[1]);
-                    lds64(sQ + (2 * 8 + r) * (128 * 8), qyr[0], qyr[1]);
+                    uint32_t qyr[2], qr[2], qb[2], gy[8];
+                    lds64(sQ + (0 * 8 + r) * (128 * 8), qyr[0], qyr[1]);
+                    lds64(sQ + (1 * 8 + r) * (128 * 8), qr[0], qr[1]);
+                    lds64(sQ + (2 * 8 + r) * (128 * 8), qb[0], qb[1]);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const int y = (int)byte_at(qyr, c), cr = (int)byte_at(qr, c) - 128, cb = (int)out_byte_bits(v[r][c]) - 128;
+                        const int y = (int)byte_at(qyr, c), cr = (int)byte_at(qr, c) - 128, cb = (int)byte_at(qb, c) - 128;
                         const int b = sat8(y + ((29049 * cb + 8192) >> 14));
                         const int gg = sat8(y + ((-5636 * cb - 11698 * cr + 8192) >> 14));
                         const int rr = sat8(y + ((22987 * cr + 8192) >> 14));
