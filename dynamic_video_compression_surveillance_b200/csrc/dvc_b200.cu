@@ -965,7 +965,7 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         static const bool fuse_env = measure_env("DVC_FUSE_VOTE", 1) != 0;
         if (h->aligned && K <= 8 && h->gray_impl == 2 && fuse_env) {
             // K1 + K2 in one kernel (k_gray_diff_vote): long segments, each rebuilding its K - 1 frames of history
-            const int seg = std::max(K, 32), nsegf = (T + seg - 1) / seg;
+            const int seg = std::max(K, std::max(8, measure_env("DVC_FUSE_SEG", 64))), nsegf = (T + seg - 1) / seg;
             dim3 gf(g16, nsegf, S);
             ProfScope ps(h, DVC_PROF_FRONT, 1, st);
 #define DVC_VOTE_CASE(KK) case KK: k_gray_diff_vote<KK><<<gf, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, h->ring, wpr, h->ring_cap, h->n_masks, thr, seg, h->min_counts, bits_a); break;
