@@ -531,8 +531,16 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         if (bs == 8 && W % 8 == 0 && k8_env && ptr8 && q >= 0.01f && q <= 1.0e6f) {
             QuantP qp;
             for (int ne = 0; ne < 3; ++ne) { qp.rcp[ne] = 1.0f / q; qp.nqs[ne] = -q; qp.o[ne] = q; }     // no folded scalings in the 8-point path
-            if (flavour == DVC_DEGRADE_FD) k_degrade8<0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
-            else k_degrade8<1><<<grid, 128, K8_SMEM_MCO, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+            static const int minb = measure_env("DVC_K8_MINB", 4);
+            if (flavour == DVC_DEGRADE_FD) {
+                if (minb == 6) k_degrade8<0, 6><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+                else if (minb == 5) k_degrade8<0, 5><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+                else k_degrade8<0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+            } else {
+                if (minb == 6) k_degrade8<1, 6><<<grid, 128, K8_SMEM_MCO, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+                else if (minb == 5) k_degrade8<1, 5><<<grid, 128, K8_SMEM_MCO, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+                else k_degrade8<1><<<grid, 128, K8_SMEM_MCO, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+            }
         } else
         if (flavour == DVC_DEGRADE_FD && bs == 4)
             k_degrade_generic<4, 0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, q, counters);

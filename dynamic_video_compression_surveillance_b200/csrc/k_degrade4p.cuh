@@ -325,8 +325,8 @@ DEVI void degrade_plane8(float (&v)[8][8], const QuantP& qp) {
 // conflict-free) while the 64-float block of the plane in flight lives in registers.
 constexpr int K8_SMEM_MCO = 128 * (3 * 8 * 8);               // 24 576 bytes: three planes of 8 x 8 bytes per thread
 
-template <int FLAVOUR>
-__global__ void __launch_bounds__(128, 4)
+template <int FLAVOUR, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB)
 k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127, const uint32_t* __restrict__ nonzero,
            uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay, int H, int W, int wpr, QuantP qp,
            Counters* __restrict__ counters) {

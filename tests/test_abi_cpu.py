@@ -93,7 +93,7 @@ def test_packed_fp32_is_not_contracted(lib):
             if fn and "k_degrade8" in fn and (" " + op + " ") in line:
                 counts8.setdefault(fn, {}).setdefault(op, 0)
                 counts8[fn][op] += 1
-    assert len(counts8) == 2, "k_degrade8<0> and k_degrade8<1> expected"
+    assert len(counts8) >= 2, "k_degrade8<0, *> and k_degrade8<1, *> expected"
     for fn, c in counts8.items():
         copies = 1                                      # the mco flavour loops over its three planes: one copy of the transform
         assert (c.get("FFMA2"), c.get("FADD2"), c.get("FMUL")) == (304 * copies, 288 * copies, 32 * copies), (fn, c)
