@@ -531,16 +531,15 @@ static int launch_degrade(char* ERRBUF, const uint8_t* frames, const uint32_t* o
         if (bs == 8 && W % 8 == 0 && k8_env && ptr8 && q >= 0.01f && q <= 1.0e6f) {
             QuantP qp;
             for (int ne = 0; ne < 3; ++ne) { qp.rcp[ne] = 1.0f / q; qp.nqs[ne] = -q; qp.o[ne] = q; }     // no folded scalings in the 8-point path
-            static const int minb = measure_env("DVC_K8_MINB", 4);
-            if (flavour == DVC_DEGRADE_FD) {
-                if (minb == 6) k_degrade8<0, 6><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
-                else if (minb == 5) k_degrade8<0, 5><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
-                else k_degrade8<0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
-            } else {
-                if (minb == 6) k_degrade8<1, 6><<<grid, 128, K8_SMEM_MCO, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
-                else if (minb == 5) k_degrade8<1, 5><<<grid, 128, K8_SMEM_MCO, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
-                else k_degrade8<1><<<grid, 128, K8_SMEM_MCO, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+            static PerDeviceOnce k8_attr;
+            if (auto once = k8_attr.begin()) {
+                CU(cudaFuncSetAttribute(k_degrade8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, k8_smem_bytes<0>()));
+                CU(cudaFuncSetAttribute(k_degrade8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k8_smem_bytes<1>()));
+                once.commit();
             }
+            dim3 g8(cdiv((size_t)(W / 8) * (H / 8), K8_THREADS), n);
+            if (flavour == DVC_DEGRADE_FD) k_degrade8<0><<<g8, K8_THREADS, k8_smem_bytes<0>(), st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
+            else k_degrade8<1><<<g8, K8_THREADS, k8_smem_bytes<1>(), st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, qp, counters);
         } else
         if (flavour == DVC_DEGRADE_FD && bs == 4)
             k_degrade_generic<4, 0><<<grid, 128, 0, st>>>(frames, over127, nonzero, compressed, overlay, H, W, wpr, q, counters);
@@ -1182,11 +1181,27 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
 // ------------------------------------------------------------------------------------------------
 // stage-level entry points (stateless; scratch from the stream-ordered allocator)
 // ------------------------------------------------------------------------------------------------
+// The stream-ordered allocator's default pool gives memory back to the driver at every synchronisation point (release threshold
+// 0), which turns the scratch of a stage-level call into a fresh driver allocation each time (about 0.5 ms per call measured on
+// dvc_degrade_blend_u8).  Keep it cached: set once per device.
+static PerDeviceOnce g_pool_once;
+static void keep_async_pool_cached() {
+    if (auto once = g_pool_once.begin()) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        once.commit();
+    }
+}
+
 struct ScopedAsyncBuf {
     void* p = nullptr;
     cudaStream_t st;
     explicit ScopedAsyncBuf(cudaStream_t s) : st(s) {}
-    cudaError_t alloc(size_t n) { return cudaMallocAsync(&p, n ? n : 1, st); }
+    cudaError_t alloc(size_t n) { keep_async_pool_cached(); return cudaMallocAsync(&p, n ? n : 1, st); }
     ~ScopedAsyncBuf() { if (p) cudaFreeAsync(p, st); }
 };
 

@@ -317,16 +317,90 @@ DEVI void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t ba
 // YCrCb -> BGR -> gray, replicated).  The quotient d / q is the exact IEEE one (quantise_t, Markstein step); the 8x8
 // transform pair is the exact restatement of cv2's 2-D routine (k_dct8.cuh).
 // ------------------------------------------------------------------------------------------------
-DEVI void degrade_plane8(float (&v)[8][8], const QuantP& qp) {
-    degrade_block8_packed(v, [&qp](P2 d) { return quantise_t<0, false>(d, qp); });
+// The 8x8 transform pair of one plane with the block staged in shared memory and every pass a ROLLED loop (two rows or two
+// columns per trip on the packed pipe).  Fully unrolled in registers the kernel was 7 800 instructions (124 KB) of straight-line
+// code and spent most of its time waiting for instruction fetch (ncu: "no_instructions" 60 % of all stall samples, 34 % FP pipe);
+// rolled, the hot code is a few hundred instructions and the 64 floats no longer pin 128 registers.
+//   sBlk   shared-memory address of this thread's float block: element (r, c) at 4 * (r * 8 + c); threads are K8_BLK_STRIDE
+//          bytes apart (66 words: 64-bit accesses of a half-warp touch all 32 banks once)
+//   sPl    shared-memory address of row 0 of the byte plane (in: pixels, out: result), rows K8_ROW_STRIDE bytes apart
+constexpr int K8_THREADS = 128;
+constexpr uint32_t K8_BLK_STRIDE = 66 * 4, K8_ROW_STRIDE = K8_THREADS * 8;
+template <int FLAVOUR> constexpr int k8_smem_bytes() { return K8_THREADS * (66 * 4 + (FLAVOUR == 1 ? 3 : 1) * 64); }
+
+DEVI P2 lds_p2(uint32_t saddr) { P2 r; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r.v) : "r"(saddr)); return r; }
+DEVI void sts_p2(uint32_t saddr, P2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(saddr), "l"(v.v) : "memory"); }
+DEVI void sts_u16(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory"); }
+
+DEVI void degrade_plane8_smem(uint32_t sBlk, uint32_t sPl, const QuantP& qp) {
+    // forward rows: bytes -> (value - 128) -> row transform, rows 2i and 2i + 1 in the two lanes
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        uint32_t x0[2], x1[2];
+        lds64(sPl + (2 * i) * K8_ROW_STRIDE, x0[0], x0[1]);
+        lds64(sPl + (2 * i + 1) * K8_ROW_STRIDE, x1[0], x1[1]);
+        P2 rp[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rp[c] = p2((float)((int)byte_at(x0, c) - 128), (float)((int)byte_at(x1, c) - 128));
+        dct8x8_row_fwd_t(rp);
+        float lo[8], hi[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) unp2(rp[c], lo[c], hi[c]);
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            sts_p2(sBlk + 4 * ((2 * i) * 8 + c), p2(lo[c], lo[c + 1]));
+            sts_p2(sBlk + 4 * ((2 * i + 1) * 8 + c), p2(hi[c], hi[c + 1]));
+        }
+    }
+    // forward columns (2j, 2j + 1 in the two lanes), quantiser, the inverse's row scale
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        P2 cp[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) cp[r] = lds_p2(sBlk + 4 * (r * 8 + 2 * j));
+        dct8x8_col_fwd_t(cp[0], cp[1], cp[2], cp[3], cp[4], cp[5], cp[6], cp[7]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sts_p2(sBlk + 4 * (r * 8 + 2 * j), mul(quantise_t<0, false>(cp[r], qp), splat<P2>(dct8_rowscale(r))));
+    }
+    // inverse rows
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        float a[8], b[8];
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            unp2(lds_p2(sBlk + 4 * ((2 * i) * 8 + c)), a[c], a[c + 1]);
+            unp2(lds_p2(sBlk + 4 * ((2 * i + 1) * 8 + c)), b[c], b[c + 1]);
+        }
+        P2 rp[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rp[c] = p2(a[c], b[c]);
+        dct8x8_row_inv_t(rp);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) unp2(rp[c], a[c], b[c]);
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            sts_p2(sBlk + 4 * ((2 * i) * 8 + c), p2(a[c], a[c + 1]));
+            sts_p2(sBlk + 4 * ((2 * i + 1) * 8 + c), p2(b[c], b[c + 1]));
+        }
+    }
+    // inverse columns, + 128, clip, truncate: two result bytes per row go back into the byte plane
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        P2 cp[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) cp[r] = lds_p2(sBlk + 4 * (r * 8 + 2 * j));
+        dct8x8_col_inv_t(cp[0], cp[1], cp[2], cp[3], cp[4], cp[5], cp[6], cp[7]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float lo, hi;
+            unp2(cp[r], lo, hi);
+            sts_u16(sPl + r * K8_ROW_STRIDE + 2 * j, out_byte_bits(lo) | (out_byte_bits(hi) << 8));
+        }
+    }
 }
 
-// MCO parks the Cr / Cb bytes of the block (later the quantised Cr bytes) in shared memory ([plane][row][thread] x 8 bytes,
-// conflict-free) while the 64-float block of the plane in flight lives in registers.
-constexpr int K8_SMEM_MCO = 128 * (3 * 8 * 8);               // 24 576 bytes: three planes of 8 x 8 bytes per thread
-
-template <int FLAVOUR, int MINB = 4>
-__global__ void __launch_bounds__(128, MINB)
+template <int FLAVOUR>
+__global__ void __launch_bounds__(K8_THREADS)
 k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over127, const uint32_t* __restrict__ nonzero,
            uint8_t* __restrict__ compressed, uint8_t* __restrict__ overlay, int H, int W, int wpr, QuantP qp,
            Counters* __restrict__ counters) {
@@ -390,94 +464,79 @@ k_degrade8(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ over
 #pragma unroll
                     for (int i = 0; i < 6; ++i) w[r][i] = o[i];
                 }
-            } else if (FLAVOUR == 0) {
-                float v[8][8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    uint32_t ya[4], yb[4];
-                    luma4_bits(w[r][0], w[r][1], w[r][2], ya);
-                    luma4_bits(w[r][3], w[r][4], w[r][5], yb);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        v[r][c] = __fsub_rn(__uint_as_float(ya[c]), 8388736.0f);
-                        v[r][4 + c] = __fsub_rn(__uint_as_float(yb[c]), 8388736.0f);
-                    }
-                }
-                degrade_plane8(v, qp);
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    grey4_words(out_byte_bits(v[r][0]), out_byte_bits(v[r][1]), out_byte_bits(v[r][2]), out_byte_bits(v[r][3]),
-                                w[r][0], w[r][1], w[r][2]);
-                    grey4_words(out_byte_bits(v[r][4]), out_byte_bits(v[r][5]), out_byte_bits(v[r][6]), out_byte_bits(v[r][7]),
-                                w[r][3], w[r][4], w[r][5]);
-                }
             } else {
-                // MCO: quantise Y, Cr, Cb (motion_compression_opt.py:162-168); YCrCb -> BGR (:171); BGR -> gray, replicated (:181-183).
-                // One pass over the pixels builds the luma block in registers and parks the Cr / Cb bytes in shared memory
-                // ([plane][row][thread] x 8 bytes: conflict-free); each plane is transformed in turn, its result bytes going back
-                // into the slot it came from.
+                // Static block.  Every stage is a rolled loop over rows (the pixel words are parked in this thread's float-block
+                // area, which the transform only needs afterwards), so the hot code stays small enough for the instruction cache.
                 extern __shared__ __align__(16) uint8_t k8_smem[];
-                const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(k8_smem) + threadIdx.x * 8u;      // + (plane * 8 + row) * 128 * 8
+                const uint32_t sBlk = (uint32_t)__cvta_generic_to_shared(k8_smem) + threadIdx.x * K8_BLK_STRIDE;
+                const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(k8_smem) + K8_THREADS * K8_BLK_STRIDE + threadIdx.x * 8u;   // + (plane * 8 + row) * K8_ROW_STRIDE
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    uint32_t ya[4], yb[4], yw[2] = {0u, 0u}, crw[2] = {0u, 0u}, cbw[2] = {0u, 0u};
-                    luma4_bits(w[r][0], w[r][1], w[r][2], ya);
-                    luma4_bits(w[r][3], w[r][4], w[r][5], yb);
+                for (int r = 0; r < 8; ++r)
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int y = (int)((c < 4 ? ya[c] : yb[c - 4]) & 0xffu);
-                        const int cr = sat8((((int)byte_at(w[r], 3 * c + 2) - y) * 11682 + (128 << 14) + 8192) >> 14);
-                        const int cb = sat8((((int)byte_at(w[r], 3 * c) - y) * 9241 + (128 << 14) + 8192) >> 14);
-                        yw[c >> 2] |= (uint32_t)y << ((c & 3) * 8);
-                        crw[c >> 2] |= (uint32_t)cr << ((c & 3) * 8);
-                        cbw[c >> 2] |= (uint32_t)cb << ((c & 3) * 8);
-                    }
-                    sts64(sQ + (0 * 8 + r) * (128 * 8), yw[0], yw[1]);
-                    sts64(sQ + (1 * 8 + r) * (128 * 8), crw[0], crw[1]);
-                    sts64(sQ + (2 * 8 + r) * (128 * 8), cbw[0], cbw[1]);
-                }
-                // one copy of the transform in the instruction stream (three inlined copies do not fit the instruction cache):
-                // every plane comes from and goes back to its shared-memory slot
+                    for (int i = 0; i < 3; ++i) sts64(sBlk + r * 24 + 8 * i, w[r][2 * i], w[r][2 * i + 1]);
+                // pixels -> byte planes: Y (fd:115-116), and Cr, Cb for the MCO flavour (mco:152-153)
 #pragma unroll 1
-                for (int k = 0; k < 3; ++k) {
-                    float v[8][8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        uint32_t x[2];
-                        lds64(sQ + (k * 8 + r) * (128 * 8), x[0], x[1]);
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) v[r][c] = (float)((int)byte_at(x, c) - 128);
-                    }
-                    degrade_plane8(v, qp);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        sts64(sQ + (k * 8 + r) * (128 * 8),
-                              out_byte_bits(v[r][0]) | (out_byte_bits(v[r][1]) << 8) | (out_byte_bits(v[r][2]) << 16) | (out_byte_bits(v[r][3]) << 24),
-                              out_byte_bits(v[r][4]) | (out_byte_bits(v[r][5]) << 8) | (out_byte_bits(v[r][6]) << 16) | (out_byte_bits(v[r][7]) << 24));
-                }
-#pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    uint32_t qyr[2], qr[2], qb[2], gy[8];
-                    lds64(sQ + (0 * 8 + r) * (128 * 8), qyr[0], qyr[1]);
-                    lds64(sQ + (1 * 8 + r) * (128 * 8), qr[0], qr[1]);
-                    lds64(sQ + (2 * 8 + r) * (128 * 8), qb[0], qb[1]);
+                    uint32_t x[6], ya[4], yb[4];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int y = (int)byte_at(qyr, c), cr = (int)byte_at(qr, c) - 128, cb = (int)byte_at(qb, c) - 128;
-                        const int b = sat8(y + ((29049 * cb + 8192) >> 14));
-                        const int gg = sat8(y + ((-5636 * cb - 11698 * cr + 8192) >> 14));
-                        const int rr = sat8(y + ((22987 * cr + 8192) >> 14));
-                        gy[c] = gray_of(b, gg, rr);
+                    for (int i = 0; i < 3; ++i) lds64(sBlk + r * 24 + 8 * i, x[2 * i], x[2 * i + 1]);
+                    luma4_bits(x[0], x[1], x[2], ya);
+                    luma4_bits(x[3], x[4], x[5], yb);
+                    sts64(sQ + r * K8_ROW_STRIDE,
+                          (ya[0] & 0xffu) | ((ya[1] & 0xffu) << 8) | ((ya[2] & 0xffu) << 16) | (ya[3] << 24),
+                          (yb[0] & 0xffu) | ((yb[1] & 0xffu) << 8) | ((yb[2] & 0xffu) << 16) | (yb[3] << 24));
+                    if (FLAVOUR == 1) {
+                        uint32_t crw[2] = {0u, 0u}, cbw[2] = {0u, 0u};
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int y = (int)((c < 4 ? ya[c] : yb[c - 4]) & 0xffu);
+                            const int cr = sat8((((int)byte_at(x, 3 * c + 2) - y) * 11682 + (128 << 14) + 8192) >> 14);
+                            const int cb = sat8((((int)byte_at(x, 3 * c) - y) * 9241 + (128 << 14) + 8192) >> 14);
+                            crw[c >> 2] |= (uint32_t)cr << ((c & 3) * 8);
+                            cbw[c >> 2] |= (uint32_t)cb << ((c & 3) * 8);
+                        }
+                        sts64(sQ + (8 + r) * K8_ROW_STRIDE, crw[0], crw[1]);
+                        sts64(sQ + (16 + r) * K8_ROW_STRIDE, cbw[0], cbw[1]);
                     }
-                    grey4_words(gy[0], gy[1], gy[2], gy[3], w[r][0], w[r][1], w[r][2]);
-                    grey4_words(gy[4], gy[5], gy[6], gy[7], w[r][3], w[r][4], w[r][5]);
+                }
+                // quantise the plane(s): motion_compression_opt.py:162-168 does Y, Cr and Cb, frame_differencing.py:121-125 only Y
+#pragma unroll 1
+                for (int k = 0; k < (FLAVOUR == 1 ? 3 : 1); ++k) degrade_plane8_smem(sBlk, sQ + (k * 8) * K8_ROW_STRIDE, qp);
+                // planes -> output pixels, stored row by row: grey Y' (fd: chroma 128, :126-130) or YCrCb -> BGR -> gray (mco:171,181-183)
+#pragma unroll 1
+                for (int r = 0; r < 8; ++r) {
+                    uint32_t qy[2], gy[8], o[6];
+                    lds64(sQ + r * K8_ROW_STRIDE, qy[0], qy[1]);
+                    if (FLAVOUR == 1) {
+                        uint32_t qr[2], qb[2];
+                        lds64(sQ + (8 + r) * K8_ROW_STRIDE, qr[0], qr[1]);
+                        lds64(sQ + (16 + r) * K8_ROW_STRIDE, qb[0], qb[1]);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int y = (int)byte_at(qy, c), cr = (int)byte_at(qr, c) - 128, cb = (int)byte_at(qb, c) - 128;
+                            const int b = sat8(y + ((29049 * cb + 8192) >> 14));
+                            const int gg = sat8(y + ((-5636 * cb - 11698 * cr + 8192) >> 14));
+                            const int rr = sat8(y + ((22987 * cr + 8192) >> 14));
+                            gy[c] = gray_of(b, gg, rr);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) gy[c] = byte_at(qy, c);
+                    }
+                    grey4_words(gy[0], gy[1], gy[2], gy[3], o[0], o[1], o[2]);
+                    grey4_words(gy[4], gy[5], gy[6], gy[7], o[3], o[4], o[5]);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        __stcs(reinterpret_cast<uint2*>(compressed + base + r * pitch + 8 * i), make_uint2(o[2 * i], o[2 * i + 1]));
                 }
             }
+            if (!is_static) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+                for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    __stcs(reinterpret_cast<uint2*>(compressed + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
+                    for (int i = 0; i < 3; ++i)
+                        __stcs(reinterpret_cast<uint2*>(compressed + base + r * pitch + 8 * i), make_uint2(w[r][2 * i], w[r][2 * i + 1]));
+            }
         }
     }
     if (counters) {
