@@ -14,6 +14,7 @@
 
 #include "../../include/dvc_b200.h"
 #include "k_ccl.cuh"
+#include "k_ccl_sweep.cuh"
 #include "k_degrade.cuh"
 #include "k_degrade4p.cuh"
 #include "k_front.cuh"
@@ -233,13 +234,54 @@ static int launch_morph_chain(char* ERRBUF, const uint32_t* src, uint32_t* dst, 
 }
 
 struct CclScratch {
-    // union-find storage per frame (k_ccl.cuh): dense slot-0 arrays [plane_words + 1] and overflow arrays
-    // [plane_words * 15], for the phase A parents, the phase B parents and the phase B areas
+    // first generation (k_ccl.cuh; frames wider than 8192 pixels and the measure flavour's A/B switch): union-find storage per
+    // frame, dense slot-0 arrays [plane_words + 1] and overflow arrays [plane_words * 15], for the phase A parents, the phase B
+    // parents and the phase B areas
     int *pa0 = nullptr, *paov = nullptr, *pb0 = nullptr, *pbov = nullptr, *ar0 = nullptr, *arov = nullptr;
     uint8_t* rowflag = nullptr;   // [frames][H]: the row holds foreground (written by the first kernel, read by the other six)
-    uint32_t* filled = nullptr;  // [frames] planes
+    uint32_t* filled = nullptr;  // [frames] planes: F of the first generation
+    // sweep kernel (k_ccl_sweep.cuh): node arrays of frames with more than SW_CAP row runs, [frames][g_stride] each
+    int *gp = nullptr, *ga = nullptr;
+    size_t g_stride = 0;
+    bool sweep = false;
     int frames = 0;
 };
+
+static PerDeviceOnce g_sweep_once;
+static int g_sweep_smem_limit = 0;
+
+// the sweep kernel takes rows of up to 4 x 2048 pixels and needs (H + 1) row bases in shared memory
+static bool ccl_sweep_usable(int H, int W) {
+    static const bool on = measure_env("DVC_CCL_SWEEP", 1) != 0;
+    return on && W <= 8192 && ccl_sweep_smem_bytes(H, W) <= 200 * 1024;
+}
+
+static int launch_contour_sweep(char* ERRBUF, const uint32_t* raw, uint32_t* out, int n, int H, int W, int thr,
+                                const CclScratch& sc, cudaStream_t st) {
+    if (auto once = g_sweep_once.begin()) {
+        int dev = 0, lim = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        CU(cudaFuncSetAttribute(k_ccl_sweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 1024));
+        CU(cudaFuncSetAttribute(k_ccl_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 1024));
+        CU(cudaFuncSetAttribute(k_ccl_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 1024));
+        g_sweep_smem_limit = lim;
+        once.commit();
+    }
+    const int wpr = words_per_row(W);
+    const size_t pw = (size_t)H * wpr, smem = ccl_sweep_smem_bytes(H, W);
+    if (smem + 2048 > (size_t)g_sweep_smem_limit) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "contour filter: %d rows do not fit in shared memory", H);
+    for (int i0 = 0; i0 < n; i0 += sc.frames) {
+        const int m = std::min(sc.frames, n - i0);
+        const uint32_t* r = raw + (size_t)i0 * pw;
+        uint32_t* o = out + (size_t)i0 * pw;
+        if (W <= 2048) k_ccl_sweep<1><<<m, SW_THREADS, smem, st>>>(r, o, sc.gp, sc.ga, sc.g_stride, H, W, wpr, thr);
+        else if (W <= 4096) k_ccl_sweep<2><<<m, SW_THREADS, smem, st>>>(r, o, sc.gp, sc.ga, sc.g_stride, H, W, wpr, thr);
+        else k_ccl_sweep<4><<<m, SW_THREADS, smem, st>>>(r, o, sc.gp, sc.ga, sc.g_stride, H, W, wpr, thr);
+        CHECK_LAUNCH();
+    }
+    return DVC_OK;
+}
 
 static int launch_contour_filter(char* ERRBUF, const uint32_t* raw, uint32_t* out, int n, int H, int W,
                                  double min_area, const CclScratch& sc, cudaStream_t st) {
@@ -247,6 +289,7 @@ static int launch_contour_filter(char* ERRBUF, const uint32_t* raw, uint32_t* ou
     const size_t pw = (size_t)H * wpr;
     const double t2 = std::floor(2.0 * min_area);
     const int thr = t2 >= 2147483647.0 ? 2147483647 : (t2 < -1.0 ? -1 : (int)t2);
+    if (sc.sweep) return launch_contour_sweep(ERRBUF, raw, out, n, H, W, thr, sc, st);
     for (int i0 = 0; i0 < n; i0 += sc.frames) {
         const int m = std::min(sc.frames, n - i0);
         dim3 grid(cdiv(pw, 256), m);
@@ -273,19 +316,28 @@ static size_t ccl_overflow_ints(int H, int W) { return (size_t)H * words_per_row
 // A dense + overflow pair shares one allocation (uf_addr reaches the overflow part through a 32-bit offset from the dense one).
 static int ccl_scratch_alloc(char* ERRBUF, CclScratch& sc, int frames, int H, int W) {
     const size_t pw = (size_t)H * words_per_row(W);
+    sc.frames = frames;
+    sc.sweep = ccl_sweep_usable(H, W);
+    if (!sc.sweep) CU(cudaMalloc(&sc.filled, pw * 4 * frames));
+    if (sc.sweep) {
+        sc.g_stride = ccl_sweep_max_nodes(H, W);
+        if (sc.g_stride >= 0x7fffffffull) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "contour filter scratch exceeds 2^31 nodes");
+        CU(cudaMalloc(&sc.gp, sc.g_stride * sizeof(int) * frames));
+        CU(cudaMalloc(&sc.ga, sc.g_stride * sizeof(int) * frames));
+        return DVC_OK;
+    }
     const size_t d = ccl_dense_ints(H, W) * sizeof(int) * frames, o = ccl_overflow_ints(H, W) * sizeof(int) * frames;
     if ((d + o) / sizeof(int) >= 0x7fffffffull) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "contour filter scratch exceeds 2^31 nodes");
-    sc.frames = frames;
     CU(cudaMalloc(&sc.pa0, d + o)); sc.paov = sc.pa0 + d / sizeof(int);
     CU(cudaMalloc(&sc.pb0, d + o)); sc.pbov = sc.pb0 + d / sizeof(int);
     CU(cudaMalloc(&sc.ar0, d + o)); sc.arov = sc.ar0 + d / sizeof(int);
-    CU(cudaMalloc(&sc.filled, pw * 4 * frames));
     CU(cudaMalloc(&sc.rowflag, (size_t)frames * H));
     return DVC_OK;
 }
 static void ccl_scratch_free(CclScratch& sc) {
     cudaFree(sc.pa0); cudaFree(sc.pb0); cudaFree(sc.ar0);
     cudaFree(sc.filled); cudaFree(sc.rowflag);
+    cudaFree(sc.gp); cudaFree(sc.ga);
     sc = CclScratch();
 }
 
@@ -1032,7 +1084,7 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         CHECK_LAUNCH();
         h->cur ^= 1;
         int rc;
-        { ProfScope ps(h, DVC_PROF_CCL, 7 * ((ST + h->ccl.frames - 1) / h->ccl.frames), st);
+        { ProfScope ps(h, DVC_PROF_CCL, (h->ccl.sweep ? 1 : 7) * ((ST + h->ccl.frames - 1) / h->ccl.frames), st);
         rc = launch_contour_filter(h->err, bits_a, bits_b, ST, H, W, h->cfg.min_area, h->ccl, st);
         }
         if (rc) return rc;
@@ -1359,18 +1411,26 @@ extern "C" int dvc_contour_filter_u8(const uint8_t* src, uint8_t* dst, int32_t n
     if (!src || !dst) return set_err(nullptr, DVC_ERR_INVALID, "dvc_contour_filter_u8: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t pw = (size_t)H * words_per_row(W);
-    const int fr = std::min(n, 8);
+    CclScratch sc;
+    sc.sweep = ccl_sweep_usable(H, W);
+    const int fr = std::min(n, sc.sweep ? 32 : 8);
     const size_t d = ccl_dense_ints(H, W) * sizeof(int) * fr, o = ccl_overflow_ints(H, W) * sizeof(int) * fr;
     ScopedAsyncBuf a(st), b(st), pa(st), pb(st), ar(st), fl(st), rfl(st);
     CU(a.alloc(pw * 4 * n));
     CU(b.alloc(pw * 4 * n));
-    CU(pa.alloc(d + o)); CU(pb.alloc(d + o)); CU(ar.alloc(d + o));      // dense + overflow pairs, one allocation each
-    CU(fl.alloc(pw * 4 * fr));
-    CU(rfl.alloc((size_t)fr * H));
-    CclScratch sc;
-    sc.rowflag = (uint8_t*)rfl.p;
-    sc.pa0 = (int*)pa.p; sc.paov = sc.pa0 + d / sizeof(int); sc.pb0 = (int*)pb.p; sc.pbov = sc.pb0 + d / sizeof(int);
-    sc.ar0 = (int*)ar.p; sc.arov = sc.ar0 + d / sizeof(int); sc.filled = (uint32_t*)fl.p; sc.frames = fr;
+    sc.frames = fr;
+    if (!sc.sweep) { CU(fl.alloc(pw * 4 * fr)); sc.filled = (uint32_t*)fl.p; }
+    if (sc.sweep) {
+        sc.g_stride = ccl_sweep_max_nodes(H, W);
+        CU(pa.alloc(sc.g_stride * sizeof(int) * fr)); CU(pb.alloc(sc.g_stride * sizeof(int) * fr));
+        sc.gp = (int*)pa.p; sc.ga = (int*)pb.p;
+    } else {
+        CU(pa.alloc(d + o)); CU(pb.alloc(d + o)); CU(ar.alloc(d + o));      // dense + overflow pairs, one allocation each
+        CU(rfl.alloc((size_t)fr * H));
+        sc.rowflag = (uint8_t*)rfl.p;
+        sc.pa0 = (int*)pa.p; sc.paov = sc.pa0 + d / sizeof(int); sc.pb0 = (int*)pb.p; sc.pbov = sc.pb0 + d / sizeof(int);
+        sc.ar0 = (int*)ar.p; sc.arov = sc.ar0 + d / sizeof(int);
+    }
     rc = pack_to_bits(src, (uint32_t*)a.p, n, H, W, st);
     if (rc) return rc;
     rc = launch_contour_filter(nullptr, (const uint32_t*)a.p, (uint32_t*)b.p, n, H, W, min_area, sc, st);

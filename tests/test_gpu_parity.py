@@ -274,6 +274,65 @@ def test_contour_filter_1080p_blobs(P):
     assert np.array_equal(got, so.contour_filter_cv2(m, 500))
 
 
+def _serpentine(h, w, r, gaps=1):
+    """Walls on every other row with one opening at alternating ends: the background is one long corridor, so the flood of
+    the contour filter's phase A has to travel every row (many sweep iterations), plus a little noise."""
+    m = np.zeros((h, w), np.uint8)
+    for y in range(1, h, 2):
+        m[y, :] = 255
+        m[y, (w - 1) if (y // 2) % 2 else 0] = 0
+    noise = r.random((h, w)) < 0.01
+    m[noise] = 255 - m[noise]
+    return m
+
+
+@pytest.mark.parametrize("shape", [(40, 2100), (23, 4200), (9, 1999), (300, 700), (200, 300), (1, 1), (2, 130), (17, 64), (33, 65)])
+def test_contour_filter_sweep_cases(P, shape):
+    """Shapes and masks aimed at the one-launch sweep kernel (k_ccl_sweep.cuh): rows of two and four 64-bit words per lane,
+    fewer rows than warps, runs and holes across word boundaries, long flood paths, more row runs than fit in shared
+    memory (dense noise: global node arrays), and more frames than one launch takes."""
+    r = rng(31)
+    h, w = shape
+    masks = [_blob_mask(r, shape, int(r.integers(3, 30))) for _ in range(3)]
+    masks += [(r.random(shape) < d).astype(np.uint8) * 255 for d in (0.45, 0.7)]
+    masks.append(_serpentine(h, w, r))
+    ring = np.zeros(shape, np.uint8)                      # nested frames: holes inside holes, edges on word boundaries
+    for k in range(0, min(h, w) // 2, 3):
+        ring[k:h - k, k:w - k] = 255 if (k // 3) % 2 == 0 else 0
+    masks.append(ring)
+    bars = np.zeros(shape, np.uint8)                      # runs that start / end exactly at 64-pixel boundaries
+    bars[::3, 64 * (w // 128):] = 255
+    bars[1::3, :64 * (w // 128 + 1)] = 255
+    masks.append(bars)
+    masks = np.stack(masks)
+    for min_area in (0, 3, 50):
+        got = host(P.contour_filter(dev(masks), min_area))
+        for i in range(len(masks)):
+            assert np.array_equal(got[i], so.contour_filter_cv2(masks[i], min_area)), (shape, i, min_area)
+
+
+def test_contour_filter_many_frames(P):
+    r = rng(32)
+    masks = np.stack([_blob_mask(r, (50, 90), int(r.integers(1, 9))) for _ in range(75)])
+    got = host(P.contour_filter(dev(masks), 4))
+    for i in range(len(masks)):
+        assert np.array_equal(got[i], so.contour_filter_cv2(masks[i], 4)), i
+
+
+def test_contour_filter_1080p_frames_and_noise(P):
+    """The bench's kind of mask (outlines of rectangles: big holes) and dense noise at full size."""
+    r = rng(33)
+    a = np.zeros((1080, 1920), np.uint8)
+    for (x, y, ww, hh) in ((100, 50, 240, 135), (300, 120, 256, 143), (1500, 800, 272, 151), (900, 400, 288, 159), (0, 900, 200, 180)):
+        a[y:y + hh, x:x + ww] = 255
+        a[y + 6:y + hh - 6, x + 8:x + ww - 8] = 0
+    b = (r.random((1080, 1920)) < 0.5).astype(np.uint8) * 255
+    c = _serpentine(1080, 1920, r)
+    for m, min_area in ((a, 500), (b, 2), (c, 500)):
+        got = host(P.contour_filter(dev(m[None]), min_area))[0]
+        assert np.array_equal(got, so.contour_filter_cv2(m, min_area))
+
+
 def _exact(bs, h=None, w=None):
     """Does this host's cv2 follow the recovered float32 sequences for every block shape a (h, w) frame cut into
     bs x bs blocks produces?  (True on the AVX-512 IPP build of the image; when False the tests fall back to the
