@@ -270,14 +270,15 @@ static int launch_contour_sweep(char* ERRBUF, const uint32_t* raw, uint32_t* out
     }
     const int wpr = words_per_row(W);
     const size_t pw = (size_t)H * wpr, smem = ccl_sweep_smem_bytes(H, W);
+    static const int chunk_rows = std::max(1, measure_env("DVC_CCL_ROWS", 16));     // consecutive rows a warp sweeps in one go
     if (smem + 2048 > (size_t)g_sweep_smem_limit) return set_err(ERRBUF, DVC_ERR_UNSUPPORTED, "contour filter: %d rows do not fit in shared memory", H);
     for (int i0 = 0; i0 < n; i0 += sc.frames) {
         const int m = std::min(sc.frames, n - i0);
         const uint32_t* r = raw + (size_t)i0 * pw;
         uint32_t* o = out + (size_t)i0 * pw;
-        if (W <= 2048) k_ccl_sweep<1><<<m, SW_THREADS, smem, st>>>(r, o, sc.gp, sc.ga, sc.g_stride, H, W, wpr, thr);
-        else if (W <= 4096) k_ccl_sweep<2><<<m, SW_THREADS, smem, st>>>(r, o, sc.gp, sc.ga, sc.g_stride, H, W, wpr, thr);
-        else k_ccl_sweep<4><<<m, SW_THREADS, smem, st>>>(r, o, sc.gp, sc.ga, sc.g_stride, H, W, wpr, thr);
+        if (W <= 2048) k_ccl_sweep<1><<<m, SW_THREADS, smem, st>>>(r, o, sc.gp, sc.ga, sc.g_stride, H, W, wpr, thr, chunk_rows);
+        else if (W <= 4096) k_ccl_sweep<2><<<m, SW_THREADS, smem, st>>>(r, o, sc.gp, sc.ga, sc.g_stride, H, W, wpr, thr, chunk_rows);
+        else k_ccl_sweep<4><<<m, SW_THREADS, smem, st>>>(r, o, sc.gp, sc.ga, sc.g_stride, H, W, wpr, thr, chunk_rows);
         CHECK_LAUNCH();
     }
     return DVC_OK;

@@ -118,16 +118,19 @@ DEVI int sw_row_meta(const uint64_t (&c)[NW], int lane, RowMeta<NW>& m) {
         m.pre[k] = cnt;
         cnt += __popcll(m.st[k]);
     }
-    int inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(SW_FULL, inc, o);
-        if (lane >= o) inc += t;
+    // exclusive prefix of cnt over the lanes, one ballot per bit of the counts (most rows: one or two bits); the ballots do not
+    // depend on each other, a shuffle scan is five dependent steps
+    const unsigned bits_used = __reduce_or_sync(SW_FULL, (unsigned)cnt);
+    const unsigned below = (1u << lane) - 1u;
+    int ex = 0, total = 0;
+    for (int b = 0; (bits_used >> b) != 0u; ++b) {
+        const unsigned mb = __ballot_sync(SW_FULL, (cnt >> b) & 1);
+        ex += __popc(mb & below) << b;
+        total += __popc(mb) << b;
     }
-    const int ex = inc - cnt;
 #pragma unroll
     for (int k = 0; k < NW; ++k) m.pre[k] += ex;
-    return __shfl_sync(SW_FULL, inc, 31);
+    return total;
 }
 template <int NW>
 DEVI int sw_node_of(const RowMeta<NW>& m, int k, int base, int bit) {
@@ -248,7 +251,6 @@ DEVI void sw_holes(int* P, const uint64_t (&b)[NW], const RowMeta<NW>& m, int ba
     }
 }
 
-constexpr int SW_CHUNK = 16;                        // consecutive rows a warp sweeps in one go
 constexpr int SW_PHASES = 4;
 
 struct SwShared {
@@ -260,6 +262,7 @@ struct SwShared {
     int* counter;             // next free node id
     int* overflow;            // a row did not get its ids: redo the phase with the global arrays
     int* next;                // [SW_PHASES] next chunk of rows to hand out
+    int chunk;                // consecutive rows a warp sweeps in one go
 };
 
 // chunks of rows are handed out dynamically: rows with foreground cluster, a static split leaves most warps at the barrier
@@ -293,13 +296,13 @@ template <int NW, bool G>
 DEVI void sw_phase_a(const SwShared& sh, int* P, const uint32_t* __restrict__ M, uint32_t* out, int H, int W, int wpr,
                      int ndw, int maxr, const uint64_t (&vm)[NW]) {
     const int lane = threadIdx.x & 31;
-    const int nchunks = (H + SW_CHUNK - 1) / SW_CHUNK;
+    const int nchunks = (H + sh.chunk - 1) / sh.chunk;
     const int last_d = (W - 1) >> 6, last_bit = (W - 1) & 63;
     uint64_t zero[NW];
 #pragma unroll
     for (int k = 0; k < NW; ++k) zero[k] = 0ull;
     for (int c = sw_next_chunk(sh.next + 0, lane); c < nchunks; c = sw_next_chunk(sh.next + 0, lane)) {
-        const int ya = c * SW_CHUNK, yb = min(H, ya + SW_CHUNK);
+        const int ya = c * sh.chunk, yb = min(H, ya + sh.chunk);
         uint64_t cur[NW], nxt[NW], u[NW];
         RowMeta<NW> um;
         int ub = 0;
@@ -360,9 +363,9 @@ template <int NW, bool G>
 DEVI void sw_seams_a(const SwShared& sh, int* P, const uint32_t* __restrict__ M, int H, int wpr, int ndw, int maxr,
                      const uint64_t (&vm)[NW]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunks = (H + SW_CHUNK - 1) / SW_CHUNK;
+    const int nchunks = (H + sh.chunk - 1) / sh.chunk;
     for (int c = 1 + warp; c < nchunks; c += SW_WARPS) {
-        const int yb = c * SW_CHUNK;
+        const int yb = c * sh.chunk;
         const bool up = sh.rowst[yb - 1] & 1, cu = sh.rowst[yb] & 1;
         if (!up && !cu) continue;
         uint64_t u[NW], w[NW];
@@ -389,9 +392,9 @@ template <int NW, bool G>
 DEVI void sw_fill(const SwShared& sh, int* P, const uint32_t* __restrict__ M, uint32_t* out, int H, int wpr, int ndw,
                   int maxr, const uint64_t (&vm)[NW]) {
     const int lane = threadIdx.x & 31;
-    const int nchunks = (H + SW_CHUNK - 1) / SW_CHUNK;
+    const int nchunks = (H + sh.chunk - 1) / sh.chunk;
     for (int c = sw_next_chunk(sh.next + 1, lane); c < nchunks; c = sw_next_chunk(sh.next + 1, lane)) {
-        const int ya = c * SW_CHUNK, yb = min(H, ya + SW_CHUNK);
+        const int ya = c * sh.chunk, yb = min(H, ya + sh.chunk);
         uint64_t cur[NW], nxt[NW];
 #pragma unroll
         for (int k = 0; k < NW; ++k) cur[k] = nxt[k] = 0ull;
@@ -420,9 +423,9 @@ DEVI void sw_fill(const SwShared& sh, int* P, const uint32_t* __restrict__ M, ui
 template <int NW, bool G>
 DEVI void sw_phase_b(const SwShared& sh, int* P, int* A, const uint32_t* out, int H, int wpr, int ndw, int maxr) {
     const int lane = threadIdx.x & 31;
-    const int nchunks = (H + SW_CHUNK - 1) / SW_CHUNK;
+    const int nchunks = (H + sh.chunk - 1) / sh.chunk;
     for (int c = sw_next_chunk(sh.next + 2, lane); c < nchunks; c = sw_next_chunk(sh.next + 2, lane)) {
-        const int ya = c * SW_CHUNK, yb = min(H, ya + SW_CHUNK);
+        const int ya = c * sh.chunk, yb = min(H, ya + sh.chunk);
         uint64_t cur[NW], nxt[NW], u[NW];
         RowMeta<NW> um;
         int ub = 0;
@@ -471,9 +474,9 @@ DEVI void sw_phase_b(const SwShared& sh, int* P, int* A, const uint32_t* out, in
 template <int NW, bool G>
 DEVI void sw_seams_b(const SwShared& sh, int* P, const uint32_t* out, int H, int wpr, int ndw, int maxr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunks = (H + SW_CHUNK - 1) / SW_CHUNK;
+    const int nchunks = (H + sh.chunk - 1) / sh.chunk;
     for (int c = 1 + warp; c < nchunks; c += SW_WARPS) {
-        const int yb = c * SW_CHUNK;
+        const int yb = c * sh.chunk;
         if (!(sh.rowst[yb - 1] & 1) || !(sh.rowst[yb] & 1)) continue;
         uint64_t u[NW], w[NW];
         RowMeta<NW> um, cm;
@@ -558,7 +561,7 @@ DEVI void sw_select(const SwShared& sh, int* P, int* A, uint32_t* out, int H, in
 template <int NW>
 __global__ void __launch_bounds__(SW_THREADS, 2)
 k_ccl_sweep(const uint32_t* __restrict__ planes, uint32_t* __restrict__ outp, int* __restrict__ gP, int* __restrict__ gA,
-            size_t g_stride, int H, int W, int wpr, int thr) {
+            size_t g_stride, int H, int W, int wpr, int thr, int chunk_rows) {
     extern __shared__ __align__(16) unsigned char sw_smem[];
     __shared__ int s_counter, s_overflow, s_next[SW_PHASES];
     SwShared sh;
@@ -570,6 +573,7 @@ k_ccl_sweep(const uint32_t* __restrict__ planes, uint32_t* __restrict__ outp, in
     sh.counter = &s_counter;
     sh.overflow = &s_overflow;
     sh.next = s_next;
+    sh.chunk = chunk_rows;
 
     const int lane = threadIdx.x & 31;
     const int frame = blockIdx.x;
