@@ -1095,7 +1095,10 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         if (rc) return rc;
         const float alpha = (float)h->cfg.release_factor, beta = (float)(1.0 - h->cfg.release_factor);
         { ProfScope ps(h, DVC_PROF_EMA, 1, st);
-        if (h->aligned) k_ema<true><<<dim3(g16, S), 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
+        static const int ema_px = measure_env("DVC_EMA_PX", 8);
+        if (h->aligned && ema_px == 8)
+            k_ema<true, 8><<<dim3(cdiv((size_t)(W / 8) * H, 256), S), 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
+        else if (h->aligned) k_ema<true><<<dim3(g16, S), 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
         else k_ema<false><<<dim3(g16, S), 256, 0, st>>>(h->acc, bits_a, bits_b, bits_c, mask_out, T, H, W, wpr, alpha, beta);
         }
         CHECK_LAUNCH();

@@ -25,7 +25,7 @@
 
 namespace dvc {
 
-constexpr int SW_WARPS = 16;
+constexpr int SW_WARPS = 24;
 constexpr int SW_THREADS = SW_WARPS * 32;
 constexpr int SW_CAP = 8192;                       // nodes (row runs) per frame held in shared memory
 constexpr unsigned SW_FULL = 0xffffffffu;

@@ -204,11 +204,13 @@ k_gray_diff_vote(const uint8_t* __restrict__ frames, int T, int H, int W, const 
 // result = saturate(round-half-even(s)).  One thread owns 16 pixels, keeps their accumulator bytes in
 // registers over the whole batch.
 // ------------------------------------------------------------------------------------------------
-template <bool ALIGNED>
-__global__ void __launch_bounds__(256)
+template <bool ALIGNED, int PX = 16>                     // PX pixels per thread: 16, or 8 (twice the threads: the walk over the batch is
+__global__ void __launch_bounds__(256)                   // a chain of dependent table look-ups, more resident warps hide it better)
 k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t* __restrict__ over127,
       uint32_t* __restrict__ nonzero, uint8_t* __restrict__ acc_all, int T, int H, int W, int wpr, float alpha,
       float beta) {
+    static_assert(PX == 16 || PX == 8, "k_ema: 8 or 16 pixels per thread");
+    constexpr int NQ = PX / 4;
     __shared__ uint8_t s_lut[512];                           // [dilated bit][acc] -> acc'
     {
         const float on = __fmul_rn(255.0f, beta);
@@ -218,32 +220,37 @@ k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t*
         }
     }
     __syncthreads();
-    const int gpr = (W + 15) >> 4;
+    const int gpr = (W + PX - 1) / PX;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)gpr * H) return;
-    const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx << 4;
+    const int y = (int)(gid / gpr), gx = (int)(gid % gpr), x0 = gx * PX;
     const size_t plane_words = (size_t)H * wpr, plane_bytes = (size_t)H * W;
-    const int npx = min(16, W - x0);
+    const int npx = min(PX, W - x0);
     {   // blockIdx.y = stream of a lock-step group: one accumulator plane per stream, T planes of everything else
         const size_t s = blockIdx.y;
         acc += s * plane_bytes;
         dilated += s * T * plane_words; over127 += s * T * plane_words; nonzero += s * T * plane_words;
         if (acc_all) acc_all += s * T * plane_bytes;
     }
-    uint32_t a[4];
+    uint32_t a[NQ];
     uint8_t* arow = acc + (size_t)y * W;
-    if (ALIGNED) { uint4 t = *reinterpret_cast<const uint4*>(arow + x0); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
-    else { for (int i = 0; i < 4; ++i) a[i] = 0; for (int i = 0; i < npx; ++i) a[i >> 2] |= (uint32_t)arow[x0 + i] << ((i & 3) * 8); }
+    if (ALIGNED) {
+        if (PX == 16) { uint4 t = *reinterpret_cast<const uint4*>(arow + x0); a[0] = t.x; a[1] = t.y; a[NQ - 2] = t.z; a[NQ - 1] = t.w; }
+        else { uint2 t = *reinterpret_cast<const uint2*>(arow + x0); a[0] = t.x; a[1] = t.y; }
+    } else { for (int i = 0; i < NQ; ++i) a[i] = 0; for (int i = 0; i < npx; ++i) a[i >> 2] |= (uint32_t)arow[x0 + i] << ((i & 3) * 8); }
     // accumulator update as a table: acc' depends only on (acc, dilated bit), so the float expression of cv2.addWeighted
     // is evaluated once per CTA for the 2 x 256 cases (no int <-> float conversions, which run on the quarter-rate XU
     // pipe, in the per-frame loop)
     for (int t = 0; t < T; ++t) {
         const size_t woff = (size_t)t * plane_words + (size_t)y * wpr;
-        const uint32_t bits = reinterpret_cast<const uint16_t*>(dilated + woff)[gx];
-        uint32_t hi = 0, nz = 0;
-        if ((a[0] | a[1] | a[2] | a[3] | bits) != 0u) {
+        const uint32_t bits = PX == 16 ? (uint32_t)reinterpret_cast<const uint16_t*>(dilated + woff)[gx]
+                                       : (uint32_t)reinterpret_cast<const uint8_t*>(dilated + woff)[gx];
+        uint32_t hi = 0, nz = 0, any = bits;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NQ; ++q) any |= a[q];
+        if (any != 0u) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
                 uint32_t nw = 0;
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
@@ -255,18 +262,27 @@ k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t*
                 hi |= ((((nw >> 7) & 0x01010101u) * 0x00204081u >> 21) & 0xfu) << (4 * q);                                   // byte > 127
                 nz |= (((((nw | ((nw & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu) << (4 * q);  // byte != 0
             }
-            if (npx < 16) { const uint32_t m = (1u << npx) - 1u; hi &= m; nz &= m; }
+            if (npx < PX) { const uint32_t m = (1u << npx) - 1u; hi &= m; nz &= m; }
         }
-        reinterpret_cast<uint16_t*>(over127 + woff)[gx] = (uint16_t)hi;
-        reinterpret_cast<uint16_t*>(nonzero + woff)[gx] = (uint16_t)nz;
+        if (PX == 16) {
+            reinterpret_cast<uint16_t*>(over127 + woff)[gx] = (uint16_t)hi;
+            reinterpret_cast<uint16_t*>(nonzero + woff)[gx] = (uint16_t)nz;
+        } else {
+            reinterpret_cast<uint8_t*>(over127 + woff)[gx] = (uint8_t)hi;
+            reinterpret_cast<uint8_t*>(nonzero + woff)[gx] = (uint8_t)nz;
+        }
         if (acc_all) {
             uint8_t* o = acc_all + (size_t)t * plane_bytes + (size_t)y * W;
-            if (ALIGNED) *reinterpret_cast<uint4*>(o + x0) = make_uint4(a[0], a[1], a[2], a[3]);
-            else for (int i = 0; i < npx; ++i) o[x0 + i] = (uint8_t)(a[i >> 2] >> ((i & 3) * 8));
+            if (ALIGNED) {
+                if (PX == 16) *reinterpret_cast<uint4*>(o + x0) = make_uint4(a[0], a[1], a[NQ - 2], a[NQ - 1]);
+                else *reinterpret_cast<uint2*>(o + x0) = make_uint2(a[0], a[1]);
+            } else for (int i = 0; i < npx; ++i) o[x0 + i] = (uint8_t)(a[i >> 2] >> ((i & 3) * 8));
         }
     }
-    if (ALIGNED) *reinterpret_cast<uint4*>(arow + x0) = make_uint4(a[0], a[1], a[2], a[3]);
-    else for (int i = 0; i < npx; ++i) arow[x0 + i] = (uint8_t)(a[i >> 2] >> ((i & 3) * 8));
+    if (ALIGNED) {
+        if (PX == 16) *reinterpret_cast<uint4*>(arow + x0) = make_uint4(a[0], a[1], a[NQ - 2], a[NQ - 1]);
+        else *reinterpret_cast<uint2*>(arow + x0) = make_uint2(a[0], a[1]);
+    } else for (int i = 0; i < npx; ++i) arow[x0 + i] = (uint8_t)(a[i >> 2] >> ((i & 3) * 8));
 }
 
 // ------------------------------------------------------------------------------------------------
