@@ -92,24 +92,32 @@ DEVI void gray16_dp2a(const uint32_t (&w)[12], uint32_t (&g)[4]) {
     }
 }
 
-// per-byte |a - b| > thr  ->  4 mask bits (bit p = byte p).  thr < 128 uses a SWAR compare + multiply gather.
-DEVI uint32_t diff_gt_bits4(uint32_t a, uint32_t b, uint32_t thr) {
+// per-byte |a - b| > thr  ->  0x80 in that byte.  thr < 128 uses a SWAR compare.
+DEVI uint32_t diff_gt_msb4(uint32_t a, uint32_t b, uint32_t thr) {
     if (thr == 0u) {
         // the reference's default (motion_threshold 0.5 -> diff > 0): a byte differs iff its XOR is non-zero
         const uint32_t x = a ^ b;
-        const uint32_t m = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) >> 7;
-        return ((m * 0x00204081u) >> 21) & 0xfu;
+        return (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
     }
     const uint32_t d = __vabsdiffu4(a, b);
     if (thr < 128u) {
         const uint32_t k7 = (0x7fu - thr) * 0x01010101u;
-        const uint32_t m = ((((d & 0x7f7f7f7fu) + k7) | d) & 0x80808080u) >> 7;      // bit 8p set iff byte p > thr
-        return ((m * 0x00204081u) >> 21) & 0xfu;
+        return (((d & 0x7f7f7f7fu) + k7) | d) & 0x80808080u;                            // bit 8p+7 set iff byte p > thr
     }
-    uint32_t bits = 0;
+    uint32_t m = 0;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) bits |= (((d >> (8 * p)) & 0xffu) > thr ? 1u : 0u) << p;
-    return bits;
+    for (int p = 0; p < 4; ++p) m |= (((d >> (8 * p)) & 0xffu) > thr ? 0x80u : 0u) << (8 * p);
+    return m;
+}
+// the flag bytes of 8 pixels (two words of diff_gt_msb4) gathered by two dot products: 128 * (bit p = pixel p)
+DEVI uint32_t gather8_x128(uint32_t m0, uint32_t m1) { return __dp4a(m1, 0x80402010u, __dp4a(m0, 0x08040201u, 0u)); }
+// per-byte |a - b| > thr  ->  4 mask bits (bit p = byte p)
+DEVI uint32_t diff_gt_bits4(uint32_t a, uint32_t b, uint32_t thr) { return __dp4a(diff_gt_msb4(a, b, thr), 0x08040201u, 0u) >> 7; }
+// 16 pixels -> 16 mask bits
+DEVI uint32_t diff_gt_bits16(const uint32_t (&a)[4], const uint32_t (&b)[4], uint32_t thr) {
+    const uint32_t lo = gather8_x128(diff_gt_msb4(a[0], b[0], thr), diff_gt_msb4(a[1], b[1], thr));
+    const uint32_t hi = gather8_x128(diff_gt_msb4(a[2], b[2], thr), diff_gt_msb4(a[3], b[3], thr));
+    return (lo >> 7) | (hi << 1);
 }
 
 DEVI void load16(const uint8_t* p, uint32_t (&v)[4]) {

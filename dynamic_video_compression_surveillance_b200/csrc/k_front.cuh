@@ -87,9 +87,7 @@ k_gray_diff_thresh(const uint8_t* __restrict__ frames, int T, int H, int W,
         } else load_bgr16_generic(fr, x0, W, w);
         uint32_t g[4];
         if (GRAY == 2) gray16_dp2a(w, g); else if (GRAY == 1) gray16_dp4a(w, g); else gray16(w, g);
-        uint32_t bits = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) bits |= diff_gt_bits4(g[q], pg[q], thr) << (4 * q);
+        uint32_t bits = diff_gt_bits16(g, pg, thr);
         bits &= vmask;
         const int slot = (int)((f0 + t) % ring_cap);
         reinterpret_cast<uint16_t*>(ring + (size_t)slot * plane_words + (size_t)y * wpr)[gx] = (uint16_t)bits;
@@ -259,9 +257,7 @@ k_diff_thresh_planes(const uint8_t* __restrict__ planes, const uint8_t* __restri
     uint32_t a[4], b[4];
     if (ALIGNED) { load16(cur + x0, a); load16(prv + x0, b); }
     else { load_u8x16_generic(cur, x0, W, a); load_u8x16_generic(prv, x0, W, b); }
-    uint32_t bits = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) bits |= diff_gt_bits4(a[q], b[q], thr) << (4 * q);
+    uint32_t bits = diff_gt_bits16(a, b, thr);
     if (W - x0 < 16) bits &= (1u << (W - x0)) - 1u;
     reinterpret_cast<uint16_t*>(bits_out + (size_t)t * H * wpr + (size_t)y * wpr)[gx] = (uint16_t)bits;
 }
@@ -322,6 +318,7 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
             else h_src[i] = (reflect101(y0 - 2 + r, H) * W + xx) * 3;
         }
     }
+    const bool edge_tile = x0 < 2 || x0 + tw + 2 > W;                 // some halo column reflects into the tile (CTA-uniform)
     // vertical / output: thread = 8 px x 4 rows
     const int cgp = tid & 15, rg = tid >> 4;
     const int ox = x0 + cgp * 8, oy = y0 + rg * 4;
@@ -367,18 +364,31 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
                 *reinterpret_cast<uint4*>(&sg[g_dst[i]]) = make_uint4(gg[0], gg[1], gg[2], gg[3]);
             }
         }
-        __syncthreads();
-        // phase 1b: halo columns
+        // phase 1b: halo columns that come from the frame (the neighbouring tiles' pixels).  Widths that are a multiple of 16: same
+        // phase as the interior, so that their loads are in flight together with the interior's.  Other widths: a clipped tile's
+        // right halo columns lie inside its last 16-pixel interior group, so they are written after the interior (phase 1c).
+        if (ALIGNED) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            if (h_src[i] != -2) {
-                uint8_t v;
-                if (h_src[i] < -2) v = sg[-(h_src[i] + 16)];
-                else { const uint8_t* p = fr + h_src[i]; v = (uint8_t)gray_of(p[0], p[1], p[2]); }
-                sg[h_dst[i]] = v;
+            for (int i = 0; i < 2; ++i) {
+                if (h_src[i] >= 0) {
+                    const uint8_t* p = fr + h_src[i];
+                    sg[h_dst[i]] = (uint8_t)gray_of(p[0], p[1], p[2]);
+                }
             }
         }
         __syncthreads();
+        // phase 1c: halo columns reflected at the image border are copies of tile pixels (tiles at the left / right edge only)
+        if (!ALIGNED || edge_tile) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (h_src[i] < -2) sg[h_dst[i]] = sg[-(h_src[i] + 16)];
+                else if (!ALIGNED && h_src[i] >= 0) {
+                    const uint8_t* p = fr + h_src[i];
+                    sg[h_dst[i]] = (uint8_t)gray_of(p[0], p[1], p[2]);
+                }
+            }
+            __syncthreads();
+        }
         // phase 2: horizontal 5 taps on 16-bit lanes, 16 px (four gray words) per task, same 544-task table as phase 1a.  Every
         // word is widened once into even / odd pixel lanes (E = px0 | px2 << 16, O = px1 | px3 << 16); the shifted operands
         // of the taps are funnel shifts of neighbouring E / O words: even outputs E(-1) + E(+1) + 4 (O(-1) + O) + 6 E, odd
@@ -412,7 +422,7 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
         {
             const uint4* col = reinterpret_cast<const uint4*>(sh) + (rg * 4) * (FF_TW / 8) + cgp;
             uint4 w0 = col[0], w1 = col[FF_TW / 8], w2 = col[2 * (FF_TW / 8)], w3 = col[3 * (FF_TW / 8)];
-            uint32_t rows_bits = 0;                                   // byte i = the 8 mask bits of row i
+            uint32_t rv[4] = {0u, 0u, 0u, 0u};                        // 128 * (the 8 mask bits of row i)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint4 w4 = col[(4 + i) * (FF_TW / 8)];
@@ -420,12 +430,13 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
                 const uint32_t vo0 = (w0.y + w4.y) + 4u * (w1.y + w3.y) + 6u * w2.y + 0x00800080u;
                 const uint32_t ve1 = (w0.z + w4.z) + 4u * (w1.z + w3.z) + 6u * w2.z + 0x00800080u;
                 const uint32_t vo1 = (w0.w + w4.w) + 4u * (w1.w + w3.w) + 6u * w2.w + 0x00800080u;
-                const uint32_t o0 = ((ve0 >> 8) & 0x00ff00ffu) | (vo0 & 0xff00ff00u);
-                const uint32_t o1 = ((ve1 >> 8) & 0x00ff00ffu) | (vo1 & 0xff00ff00u);
-                if (emit) rows_bits |= (diff_gt_bits4(o0, pv[i][0], thr) | (diff_gt_bits4(o1, pv[i][1], thr) << 4)) << (8 * i);
+                // every 16-bit lane is < 2^16 (16 * 4080 + 128): the blurred pixel is the lane's high byte
+                const uint32_t o0 = __byte_perm(ve0, vo0, 0x7351u), o1 = __byte_perm(ve1, vo1, 0x7351u);
+                if (emit) rv[i] = gather8_x128(diff_gt_msb4(o0, pv[i][0], thr), diff_gt_msb4(o1, pv[i][1], thr));
                 pv[i][0] = o0; pv[i][1] = o1;
                 w0 = w1; w1 = w2; w2 = w3; w3 = w4;
             }
+            const uint32_t rows_bits = (rv[0] >> 7) | (rv[1] << 1) | (rv[2] << 9) | (rv[3] << 17);      // byte i = the mask bits of row i
             if (emit) {
                 // 4 x 4 byte transpose over lanes 4k..4k+3: lane q ends with the 32-bit plane word of row q
                 const uint32_t p1 = __shfl_xor_sync(0xffffffffu, rows_bits, 1);

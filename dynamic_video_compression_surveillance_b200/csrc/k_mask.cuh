@@ -169,18 +169,18 @@ k_gray_diff_vote(const uint8_t* __restrict__ frames, int T, int H, int W, const 
         for (int t = t0 - nin; t < t0; ++t) {
             uint32_t g[4];
             gray_of_frame(t, g);
-            uint32_t b = 0;
+            const uint32_t b = diff_gt_bits16(g, pg, thr);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { b |= diff_gt_bits4(g[q], pg[q], thr) << (4 * q); pg[q] = g[q]; }
+            for (int q = 0; q < 4; ++q) pg[q] = g[q];
             push(b); add(b);
         }
     }
     for (int t = t0; t < t1; ++t) {
         uint32_t g[4];
         gray_of_frame(t, g);
-        uint32_t b = 0;
+        const uint32_t b = diff_gt_bits16(g, pg, thr);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { b |= diff_gt_bits4(g[q], pg[q], thr) << (4 * q); pg[q] = g[q]; }
+        for (int q = 0; q < 4; ++q) pg[q] = g[q];
         if (nin == K) sub((hst[(K - 1) >> 1] >> (((K - 1) & 1) * 16)) & 0xffffu);      // the piece pushed K frames ago leaves
         else ++nin;
         add(b);
