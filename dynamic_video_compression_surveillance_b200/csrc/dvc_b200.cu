@@ -636,8 +636,8 @@ struct dvc_handle {
     // two-stream software pipeline: mask kernels of batch c+1 overlap the degrade kernel of batch c
     bool overlap;                 // dvc_set_overlap: applies to dvc_process_batch (dvc_process_host always pipelines)
     int pp;                       // scratch set / event parity of the next batch
-    cudaStream_t s_mask, s_k4;
-    cudaEvent_t ev_in, ev_mask[2], ev_k4[2];
+    cudaStream_t s_front, s_mask, s_k4;      // pipelined mode: front kernel | mask kernels | degrade kernel, each a batch apart
+    cudaEvent_t ev_in, ev_front[2], ev_mask[2], ev_k4[2];
     bool ev_used[2];
     cudaEvent_t ev_user;          // end of the last batch issued on a caller's stream (strict-order mode)
     bool ev_user_used;
@@ -690,6 +690,7 @@ static int alloc_staging(dvc_handle* h) {
 static cudaError_t handle_join(dvc_handle* h) {
     cudaError_t e;
     if (h->ev_user_used && (e = cudaEventSynchronize(h->ev_user)) != cudaSuccess) return e;
+    if (h->s_front && (e = cudaStreamSynchronize(h->s_front)) != cudaSuccess) return e;
     if (h->s_mask && (e = cudaStreamSynchronize(h->s_mask)) != cudaSuccess) return e;
     if (h->s_k4 && (e = cudaStreamSynchronize(h->s_k4)) != cudaSuccess) return e;
     if (h->staging) {
@@ -769,11 +770,13 @@ static int create_impl(const dvc_config* cfg, dvc_handle* h) {
             CU(cudaMalloc(&h->bits[s][k], h->plane_words * 4 * T));
             CU(cudaMemset(h->bits[s][k], 0, h->plane_words * 4 * T));
         }
+    CU(cudaStreamCreateWithFlags(&h->s_front, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->s_mask, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->s_k4, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
     for (int s = 0; s < 2; ++s) {
+        CU(cudaEventCreateWithFlags(&h->ev_front[s], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_mask[s], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_k4[s], cudaEventDisableTiming));
     }
@@ -812,11 +815,12 @@ extern "C" int dvc_destroy(dvc_handle* h) {
     cudaFree(h->prev_gray[0]); cudaFree(h->prev_gray[1]); cudaFree(h->acc); cudaFree(h->ring);
     for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(h->bits[s][k]);
     cudaFree(h->blurred); cudaFree(h->counters_dev); cudaFree(h->resize_tables);
+    if (h->s_front) cudaStreamDestroy(h->s_front);
     if (h->s_mask) cudaStreamDestroy(h->s_mask);
     if (h->s_k4) cudaStreamDestroy(h->s_k4);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_user) cudaEventDestroy(h->ev_user);
-    for (int s = 0; s < 2; ++s) { if (h->ev_mask[s]) cudaEventDestroy(h->ev_mask[s]); if (h->ev_k4[s]) cudaEventDestroy(h->ev_k4[s]); }
+    for (int s = 0; s < 2; ++s) { if (h->ev_front[s]) cudaEventDestroy(h->ev_front[s]); if (h->ev_mask[s]) cudaEventDestroy(h->ev_mask[s]); if (h->ev_k4[s]) cudaEventDestroy(h->ev_k4[s]); }
     ccl_scratch_free(h->ccl);
     if (h->staging) {
         for (int b = 0; b < 2; ++b) {
@@ -1006,8 +1010,12 @@ extern "C" int64_t dvc_launch_count(const dvc_handle* h) { return h ? h->launche
 // ------------------------------------------------------------------------------------------------
 // Mask kernels run on `st`, the degrade kernel on `st_k4` (the same stream, or a second one so that it overlaps
 // the mask kernels of the next batch); `set` selects the scratch bit-planes.
+// st_front / st / st_k4: streams of the front kernel, of the other mask kernels and of the degrade kernel.  In pipelined mode they
+// differ: the front kernel of batch n + 1 (issue- or HBM-bound, touches only the frames, its own state and scratch set (n + 1) % 2)
+// runs beside the contour filter / morphology / EMA of batch n (latency-bound, a few hundred CTAs), which run beside the degrade
+// kernel of batch n - 1.
 static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8_t* overlay, uint8_t* compressed,
-                              uint8_t* mask_out, cudaStream_t st, cudaStream_t st_k4, int set) {
+                              uint8_t* mask_out, cudaStream_t st_front, cudaStream_t st, cudaStream_t st_k4, int set) {
     char* ERRBUF = h->err;
     uint32_t* const bits_a = h->bits[set][0];
     uint32_t* const bits_b = h->bits[set][1];
@@ -1027,14 +1035,17 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
             // K1 + K2 in one kernel (k_gray_diff_vote): long segments, each rebuilding its K - 1 frames of history
             const int seg = std::max(K, std::max(8, measure_env("DVC_FUSE_SEG", 64))), nsegf = (T + seg - 1) / seg;
             dim3 gf(g16, nsegf, S);
-            ProfScope ps(h, DVC_PROF_FRONT, 1, st);
-#define DVC_VOTE_CASE(KK) case KK: k_gray_diff_vote<KK><<<gf, 256, 0, st>>>(frames, T, H, W, pg_in, pg_out, h->ring, wpr, h->ring_cap, h->n_masks, thr, seg, h->min_counts, bits_a); break;
+            {
+            ProfScope ps(h, DVC_PROF_FRONT, 1, st_front);
+#define DVC_VOTE_CASE(KK) case KK: k_gray_diff_vote<KK><<<gf, 256, 0, st_front>>>(frames, T, H, W, pg_in, pg_out, h->ring, wpr, h->ring_cap, h->n_masks, thr, seg, h->min_counts, bits_a); break;
             switch (K) {
                 DVC_VOTE_CASE(1) DVC_VOTE_CASE(2) DVC_VOTE_CASE(3) DVC_VOTE_CASE(4)
                 DVC_VOTE_CASE(5) DVC_VOTE_CASE(6) DVC_VOTE_CASE(7) DVC_VOTE_CASE(8)
             }
 #undef DVC_VOTE_CASE
+            }
             CHECK_LAUNCH();
+            if (st_front != st) { CU(cudaEventRecord(h->ev_front[set], st_front)); CU(cudaStreamWaitEvent(st, h->ev_front[set], 0)); }
             h->cur ^= 1;
         } else {
         const int nseg = (T + h->seg_len - 1) / h->seg_len;
@@ -1078,11 +1089,12 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         const int seg = std::min(32, std::max(4, (T + want_segs - 1) / want_segs));
         const int nseg = (T + seg - 1) / seg;
         dim3 gf(wpr / 4, (H + FF_TH - 1) / FF_TH, S * nseg);
-        { ProfScope ps(h, DVC_PROF_FRONT, 1, st);
-        if (h->aligned) k_fd_front<true><<<gf, 256, 0, st>>>(frames, T, H, W, h->prev_gray[h->cur], h->prev_gray[h->cur ^ 1], bits_a, wpr, thr, seg, nseg);
-        else k_fd_front<false><<<gf, 256, 0, st>>>(frames, T, H, W, h->prev_gray[h->cur], h->prev_gray[h->cur ^ 1], bits_a, wpr, thr, seg, nseg);
+        { ProfScope ps(h, DVC_PROF_FRONT, 1, st_front);
+        if (h->aligned) k_fd_front<true><<<gf, 256, 0, st_front>>>(frames, T, H, W, h->prev_gray[h->cur], h->prev_gray[h->cur ^ 1], bits_a, wpr, thr, seg, nseg);
+        else k_fd_front<false><<<gf, 256, 0, st_front>>>(frames, T, H, W, h->prev_gray[h->cur], h->prev_gray[h->cur ^ 1], bits_a, wpr, thr, seg, nseg);
         }
         CHECK_LAUNCH();
+        if (st_front != st) { CU(cudaEventRecord(h->ev_front[set], st_front)); CU(cudaStreamWaitEvent(st, h->ev_front[set], 0)); }
         h->cur ^= 1;
         int rc;
         { ProfScope ps(h, DVC_PROF_CCL, (h->ccl.sweep ? 1 : 7) * ((ST + h->ccl.frames - 1) / h->ccl.frames), st);
@@ -1126,6 +1138,15 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
     return DVC_OK;
 }
 
+// fd mode: the front kernel (issue-bound) gets its own stream and runs a batch ahead of the contour filter / EMA (latency-bound):
+// 129 k -> 143 k frames/s at 1080p.  Window mode: its front kernel is HBM-bound like the degrade kernel it would run beside
+// (201 k -> 194 k frames/s with its own stream), so it stays on the mask stream.
+static cudaStream_t front_stream_of(dvc_handle* h) {
+    static const int sel = measure_env("DVC_FRONT_STREAM", -1);       // -1: by mode, 0: never, 1: always
+    const bool own = sel < 0 ? h->cfg.mode == DVC_MODE_FD : sel != 0;
+    return own ? h->s_front : h->s_mask;
+}
+
 extern "C" int dvc_process_batch(dvc_handle* h, const uint8_t* frames_dev, int32_t n_frames, uint8_t* overlay_dev,
                                  uint8_t* compressed_dev, uint8_t* mask_dev, void* stream) {
     char* ERRBUF = h ? h->err : nullptr;
@@ -1136,17 +1157,22 @@ extern "C" int dvc_process_batch(dvc_handle* h, const uint8_t* frames_dev, int32
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     if (!h->overlap) {
-        int rc = process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, st, st, 0);
+        int rc = process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, st, st, st, 0);
         if (rc == DVC_OK) { CU(cudaEventRecord(h->ev_user, st)); h->ev_user_used = true; }
         return rc;
     }
     // pipelined: the batch is ordered after the work already in `stream`, but `stream` is only re-joined by dvc_flush
     const int set = h->pp;
     h->pp ^= 1;
+    cudaStream_t sf = front_stream_of(h);
     CU(cudaEventRecord(h->ev_in, st));
     CU(cudaStreamWaitEvent(h->s_mask, h->ev_in, 0));
     if (h->ev_used[set]) CU(cudaStreamWaitEvent(h->s_mask, h->ev_k4[set], 0));      // scratch set free again
-    return process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, h->s_mask, h->s_k4, set);
+    if (sf != h->s_mask) {
+        CU(cudaStreamWaitEvent(sf, h->ev_in, 0));
+        if (h->ev_used[set]) CU(cudaStreamWaitEvent(sf, h->ev_k4[set], 0));
+    }
+    return process_batch_impl(h, frames_dev, n_frames, overlay_dev, compressed_dev, mask_dev, sf, h->s_mask, h->s_k4, set);
 }
 
 extern "C" int dvc_set_overlap(dvc_handle* h, int32_t on) {
@@ -1207,15 +1233,18 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
                                (size_t)T * h->frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
         CU(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
         CU(cudaStreamWaitEvent(h->s_mask, h->ev_h2d[b], 0));
+        cudaStream_t sf = front_stream_of(h);
+        if (sf != h->s_mask) CU(cudaStreamWaitEvent(sf, h->ev_h2d[b], 0));
         if (c >= 2) {
             CU(cudaStreamWaitEvent(h->s_mask, h->ev_k4[b], 0));      // scratch set b free
+            if (sf != h->s_mask) CU(cudaStreamWaitEvent(sf, h->ev_k4[b], 0));
             CU(cudaStreamWaitEvent(h->s_mask, h->ev_d2h[b], 0));     // output staging of chunk c-2 downloaded
             CU(cudaStreamWaitEvent(h->s_k4, h->ev_d2h[b], 0));
         }
         static const bool no_kernels = measure_env("DVC_HOST_NOKERNEL", 0) != 0;   // copy-pipeline probe
         if (no_kernels) { CU(cudaEventRecord(h->ev_k4[b], h->s_k4)); h->ev_used[b] = true; rc = DVC_OK; } else
         rc = process_batch_impl(h, h->st_in[b], T, overlay_host ? h->st_ov[b] : nullptr, compressed_host ? h->st_cp[b] : nullptr,
-                                mask_host ? h->st_mask[b] : nullptr, h->s_mask, h->s_k4, b);
+                                mask_host ? h->st_mask[b] : nullptr, sf, h->s_mask, h->s_k4, b);
         if (rc) { handle_join(h); return rc; }
         CU(cudaStreamWaitEvent(h->s_d2h, h->ev_k4[b], 0));
         for (int sidx = 0; sidx < S; ++sidx) {
@@ -1229,6 +1258,7 @@ extern "C" int dvc_process_host(dvc_handle* h, const uint8_t* frames_host, int64
     CU(cudaStreamSynchronize(h->s_d2h));
     CU(cudaStreamSynchronize(h->s_k4));
     CU(cudaStreamSynchronize(h->s_mask));
+    CU(cudaStreamSynchronize(h->s_front));
     h->ev_used[0] = h->ev_used[1] = false;
     h->pp = 0;
     return DVC_OK;
