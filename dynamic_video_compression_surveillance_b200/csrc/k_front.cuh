@@ -272,7 +272,11 @@ k_diff_thresh_planes(const uint8_t* __restrict__ planes, const uint8_t* __restri
 // grid (tiles_x, tiles_y, S * nseg): z = stream * nseg + segment; a segment that does not start the batch first blurs
 // the frame before it (1 / seg_len extra work) instead of waiting for its neighbour.
 // ------------------------------------------------------------------------------------------------
-constexpr int FF_TW = 128, FF_TH = 64, FF_PAD = 16, FF_GP = FF_TW + 2 * FF_PAD, FF_ROWS = FF_TH + 4;
+// 60 output rows + 4 halo rows = 64 staged rows: 64 x 8 groups of 16 px are exactly two rounds of the CTA's 256 threads for the gray
+// and the horizontal pass and 64 x 4 halo pixels exactly one (a 64-row tile needed three rounds, the third 1/8 full), and 1080 =
+// 18 x 60.  The vertical pass (8 px x 4 rows per thread) uses 240 of the 256 threads.
+constexpr int FF_TW = 128, FF_TH = 60, FF_PAD = 16, FF_GP = FF_TW + 2 * FF_PAD, FF_ROWS = FF_TH + 4;
+constexpr int FF_GR = (FF_ROWS * 8 + 255) / 256, FF_HR = (FF_ROWS * 4 + 255) / 256;      // rounds of gray / halo tasks
 
 template <bool ALIGNED>
 __global__ void __launch_bounds__(256, 5)
@@ -293,9 +297,9 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
 
     // ---- per-thread task tables (frame independent) ----
     // gray: 68 rows x 8 groups of 16 px = 544 tasks, three rounds
-    int g_src[3], g_dst[3];
+    int g_src[FF_GR], g_dst[FF_GR];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < FF_GR; ++i) {
         const int task = tid + 256 * i, r = task >> 3, g = task & 7, x = x0 + g * 16;
         g_src[i] = -1; g_dst[i] = 0;
         if (task < FF_ROWS * 8 && x < W) {
@@ -304,9 +308,9 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
         }
     }
     // halo columns: 68 rows x 4 = 272 tasks (left x0-2, x0-1; right: the two columns after the tile's last valid one)
-    int h_src[2], h_dst[2];
+    int h_src[FF_HR], h_dst[FF_HR];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FF_HR; ++i) {
         const int task = tid + 256 * i;
         h_src[i] = -2; h_dst[i] = 0;
         if (task < FF_ROWS * 4) {
@@ -323,10 +327,11 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
     const int cgp = tid & 15, rg = tid >> 4;
     const int ox = x0 + cgp * 8, oy = y0 + rg * 4;
     const int lane = tid & 31;
+    const bool vact = rg * 4 < FF_TH;                                 // the last 16 threads have no rows (they still take part in the shuffles)
     uint32_t pv[4][2];                                                // previous blurred values of this thread's pixels
 #pragma unroll
     for (int i = 0; i < 4; ++i) { pv[i][0] = pv[i][1] = 0u; }
-    if (t0 == 0) {
+    if (t0 == 0 && vact) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int y = oy + i;
@@ -347,7 +352,7 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
         const bool emit = t >= t0;
         // phase 1a: interior gray
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < FF_GR; ++i) {
             if (g_src[i] >= 0) {
                 uint32_t w[12], gg[4];
                 const uint8_t* row = fr + g_src[i];
@@ -369,7 +374,7 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
         // right halo columns lie inside its last 16-pixel interior group, so they are written after the interior (phase 1c).
         if (ALIGNED) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < FF_HR; ++i) {
                 if (h_src[i] >= 0) {
                     const uint8_t* p = fr + h_src[i];
                     sg[h_dst[i]] = (uint8_t)gray_of(p[0], p[1], p[2]);
@@ -380,7 +385,7 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
         // phase 1c: halo columns reflected at the image border are copies of tile pixels (tiles at the left / right edge only)
         if (!ALIGNED || edge_tile) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < FF_HR; ++i) {
                 if (h_src[i] < -2) sg[h_dst[i]] = sg[-(h_src[i] + 16)];
                 else if (!ALIGNED && h_src[i] >= 0) {
                     const uint8_t* p = fr + h_src[i];
@@ -394,7 +399,7 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
         // of the taps are funnel shifts of neighbouring E / O words: even outputs E(-1) + E(+1) + 4 (O(-1) + O) + 6 E, odd
         // outputs O(-1) + O(+1) + 4 (E + E(+1)) + 6 O, where (-1) / (+1) is the lane-shifted word pair.  h <= 4080 per lane.
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < FF_GR; ++i) {
             const int task = tid + 256 * i;
             if (task < FF_ROWS * 8) {
                 const int r = task >> 3, g = task & 7;
@@ -421,8 +426,9 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
         // phase 3: vertical 5 taps + rounding for 8 px x 4 rows, absdiff + threshold against the previous blurred values
         {
             const uint4* col = reinterpret_cast<const uint4*>(sh) + (rg * 4) * (FF_TW / 8) + cgp;
-            uint4 w0 = col[0], w1 = col[FF_TW / 8], w2 = col[2 * (FF_TW / 8)], w3 = col[3 * (FF_TW / 8)];
             uint32_t rv[4] = {0u, 0u, 0u, 0u};                        // 128 * (the 8 mask bits of row i)
+            if (vact) {
+            uint4 w0 = col[0], w1 = col[FF_TW / 8], w2 = col[2 * (FF_TW / 8)], w3 = col[3 * (FF_TW / 8)];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint4 w4 = col[(4 + i) * (FF_TW / 8)];
@@ -436,6 +442,7 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
                 pv[i][0] = o0; pv[i][1] = o1;
                 w0 = w1; w1 = w2; w2 = w3; w3 = w4;
             }
+            }
             const uint32_t rows_bits = (rv[0] >> 7) | (rv[1] << 1) | (rv[2] << 9) | (rv[3] << 17);      // byte i = the mask bits of row i
             if (emit) {
                 // 4 x 4 byte transpose over lanes 4k..4k+3: lane q ends with the 32-bit plane word of row q
@@ -444,13 +451,13 @@ k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_
                 const uint32_t p2 = __shfl_xor_sync(0xffffffffu, a1, 2);
                 const uint32_t word = (lane & 2) ? __byte_perm(a1, p2, 0x3276u) : __byte_perm(a1, p2, 0x5410u);
                 const int y = oy + (lane & 3);
-                if (y < H && wj < wpr) bits_out[(size_t)t * plane_words + (size_t)y * wpr + wj] = word & wvm;
+                if (vact && y < H && wj < wpr) bits_out[(size_t)t * plane_words + (size_t)y * wpr + wj] = word & wvm;
             }
         }
         // (the next frame's phase 1 writes sg, which nobody reads after the barrier above; its phase 2 writes sh only after
         //  two more barriers, by which time every thread has left phase 3)
     }
-    if (t1 == T && prev_gray_out) {
+    if (t1 == T && prev_gray_out && vact) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int y = oy + i;
