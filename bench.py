@@ -272,6 +272,9 @@ def workload_config(args, h, w):
     return {"workload": f"{cfg_name}: single {args.resolution} ({w}x{h}) synthetic stream per GPU, {args.frames} frames, "
                         f"{loop_name(args.mode)}", "mode": args.mode, "frames_per_step": args.frames, "max_batch": args.max_batch,
             "two_stream_overlap": not args.no_overlap,
+            "pipeline": ("strict stream order" if args.no_overlap else
+                         "batches pipelined over the handle's streams: mask kernels of batch n + 1 beside the degrade kernel of batch n"
+                         + ("; fd mode: the front kernel on a third stream, one more batch ahead" if args.mode == "fd" else "")),
             "l2_policy": f"inputs (clip {args.frames * h * w * 3 / 1e9:.1f} GB) and outputs ({2 * args.frames * h * w * 3 / 1e9:.1f} GB) per step "
                          "are far larger than the 126 MB L2"}
 
