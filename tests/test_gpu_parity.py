@@ -286,7 +286,7 @@ def _serpentine(h, w, r, gaps=1):
     return m
 
 
-@pytest.mark.parametrize("shape", [(40, 2100), (23, 4200), (9, 1999), (300, 700), (200, 300), (1, 1), (2, 130), (17, 64), (33, 65)])
+@pytest.mark.parametrize("shape", [(40, 2100), (23, 4200), (9, 1999), (300, 700), (200, 300), (1, 1), (2, 130), (17, 64), (33, 65), (3000, 70)])
 def test_contour_filter_sweep_cases(P, shape):
     """Shapes and masks aimed at the one-launch sweep kernel (k_ccl_sweep.cuh): rows of two and four 64-bit words per lane,
     fewer rows than warps, runs and holes across word boundaries, long flood paths, more row runs than fit in shared
