@@ -275,7 +275,9 @@ DEVI int sw_next_chunk(int* ctr, int lane) {
     return __shfl_sync(SW_FULL, c, 0);
 }
 // node ids of a row: a range from the shared counter, or the row's fixed range of the global arrays
-template <bool G>
+// Phase A has no use for the area and row arrays that follow P in shared memory: its parents may run over them.
+constexpr int SW_CAP_A = SW_CAP * 10 / 4;
+template <bool G, int CAP>
 DEVI int sw_alloc(const SwShared& sh, int y, int cnt, int maxr, int lane, bool& ok) {
     if (G) {
         if (lane == 0) sh.rowbase[y] = cnt;
@@ -284,7 +286,7 @@ DEVI int sw_alloc(const SwShared& sh, int y, int cnt, int maxr, int lane, bool& 
     int b = 0;
     if (lane == 0 && cnt) b = atomicAdd(sh.counter, cnt);
     b = __shfl_sync(SW_FULL, b, 0);
-    if (b + cnt > SW_CAP) {
+    if (b + cnt > CAP) {
         if (lane == 0) *sh.overflow = 1;
         ok = false;
     }
@@ -329,7 +331,7 @@ DEVI void sw_phase_a(const SwShared& sh, int* P, const uint32_t* __restrict__ M,
                 for (int k = 0; k < NW; ++k) b[k] = ~cur[k] & vm[k];
                 RowMeta<NW> cm;
                 const int cnt = sw_row_meta<NW>(b, lane, cm);
-                const int rb = sw_alloc<G>(sh, y, cnt, maxr, lane, ok);
+                const int rb = sw_alloc<G, SW_CAP_A>(sh, y, cnt, maxr, lane, ok);
                 if (ok) {
                     const bool all_out = y == 0 || y == H - 1 || (y > ya && !have_u);
 #pragma unroll
@@ -447,7 +449,7 @@ DEVI void sw_phase_b(const SwShared& sh, int* P, int* A, const uint32_t* out, in
             } else {
                 RowMeta<NW> cm;
                 const int cnt = sw_row_meta<NW>(cur, lane, cm);
-                const int rb = sw_alloc<G>(sh, y, cnt, maxr, lane, ok);
+                const int rb = sw_alloc<G, SW_CAP>(sh, y, cnt, maxr, lane, ok);
                 if (ok) {
 #pragma unroll
                     for (int k = 0; k < NW; ++k) {
