@@ -205,7 +205,7 @@ k_gray_diff_vote(const uint8_t* __restrict__ frames, int T, int H, int W, const 
 // registers over the whole batch.
 // ------------------------------------------------------------------------------------------------
 template <bool ALIGNED, int PX = 16>                     // PX pixels per thread: 16, or 8 (twice the threads: the walk over the batch is
-__global__ void __launch_bounds__(256)                   // a chain of dependent table look-ups, more resident warps hide it better)
+__global__ void __launch_bounds__(256, PX == 8 ? 4 : 1)   // a chain of dependent table look-ups, more resident warps hide it better)
 k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t* __restrict__ over127,
       uint32_t* __restrict__ nonzero, uint8_t* __restrict__ acc_all, int T, int H, int W, int wpr, float alpha,
       float beta) {
@@ -241,10 +241,12 @@ k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t*
     // accumulator update as a table: acc' depends only on (acc, dilated bit), so the float expression of cv2.addWeighted
     // is evaluated once per CTA for the 2 x 256 cases (no int <-> float conversions, which run on the quarter-rate XU
     // pipe, in the per-frame loop)
-    for (int t = 0; t < T; ++t) {
+    auto piece = [&](int t) -> uint32_t {
+        const size_t wo = (size_t)t * plane_words + (size_t)y * wpr;
+        return PX == 16 ? (uint32_t)reinterpret_cast<const uint16_t*>(dilated + wo)[gx] : (uint32_t)reinterpret_cast<const uint8_t*>(dilated + wo)[gx];
+    };
+    auto step = [&](int t, uint32_t bits) {
         const size_t woff = (size_t)t * plane_words + (size_t)y * wpr;
-        const uint32_t bits = PX == 16 ? (uint32_t)reinterpret_cast<const uint16_t*>(dilated + woff)[gx]
-                                       : (uint32_t)reinterpret_cast<const uint8_t*>(dilated + woff)[gx];
         uint32_t hi = 0, nz = 0, any = bits;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) any |= a[q];
@@ -278,7 +280,18 @@ k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t*
                 else *reinterpret_cast<uint2*>(o + x0) = make_uint2(a[0], a[1]);
             } else for (int i = 0; i < npx; ++i) o[x0 + i] = (uint8_t)(a[i >> 2] >> ((i & 3) * 8));
         }
+    };
+    // the walk over the frames is a chain of dependent look-ups; the mask pieces it consumes are not: PF of them are loaded ahead
+    constexpr int PF = 8;                                    // (4: no gain; 16, or 8 under a 48-register cap: slightly slower)
+    int t = 0;
+    for (; t + PF <= T; t += PF) {
+        uint32_t pf[PF];
+#pragma unroll
+        for (int j = 0; j < PF; ++j) pf[j] = piece(t + j);
+#pragma unroll
+        for (int j = 0; j < PF; ++j) step(t + j, pf[j]);
     }
+    for (; t < T; ++t) step(t, piece(t));
     if (ALIGNED) {
         if (PX == 16) *reinterpret_cast<uint4*>(arow + x0) = make_uint4(a[0], a[1], a[NQ - 2], a[NQ - 1]);
         else *reinterpret_cast<uint2*>(arow + x0) = make_uint2(a[0], a[1]);
