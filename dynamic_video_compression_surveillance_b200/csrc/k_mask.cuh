@@ -282,7 +282,7 @@ k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t*
         }
     };
     // the walk over the frames is a chain of dependent look-ups; the mask pieces it consumes are not: PF of them are loaded ahead
-    constexpr int PF = 8;                                    // (4: no gain; 16, or 8 under a 48-register cap: slightly slower)
+    constexpr int PF = PX == 8 ? 8 : 1;                      // (4: no gain; 16, or 8 under a 48-register cap: slightly slower)
     int t = 0;
     for (; t + PF <= T; t += PF) {
         uint32_t pf[PF];
