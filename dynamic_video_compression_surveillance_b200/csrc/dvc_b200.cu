@@ -119,6 +119,15 @@ static bool chain_push(MorphChain& ch, int op, int shape, int k) {
                 return true;
             }
         }
+        // Likewise MORPH_ELLIPSE (2, 2) twice (the E E in the middle of CLOSE, OPEN): one pass with the summed element (kind 3)
+        if (ch.n > 0 && shape == DVC_SHAPE_ELLIPSE && k == 2) {
+            MorphPrim& q = ch.p[ch.n - 1];
+            if (q.kind == 1 && (bool)q.erode == erode) {
+                q.kind = 3;
+                ch.halo_top += 1;           // the element reaches one more row up; nothing below the anchor
+                return true;
+            }
+        }
         if (ch.n >= MORPH_MAX_PRIMS) return false;
         MorphPrim& p = ch.p[ch.n];
         if (!make_prim(shape, k, erode, p)) return false;

@@ -309,7 +309,7 @@ struct MorphPrim {
     int8_t separable;                  // all rows share one run and rows are contiguous
     int8_t nrows;                      // rows of the structuring element that are non-empty
     int8_t small;                      // fits in 3x3 around the anchor: small_rows[] holds per-row flags
-    int16_t kind;                      // 0 = runtime paths; 1xx = rect_pass<xx>; 1, 2 = small_pass specialisations
+    int16_t kind;                      // 0 = runtime paths; 1xx = rect_pass<xx>; 1, 2 = small_pass specialisations; 3 = MORPH_ELLIPSE 2x2 twice
     int8_t small_rows[3];              // dy = -1, 0, +1: bit0 present, bit1 dx=-1 present, bit2 dx=+1 present
     int8_t dy[MORPH_MAX_K];            // row offset (kernel row - anchor)
     int8_t lo[MORPH_MAX_K];            // run of column offsets [lo, hi] in that row
@@ -483,6 +483,31 @@ DEVI void small_pass(const uint32_t* A, uint32_t* B, const BandCtx& c, uint32_t 
     __syncthreads();
 }
 
+// MORPH_ELLIPSE (2, 2) = {(0,0), (-1,0), (0,-1)} applied twice with the same polarity (the two erosions in the middle of CLOSE, OPEN:
+// the reference's mask clean-up, motion_compression_opt.py:89-90) is one pass with the Minkowski sum
+// {(0,0), (-1,0), (-2,0), (0,-1), (-1,-1), (0,-2)}: out[r] = t[r] | l2[r] | t[r-1] | m[r-2] with t = m | l1, lk = the row shifted by k
+// pixels.  Exact with cv2's ignored borders for the same reason as merged rectangles: all offsets point the same way, so the
+// intermediate pixel of a two-step path lies between its end points.  A -> B, rows stream through registers once.
+DEVI void ellipse2x2_pass(const uint32_t* A, uint32_t* B, const BandCtx& c, uint32_t flip) {
+    uint32_t t1 = 0, m1 = 0, m2 = 0;            // t[x-1], m[x-1], m[x-2]
+    const uint32_t* row = A + (c.ra - 2) * c.wpr;
+    uint32_t* out = B + (c.ra - 2) * c.wpr + c.j;
+    if (c.ra < c.rb)
+        for (int x = c.ra - 2; x < c.rb; ++x, row += c.wpr, out += c.wpr) {
+            uint32_t m = 0, l1 = 0, l2 = 0;
+            if (x >= c.r_lo && x < c.r_hi) {
+                m = (row[c.j] ^ flip) & c.vm;
+                const uint32_t p = (row[c.jp] ^ flip) & c.pm;
+                l1 = __funnelshift_l(p, m, 1);
+                l2 = __funnelshift_l(p, m, 2);
+            }
+            const uint32_t t = m | l1;
+            if (x >= c.ra) *out = ((t | l2 | t1 | m2) ^ flip) & c.vm;
+            m2 = m1; m1 = m; t1 = t;
+        }
+    __syncthreads();
+}
+
 // grid: (bands, n_images); dynamic smem: 2 planes of ext_rows x wpr words + one mbarrier.
 // Thread (g, j) owns word column j of a contiguous run of rows (row group g), so consecutive outputs of a
 // thread reuse the rows it has just read (3x3-bounded elements stream each input row through registers
@@ -576,6 +601,7 @@ k_morph_chain(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int 
                 case 133: rect_pass<33>(A, B, cx, flip); swap = false; break;
                 case 1: small_pass<1, 3, 0>(A, B, cx, flip); break;     // MORPH_ELLIPSE 2x2
                 case 2: small_pass<1, 7, 1>(A, B, cx, flip); break;     // MORPH_ELLIPSE 3x3 (a cross)
+                case 3: ellipse2x2_pass(A, B, cx, flip); break;         // MORPH_ELLIPSE 2x2, twice
                 default: break;
             }
             if (swap) { uint32_t* t = A; A = B; B = t; }
