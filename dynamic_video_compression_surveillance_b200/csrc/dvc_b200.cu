@@ -1095,8 +1095,10 @@ static int process_batch_impl(dvc_handle* h, const uint8_t* frames, int T, uint8
         // gray -> blur5 -> absdiff -> threshold fused and walking the frames of a segment: the blurred planes stay in registers
         const int tiles = (wpr / 4) * ((H + FF_TH - 1) / FF_TH);
         const int want_segs = std::max(1, (1500 + tiles * S - 1) / (tiles * S));          // enough CTAs for a few waves
-        const int seg = std::min(32, std::max(4, (T + want_segs - 1) / want_segs));
-        const int nseg = (T + seg - 1) / seg;
+        static const int seg_env = measure_env("DVC_FD_SEG", 0);                          // > 0: frames a CTA walks
+        const int seg0 = seg_env > 0 ? seg_env : std::min(32, std::max(4, (T + want_segs - 1) / want_segs));
+        const int nseg = (T + seg0 - 1) / seg0;
+        const int seg = (T + nseg - 1) / nseg;                                              // balanced: no short last segment
         dim3 gf(wpr / 4, (H + FF_TH - 1) / FF_TH, S * nseg);
         { ProfScope ps(h, DVC_PROF_FRONT, 1, st_front);
         if (h->aligned) k_fd_front<true><<<gf, 256, 0, st_front>>>(frames, T, H, W, h->prev_gray[h->cur], h->prev_gray[h->cur ^ 1], bits_a, wpr, thr, seg, nseg);
