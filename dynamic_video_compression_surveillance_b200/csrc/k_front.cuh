@@ -278,8 +278,13 @@ k_diff_thresh_planes(const uint8_t* __restrict__ planes, const uint8_t* __restri
 constexpr int FF_TW = 128, FF_TH = 60, FF_PAD = 16, FF_GP = FF_TW + 2 * FF_PAD, FF_ROWS = FF_TH + 4;
 constexpr int FF_GR = (FF_ROWS * 8 + 255) / 256, FF_HR = (FF_ROWS * 4 + 255) / 256;      // rounds of gray / halo tasks
 
+// 6 CTAs per SM = 40 registers (a few spills): alone the kernel is 1 % slower than with 48, beside the contour filter and the EMA of
+// the previous batch (three-stream pipeline) the smaller footprint is worth +0.7 % on the loop; 32 registers: 50 % slower
+#ifndef DVC_FF_MINB
+#define DVC_FF_MINB 6
+#endif
 template <bool ALIGNED>
-__global__ void __launch_bounds__(256, 5)
+__global__ void __launch_bounds__(256, DVC_FF_MINB)
 k_fd_front(const uint8_t* __restrict__ frames, int T, int H, int W, const uint8_t* __restrict__ prev_gray_in,
            uint8_t* __restrict__ prev_gray_out, uint32_t* __restrict__ bits_out, int wpr, uint32_t thr, int seg_len, int nseg) {
     __shared__ __align__(16) uint8_t sg[FF_ROWS * FF_GP];            // gray, column c <-> x = x0 - FF_PAD + c

@@ -767,7 +767,8 @@ def test_window_front_end_gray_variants_measure_build():
 
 
 def test_two_stream_overlap_matches_strict_order(P):
-    """dvc_set_overlap: mask kernels of batch c+1 overlap the degrade kernel of batch c; results must not change."""
+    """dvc_set_overlap: mask kernels of batch c+1 overlap the degrade kernel of batch c (fd mode: the front kernel on a third stream,
+    one more batch ahead); results must not change."""
     from dynamic_video_compression_surveillance_b200.synth import make_clip
     h, w, n = 120, 176, 70
     frames = make_clip((h, w), n, seed=9).frames()
