@@ -205,7 +205,10 @@ k_gray_diff_vote(const uint8_t* __restrict__ frames, int T, int H, int W, const 
 // registers over the whole batch.
 // ------------------------------------------------------------------------------------------------
 template <bool ALIGNED, int PX = 16>                     // PX pixels per thread: 16, or 8 (twice the threads: the walk over the batch is
-__global__ void __launch_bounds__(256, PX == 8 ? 4 : 1)   // a chain of dependent table look-ups, more resident warps hide it better)
+#ifndef DVC_EMA_MINB
+#define DVC_EMA_MINB 4
+#endif
+__global__ void __launch_bounds__(256, PX == 8 ? DVC_EMA_MINB : 1)   // a chain of dependent table look-ups, more resident warps hide it better)
 k_ema(uint8_t* __restrict__ acc, const uint32_t* __restrict__ dilated, uint32_t* __restrict__ over127,
       uint32_t* __restrict__ nonzero, uint8_t* __restrict__ acc_all, int T, int H, int W, int wpr, float alpha,
       float beta) {
